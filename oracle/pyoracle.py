@@ -1,0 +1,188 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+scavislam_b200/ never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_up = C.POINTER(C.c_ubyte)
+
+
+class OBAProblem(C.Structure):
+    _fields_ = [("P", C.c_int), ("L", C.c_int), ("E", C.c_int), ("C", C.c_int),
+                ("pose_qt", c_dp), ("fixed", c_up), ("psi", c_dp),
+                ("e_point", c_ip), ("e_pose", c_ip), ("e_anchor", c_ip),
+                ("e_obs", c_dp), ("e_info", c_dp),
+                ("c_i", c_ip), ("c_j", c_ip), ("c_T", c_dp), ("c_Lambda", c_dp),
+                ("f", C.c_double), ("px", C.c_double), ("py", C.c_double), ("b", C.c_double)]
+
+
+OBA_MAX_ITERS = 64
+
+
+class OBAStats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("trials_total", C.c_int),
+                ("chi2_init", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double),
+                ("chi2_iter", C.c_double * OBA_MAX_ITERS), ("lambda_iter", C.c_double * OBA_MAX_ITERS),
+                ("trials_iter", C.c_int * OBA_MAX_ITERS), ("nnzb_S", C.c_int), ("nnzb_L", C.c_int)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        for name, nd in (("oba_se3_exp", 2), ("oba_se3_log", 2), ("oba_se3_inv", 2), ("oba_se3_adj", 2),
+                         ("oba_invert_depth", 2), ("oba_se3_mul", 3), ("oba_se3_act", 3)):
+            getattr(L, name).argtypes = [c_dp] * nd
+            getattr(L, name).restype = None
+        L.oba_edge_error.argtypes = [c_dp] * 6
+        L.oba_edge_jacobians.argtypes = [c_dp] * 7
+        L.oba_posepose_error.argtypes = [c_dp] * 4
+        L.oba_posepose_jacobians.argtypes = [c_dp] * 4
+        L.oba_chi2.argtypes = [C.POINTER(OBAProblem), C.c_int, C.c_double]
+        L.oba_chi2.restype = C.c_double
+        L.oba_reduced_system.argtypes = [C.POINTER(OBAProblem), C.c_int, C.c_double, C.c_double, c_dp, c_dp]
+        L.oba_reduced_system.restype = C.c_double
+        L.oba_full_system.argtypes = [C.POINTER(OBAProblem), C.c_int, C.c_double, c_dp, c_dp]
+        L.oba_full_system.restype = C.c_double
+        L.oba_optimize.argtypes = [C.POINTER(OBAProblem), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                   c_dp, c_dp, C.POINTER(OBAStats)]
+        L.oba_optimize.restype = C.c_int
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def as_c_problem(pb):
+    """pb: scavislam_b200.synth.BAProblem-like (numpy arrays).  Returns (struct, keepalive)."""
+    keep = dict(
+        pose_qt=np.ascontiguousarray(pb.pose_qt, np.float64), fixed=np.ascontiguousarray(pb.fixed, np.uint8),
+        psi=np.ascontiguousarray(pb.psi, np.float64),
+        e_point=np.ascontiguousarray(pb.e_point, np.int32), e_pose=np.ascontiguousarray(pb.e_pose, np.int32),
+        e_anchor=np.ascontiguousarray(pb.e_anchor, np.int32),
+        e_obs=np.ascontiguousarray(pb.e_obs, np.float64), e_info=np.ascontiguousarray(pb.e_info, np.float64),
+        c_i=np.ascontiguousarray(pb.c_i, np.int32), c_j=np.ascontiguousarray(pb.c_j, np.int32),
+        c_T=np.ascontiguousarray(pb.c_T, np.float64), c_Lambda=np.ascontiguousarray(pb.c_Lambda, np.float64))
+    k = keep
+    s = OBAProblem(pb.P, pb.L, pb.E, pb.C, _dp(k["pose_qt"]), k["fixed"].ctypes.data_as(c_up), _dp(k["psi"]),
+                   _ip(k["e_point"]), _ip(k["e_pose"]), _ip(k["e_anchor"]), _dp(k["e_obs"]), _dp(k["e_info"]),
+                   _ip(k["c_i"]), _ip(k["c_j"]), _dp(k["c_T"]), _dp(k["c_Lambda"]),
+                   float(pb.cam[0]), float(pb.cam[1]), float(pb.cam[2]), float(pb.cam[3]))
+    return s, keep
+
+
+def f64(*shape):
+    return np.zeros(shape, np.float64)
+
+
+def se3_exp(d):
+    T = f64(7); lib().oba_se3_exp(_dp(np.ascontiguousarray(d, np.float64)), _dp(T)); return T
+
+
+def se3_log(T):
+    d = f64(6); lib().oba_se3_log(_dp(np.ascontiguousarray(T, np.float64)), _dp(d)); return d
+
+
+def se3_mul(A, B):
+    o = f64(7)
+    lib().oba_se3_mul(_dp(np.ascontiguousarray(A, np.float64)), _dp(np.ascontiguousarray(B, np.float64)), _dp(o))
+    return o
+
+
+def se3_inv(A):
+    o = f64(7); lib().oba_se3_inv(_dp(np.ascontiguousarray(A, np.float64)), _dp(o)); return o
+
+
+def se3_act(A, x):
+    o = f64(3)
+    lib().oba_se3_act(_dp(np.ascontiguousarray(A, np.float64)), _dp(np.ascontiguousarray(x, np.float64)), _dp(o))
+    return o
+
+
+def se3_adj(A):
+    o = f64(6, 6); lib().oba_se3_adj(_dp(np.ascontiguousarray(A, np.float64)), _dp(o)); return o
+
+
+def edge_error(cam, Tp, Ta, psi, obs):
+    a = [np.ascontiguousarray(x, np.float64) for x in (cam, Tp, Ta, psi, obs)]
+    e = f64(3); lib().oba_edge_error(*[_dp(x) for x in a], _dp(e)); return e
+
+
+def edge_jacobians(cam, Tp, Ta, psi):
+    a = [np.ascontiguousarray(x, np.float64) for x in (cam, Tp, Ta, psi)]
+    Jpsi, Jp, Ja = f64(3, 3), f64(3, 6), f64(3, 6)
+    lib().oba_edge_jacobians(*[_dp(x) for x in a], _dp(Jpsi), _dp(Jp), _dp(Ja))
+    return Jpsi, Jp, Ja
+
+
+def posepose_error(T21, T1, T2):
+    a = [np.ascontiguousarray(x, np.float64) for x in (T21, T1, T2)]
+    e = f64(6); lib().oba_posepose_error(*[_dp(x) for x in a], _dp(e)); return e
+
+
+def posepose_jacobians(T21, err):
+    a = [np.ascontiguousarray(x, np.float64) for x in (T21, err)]
+    Ji, Jj = f64(6, 6), f64(6, 6)
+    lib().oba_posepose_jacobians(*[_dp(x) for x in a], _dp(Ji), _dp(Jj)); return Ji, Jj
+
+
+def chi2(pb, robust=True, delta=1.0):
+    s, keep = as_c_problem(pb)
+    return lib().oba_chi2(C.byref(s), int(robust), float(delta))
+
+
+def reduced_system(pb, robust=True, delta=1.0, lam=50.0):
+    s, keep = as_c_problem(pb)
+    n = 6 * pb.P
+    S, bs = f64(n, n), f64(n)
+    chi = lib().oba_reduced_system(C.byref(s), int(robust), float(delta), float(lam), _dp(S), _dp(bs))
+    return S, bs, chi
+
+
+def full_system(pb, robust=True, delta=1.0):
+    s, keep = as_c_problem(pb)
+    n = 6 * pb.P + 3 * pb.L
+    H, b = f64(n, n), f64(n)
+    chi = lib().oba_full_system(C.byref(s), int(robust), float(delta), _dp(H), _dp(b))
+    return H, b, chi
+
+
+def optimize(pb, num_iters, robust=True, delta=1.0, lambda_init=50.0, max_trials=5):
+    s, keep = as_c_problem(pb)
+    poses, psi = f64(pb.P, 7), f64(pb.L, 3)
+    st = OBAStats()
+    it = lib().oba_optimize(C.byref(s), int(num_iters), int(robust), float(delta), float(lambda_init),
+                            int(max_trials), _dp(poses), _dp(psi), C.byref(st))
+    stats = dict(iterations=it, trials_total=st.trials_total, chi2_init=st.chi2_init, chi2_final=st.chi2_final,
+                 lambda_final=st.lambda_final, chi2_iter=list(st.chi2_iter[:max(it, 0)]),
+                 lambda_iter=list(st.lambda_iter[:max(it, 0)]), trials_iter=list(st.trials_iter[:max(it, 0)]),
+                 nnzb_S=st.nnzb_S, nnzb_L=st.nnzb_L)
+    return poses, psi, stats
