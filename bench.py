@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native ScaViSLAM BA hot path.
+
+Metric (BASELINE.json): Gauss-Newton/LM iterations per second on the 200-keyframe /
+20k-landmark synthetic double window (config C2), 10 iterations per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one svs_ba_optimize(num_iters=10) over the whole window, starting from the same
+initial state (svs_ba_reset_state, device-to-device).  `value` counts iterations with the
+problem already resident in HBM; `e2e` goes through svs_optimiseInnerAndOuterWindow with HOST
+buffers (H2D of the problem, symbolic analysis, all iterations, D2H of poses and points inside
+the timed region).  N > 1 (torchrun): every rank owns an independent window (config C4,
+replicas, no data-path collective), value = total iterations / max-over-ranks time.
+
+--impl reference times the CPU oracle (oracle/ba_oracle.c, the restatement of the reference's
+g2o path; the reference itself cannot be built here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_ITERS = 10
+WORKLOAD = "C2: 200-keyframe / 20k-landmark synthetic inner+outer window, 10 LM iterations per step"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def schur_kernel_bytes(st, pb):
+    """Algorithmic bytes of one fused linearise+Schur launch (BASELINE.md / SURVEY.md 8d):
+    reads 40 B/edge + 24 B/landmark + 56 B/pose, writes the Hpl spill 144 B/edge, 96 B/landmark
+    (Hll, b_l) and 288 B per block of the reduced system."""
+    return 184 * pb.E + 120 * pb.L + 288 * st["nnzb_S"] + 56 * pb.P
+
+
+def run_reference(args):
+    from oracle import pyoracle as po
+    from scavislam_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pb = synth.make_config("C2")
+    for _ in range(max(args.warmup, 1)):
+        po.optimize(pb, NUM_ITERS)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(args.steps):
+        _, _, st = po.optimize(pb, NUM_ITERS)
+        iters += st["iterations"]
+    dt = time.perf_counter() - t0
+    v = iters / dt
+    line = {
+        "impl": "reference", "metric": "GN iterations/sec on 200KF/20k-pt window", "value": v, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "P": pb.P, "L": pb.L, "E": pb.E, "C": pb.C, "iters_per_step": NUM_ITERS},
+        "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} steps x {NUM_ITERS} LM iterations of the full C2 window, "
+                                   "oracle/ba_oracle.c (single thread, as the reference's backend thread runs g2o)"},
+        "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    from scavislam_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # every rank: an independent window of the C2 shape (rank 0 = the C2 seed itself)
+    pb = synth.make_config("C2") if rank == 0 else synth.make_window(200, 20000, 1234 + 100 + rank, name=f"C4[{rank}]")
+    ba = capi.BundleAdjuster(device=local)
+    ba.set_problem(pb)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        ba.reset_state()
+        flush.zero_()                       # evict the window from L2 between steps (untimed)
+        torch.cuda.synchronize()
+        it, st = ba.optimize(NUM_ITERS)     # device time measured by CUDA events on the library stream
+        return it, st
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    ms = 0.0
+    iters = 0
+    launches = 0
+    agg = {"ms_build": 0.0, "ms_solve": 0.0, "ms_update": 0.0, "ms_control": 0.0}
+    trials = 0
+    st = None
+    for _ in range(args.steps):
+        it, st = step()
+        ms += st["ms_total"]
+        iters += it
+        launches += st["launches"]
+        trials += st["trials_total"]
+        for k in agg:
+            agg[k] += st[k]
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+
+    # end to end through the reference-facing call with host buffers
+    e2e_iters = 0
+    for _ in range(2):
+        ba.optimise_inner_and_outer_window(pb, NUM_ITERS)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        it, poses, psi, _ = ba.optimise_inner_and_outer_window(pb, NUM_ITERS)
+        e2e_iters += it
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(getattr(pb, k).nbytes for k in ("pose_qt", "fixed", "psi", "e_point", "e_pose", "e_anchor", "e_obs",
+                                               "e_info", "c_i", "c_j", "c_T", "c_Lambda"))
+    d2h = pb.pose_qt.nbytes + pb.psi.nbytes
+
+    # max over ranks / sums
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+    n = torch.tensor([iters, e2e_iters, launches], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    ms_max, e2e_max = float(t[0]), float(t[1])
+    tot_iters, tot_e2e, tot_launch = float(n[0]), float(n[1]), int(n[2])
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        kb = schur_kernel_bytes(st, pb)
+        k_ms = agg["ms_build"] / max(trials, 1)
+        achieved = kb / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k_build_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        # bounded CPU baseline sample on this box's host cores
+        from oracle import pyoracle as po
+        po.optimize(pb, NUM_ITERS)
+        c0 = time.perf_counter()
+        cit = 0
+        nrun = 0
+        while time.perf_counter() - c0 < 10.0 and nrun < 40:
+            _, _, so = po.optimize(pb, NUM_ITERS)
+            cit += so["iterations"]
+            nrun += 1
+        cdt = time.perf_counter() - c0
+        line = {
+            "metric": "GN iterations/sec on 200KF/20k-pt window", "value": tot_iters / (ms_max * 1e-3),
+            "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "P": pb.P, "L": pb.L, "E": pb.E, "C": pb.C,
+                       "iters_per_step": NUM_ITERS, "parallelism": f"replicas x{world} (independent windows)",
+                       "l2": "flushed between steps (256 MiB write, untimed); iterations inside a step reuse L2 "
+                             "as the real workload does",
+                       "timing": "sum of per-step CUDA-event times on the library stream, max over ranks",
+                       "wall_s_timed_region": wall},
+            "e2e": {"value": tot_e2e / e2e_max, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_max / args.steps},
+            "gpu_launches": tot_launch,
+            "roofline": {"bound": "hbm", "kernel": "k_build (fused linearise + Schur elimination)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kb,
+                         "avg_launch_ms": k_ms, "share_of_step": agg["ms_build"] / ms},
+            "kernel_ms_per_step": {k: v / args.steps for k, v in agg.items()},
+            "cpu_baseline": {"value": cit / cdt, "unit": "iterations/s", "cores": 1, "kind": "port",
+                             "sample": f"{nrun} runs x {NUM_ITERS} LM iterations of the full C2 window "
+                                       f"({cdt:.1f} s), oracle/ba_oracle.c single thread"},
+            "clocks": clocks,
+            "trials_per_step": trials / args.steps,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/*
+ * svs_b200.h -- C ABI of libsvsb200.so: B200-native (sm_100a) implementation of
+ * ScaViSLAM's double-window bundle-adjustment iteration and dense stereo
+ * front-end kernels.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Every entry point names the reference interface it replaces
+ * (paths relative to the ScaViSLAM tree, commit b29d070).
+ *
+ * Conventions
+ *   SE3      double[7] = qx qy qz qw tx ty tz   (Eigen coeffs order; T_me_from_world)
+ *   tangent  (upsilon, omega): translation first, left-multiplicative update
+ *            T <- exp(delta) * T          (anchored_points.cpp:53-58)
+ *   points   psi = (x/z, y/z, 1/z) in the anchor frame (maths_utils.h:66-69)
+ *   status   0 = ok, <0 = error (svs_last_error gives the text); never throws
+ *   threads  a handle may be used by one host thread at a time; distinct
+ *            handles are independent (own stream, own workspaces)
+ */
+#ifndef SVS_B200_H
+#define SVS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVS_OK 0
+#define SVS_ERR_INVALID (-1)      /* bad argument / index out of range */
+#define SVS_ERR_CUDA (-2)         /* CUDA runtime error (text in svs_last_error) */
+#define SVS_ERR_UNSUPPORTED (-3)  /* structurally valid input this build cannot take */
+#define SVS_ERR_STATE (-4)        /* call order (e.g. optimize before set_problem) */
+#define SVS_ERR_NOGPU (-5)        /* no CUDA device: there is NO CPU fallback */
+
+/* ------------------------------------------------------------------ BA */
+
+typedef struct svs_ba svs_ba;
+
+/* G2oCameraParameters (g2o_types/anchored_points.h:40-58) */
+typedef struct {
+  double f, px, py, b;
+} svs_cam;
+
+typedef struct {
+  int device;        /* CUDA device ordinal, -1 = current device */
+  int flags;         /* SVS_BA_* */
+  int reserved[6];
+} svs_ba_opts;
+
+#define SVS_BA_DEFAULT 0
+/* Skip the spurious J1'WJ1 prior g2o adds to the anchor pose for an observation
+ * made in the landmark's own anchor frame.  Off = reference behaviour. */
+#define SVS_BA_SKIP_SELF_ANCHOR_HESSIAN 1
+/* Keep the pose ordering of the caller instead of the fill-reducing one. */
+#define SVS_BA_NATURAL_ORDER 2
+
+#define SVS_BA_MAX_ITERS 64
+
+/* Mirrors g2o's per-iteration verbose line (slam_graph.cpp:1066) and
+ * SlamGraph::Statistics (slam_graph.hpp:366-386). */
+typedef struct {
+  int iterations;                       /* return value of g2o optimize() */
+  int trials_total;                     /* Levenberg trials (factorisations) */
+  double chi2_init;
+  double chi2_final;
+  double lambda_final;
+  double chi2_iter[SVS_BA_MAX_ITERS];   /* robust chi2 after outer iteration i */
+  double lambda_iter[SVS_BA_MAX_ITERS];
+  int trials_iter[SVS_BA_MAX_ITERS];
+  int num_frames, num_points;           /* Statistics::num_frames / num_points */
+  int num_point_edges, num_frame_edges; /* Statistics::num_point_edges / num_frame_edges */
+  int nnzb_S;                           /* lower blocks of the reduced system incl. diagonal */
+  int nnzb_L;                           /* blocks of its Cholesky factor */
+  int max_track;                        /* longest landmark track (slots incl. anchor) */
+  float ms_total;                       /* device time of the whole optimize() */
+  float ms_build;                       /* fused linearise + Schur kernel, summed over trials */
+  float ms_solve;                       /* reduced-system factor + solve + pose update */
+  float ms_update;                      /* back-substitution + point update + trial chi2 */
+  float ms_control;                     /* LM decision kernel */
+  int launches;                         /* kernels launched by this call */
+} svs_ba_stats;
+
+/* Replaces: constructing g2o::SparseOptimizer + BlockSolver_6_3 + LinearSolverCSparse +
+ * OptimizationAlgorithmLevenberg in SlamGraph::setupG2o (slam_graph.cpp:1063-1080). */
+int svs_ba_create(const svs_ba_opts *opts, svs_ba **out);
+void svs_ba_destroy(svs_ba *h);
+const char *svs_last_error(const svs_ba *h);
+
+/* Replaces SlamGraph::copyDataToG2o (slam_graph.cpp:985-1032) and the vertex/edge builders
+ * addPoseToG2o / addPointToG2o / addObsToG2o / addConstraintToG2o
+ * (slam_graph.cpp:907-920, slam_graph-impl.cpp:29-126).
+ *   T_qt[P][7], fixed[P] (may be NULL = none fixed), psi[L][3]
+ *   e_point/e_pose/e_anchor[E]: vertex 0/1/2 of each G2oEdgeProjectPSI2UVU as indices into the
+ *     arrays above; all edges of a point must share one anchor (Point::anchorframe_id);
+ *   e_obs[E][3] = (u, v, u_right); e_info_diag[E][3] = diagonal of Lambda
+ *   c_i/c_j[C]: vertex 0/1 of each G2oEdgeSE3; c_T_ji[C][7] = measurement T_2_from_1;
+ *   c_Lambda[C][36] row-major information.
+ * Host buffers; copied to the device before the call returns.  Also performs the symbolic
+ * analysis g2o does in BlockSolver::buildStructure + CSparse's symbolic phase. */
+int svs_ba_set_problem(svs_ba *h, int P, const double *T_qt, const unsigned char *fixed,
+                       int L, const double *psi,
+                       int E, const int *e_point, const int *e_pose, const int *e_anchor,
+                       const double *e_obs, const double *e_info_diag,
+                       int C, const int *c_i, const int *c_j, const double *c_T_ji,
+                       const double *c_Lambda, const svs_cam *cam);
+
+/* Replaces optimizer.initializeOptimization(); lm->setUserLambdaInit(lambda);
+ * optimizer.optimize(num_iters) (slam_graph.cpp:336-346) with RobustKernelHuber(delta) on the
+ * observation edges when `robust` (slam_graph-impl.cpp:86-90; the reference leaves delta = 1).
+ * All iterations run on the device.  Returns g2o's value: iterations performed, -1 if the
+ * problem is empty; <= -100 encodes an SVS_ERR_* as (-100 + err). */
+int svs_ba_optimize(svs_ba *h, int num_iters, int robust, double huber_delta,
+                    double lambda_init, int max_trials, svs_ba_stats *stats);
+
+/* Replaces SlamGraph::restoreDataFromG2o (slam_graph.cpp:1037-1058); psi is returned in
+ * inverse-depth form, xyz_anchor = invert_depth(psi). */
+int svs_ba_get_poses(svs_ba *h, double *T_qt);
+int svs_ba_get_points(svs_ba *h, double *psi);
+
+/* Restore the state uploaded by set_problem (device-to-device; for repeated measurement). */
+int svs_ba_reset_state(svs_ba *h);
+
+/* SlamGraph::optimize(const OptParams&) in one call from host buffers
+ * (north-star name; slam_graph.cpp:319-355): set_problem + optimize + get_*.
+ * T_qt and psi are updated in place. */
+int svs_optimiseInnerAndOuterWindow(svs_ba *h, int P, double *T_qt, const unsigned char *fixed,
+                                    int L, double *psi,
+                                    int E, const int *e_point, const int *e_pose, const int *e_anchor,
+                                    const double *e_obs, const double *e_info_diag,
+                                    int C, const int *c_i, const int *c_j, const double *c_T_ji,
+                                    const double *c_Lambda, const svs_cam *cam,
+                                    int num_iters, int robust, double huber_delta,
+                                    svs_ba_stats *stats);
+
+/* Inspection hooks used by the parity tests (device results copied to host buffers). */
+/* g2o SparseOptimizer::activeRobustChi2 at the current state. */
+int svs_ba_chi2(svs_ba *h, int robust, double huber_delta, double *chi2);
+/* Reduced camera system the fused kernel produces at the current state:
+ * S dense (6P x 6P row-major, symmetric, lambda included), bs (6P).  BlockSolver::solve
+ * Schur part (g2o) on the system of BlockSolver::buildSystem. */
+int svs_ba_reduced_system(svs_ba *h, int robust, double huber_delta, double lambda,
+                          double *S_dense, double *bs, double *chi2);
+/* Solve the reduced system once: x (6P) = S^-1 bs with the device block Cholesky
+ * (LinearSolverCSparse::solve, slam_graph.cpp:55-60).  Returns 1 if not positive definite. */
+int svs_ba_solve_reduced(svs_ba *h, int robust, double huber_delta, double lambda, double *x);
+
+/* Library/device info: writes "name;sm;SMs;..." into buf. */
+int svs_device_info(char *buf, int buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVS_B200_H */

@@ -1,0 +1,219 @@
+"""ctypes binding of libsvsb200.so (the C ABI declared in include/svs_b200.h).
+
+This is how the tests and bench.py reach the product: through the same C ABI a
+maintainer of the reference would bind from C++.  There is no
+CPU fallback here: if the library is missing or no CUDA device is present the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvsb200.so")
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_up = C.POINTER(C.c_ubyte)
+
+SVS_BA_MAX_ITERS = 64
+SVS_BA_SKIP_SELF_ANCHOR_HESSIAN = 1
+SVS_BA_NATURAL_ORDER = 2
+
+
+class SvsCam(C.Structure):
+    _fields_ = [("f", C.c_double), ("px", C.c_double), ("py", C.c_double), ("b", C.c_double)]
+
+
+class SvsBaOpts(C.Structure):
+    _fields_ = [("device", C.c_int), ("flags", C.c_int), ("reserved", C.c_int * 6)]
+
+
+class SvsBaStats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("trials_total", C.c_int),
+                ("chi2_init", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double),
+                ("chi2_iter", C.c_double * SVS_BA_MAX_ITERS), ("lambda_iter", C.c_double * SVS_BA_MAX_ITERS),
+                ("trials_iter", C.c_int * SVS_BA_MAX_ITERS),
+                ("num_frames", C.c_int), ("num_points", C.c_int),
+                ("num_point_edges", C.c_int), ("num_frame_edges", C.c_int),
+                ("nnzb_S", C.c_int), ("nnzb_L", C.c_int), ("max_track", C.c_int),
+                ("ms_total", C.c_float), ("ms_build", C.c_float), ("ms_solve", C.c_float),
+                ("ms_update", C.c_float), ("ms_control", C.c_float), ("launches", C.c_int)]
+
+    def as_dict(self):
+        n = max(self.iterations, 0)
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("chi2_iter", "lambda_iter", "trials_iter")}
+        d["chi2_iter"] = list(self.chi2_iter[:n])
+        d["lambda_iter"] = list(self.lambda_iter[:n])
+        d["trials_iter"] = list(self.trials_iter[:n])
+        return d
+
+
+EXPORTS = [
+    "svs_ba_create", "svs_ba_destroy", "svs_last_error", "svs_ba_set_problem", "svs_ba_optimize",
+    "svs_ba_get_poses", "svs_ba_get_points", "svs_ba_reset_state", "svs_optimiseInnerAndOuterWindow",
+    "svs_ba_chi2", "svs_ba_reduced_system", "svs_ba_solve_reduced", "svs_device_info",
+]
+
+
+def lib():
+    """Load libsvsb200.so; raises if it was not built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.svs_ba_create.argtypes = [C.POINTER(SvsBaOpts), C.POINTER(vp)]
+    L.svs_ba_destroy.argtypes = [vp]
+    L.svs_ba_destroy.restype = None
+    L.svs_last_error.argtypes = [vp]
+    L.svs_last_error.restype = C.c_char_p
+    prob = [C.c_int, c_dp, c_up, C.c_int, c_dp, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp,
+            C.c_int, c_ip, c_ip, c_dp, c_dp, C.POINTER(SvsCam)]
+    L.svs_ba_set_problem.argtypes = [vp] + prob
+    L.svs_ba_optimize.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(SvsBaStats)]
+    L.svs_ba_get_poses.argtypes = [vp, c_dp]
+    L.svs_ba_get_points.argtypes = [vp, c_dp]
+    L.svs_ba_reset_state.argtypes = [vp]
+    L.svs_optimiseInnerAndOuterWindow.argtypes = [vp] + prob + [C.c_int, C.c_int, C.c_double, C.POINTER(SvsBaStats)]
+    L.svs_ba_chi2.argtypes = [vp, C.c_int, C.c_double, c_dp]
+    L.svs_ba_reduced_system.argtypes = [vp, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+    L.svs_ba_solve_reduced.argtypes = [vp, C.c_int, C.c_double, C.c_double, c_dp]
+    L.svs_device_info.argtypes = [C.c_char_p, C.c_int]
+    _LIB = L
+    return L
+
+
+def device_info() -> str:
+    buf = C.create_string_buffer(256)
+    rc = lib().svs_device_info(buf, 256)
+    if rc != 0:
+        raise RuntimeError(f"svs_device_info: {buf.value.decode()} (rc={rc})")
+    return buf.value.decode()
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+class SvsError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(f"svs error {rc}: {msg}")
+        self.rc = rc
+
+
+class BundleAdjuster:
+    """Thin host-side mirror of SlamGraph::optimize (reference slam_graph.cpp:319-355)."""
+
+    def __init__(self, device: int = -1, flags: int = 0):
+        self._h = C.c_void_p()
+        o = SvsBaOpts(device, flags)
+        rc = lib().svs_ba_create(C.byref(o), C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_ba_create failed (no CUDA device? there is no CPU fallback)")
+        self._keep = None
+        self.P = self.L = 0
+
+    def close(self):
+        if self._h:
+            lib().svs_ba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SvsError(rc, lib().svs_last_error(self._h).decode())
+
+    @staticmethod
+    def _arrays(pb):
+        return dict(
+            pose_qt=np.ascontiguousarray(pb.pose_qt, np.float64), fixed=np.ascontiguousarray(pb.fixed, np.uint8),
+            psi=np.ascontiguousarray(pb.psi, np.float64),
+            e_point=np.ascontiguousarray(pb.e_point, np.int32), e_pose=np.ascontiguousarray(pb.e_pose, np.int32),
+            e_anchor=np.ascontiguousarray(pb.e_anchor, np.int32),
+            e_obs=np.ascontiguousarray(pb.e_obs, np.float64), e_info=np.ascontiguousarray(pb.e_info, np.float64),
+            c_i=np.ascontiguousarray(pb.c_i, np.int32), c_j=np.ascontiguousarray(pb.c_j, np.int32),
+            c_T=np.ascontiguousarray(pb.c_T, np.float64), c_Lambda=np.ascontiguousarray(pb.c_Lambda, np.float64))
+
+    @staticmethod
+    def _prob_args(pb, k):
+        cam = SvsCam(float(pb.cam[0]), float(pb.cam[1]), float(pb.cam[2]), float(pb.cam[3]))
+        return [pb.P, _dp(k["pose_qt"]), k["fixed"].ctypes.data_as(c_up), pb.L, _dp(k["psi"]),
+                pb.E, _ip(k["e_point"]), _ip(k["e_pose"]), _ip(k["e_anchor"]), _dp(k["e_obs"]), _dp(k["e_info"]),
+                pb.C, _ip(k["c_i"]), _ip(k["c_j"]), _dp(k["c_T"]), _dp(k["c_Lambda"]), C.byref(cam)], cam
+
+    def set_problem(self, pb):
+        k = self._arrays(pb)
+        args, cam = self._prob_args(pb, k)
+        self._check(lib().svs_ba_set_problem(self._h, *args))
+        self.P, self.L = pb.P, pb.L
+
+    def optimize(self, num_iters, robust=True, huber_delta=1.0, lambda_init=50.0, max_trials=5):
+        st = SvsBaStats()
+        it = lib().svs_ba_optimize(self._h, int(num_iters), int(robust), float(huber_delta), float(lambda_init),
+                                   int(max_trials), C.byref(st))
+        if it <= -100:
+            raise SvsError(it + 100, lib().svs_last_error(self._h).decode())
+        return it, st.as_dict()
+
+    def poses(self):
+        out = np.zeros((self.P, 7))
+        self._check(lib().svs_ba_get_poses(self._h, _dp(out)))
+        return out
+
+    def points(self):
+        out = np.zeros((self.L, 3))
+        self._check(lib().svs_ba_get_points(self._h, _dp(out)))
+        return out
+
+    def reset_state(self):
+        self._check(lib().svs_ba_reset_state(self._h))
+
+    def chi2(self, robust=True, huber_delta=1.0):
+        v = C.c_double()
+        self._check(lib().svs_ba_chi2(self._h, int(robust), float(huber_delta), C.byref(v)))
+        return v.value
+
+    def reduced_system(self, robust=True, huber_delta=1.0, lam=50.0):
+        n = 6 * self.P
+        S, bs = np.zeros((n, n)), np.zeros(n)
+        chi = C.c_double()
+        self._check(lib().svs_ba_reduced_system(self._h, int(robust), float(huber_delta), float(lam), _dp(S), _dp(bs),
+                                                C.byref(chi)))
+        return S, bs, chi.value
+
+    def solve_reduced(self, robust=True, huber_delta=1.0, lam=50.0):
+        x = np.zeros(6 * self.P)
+        rc = lib().svs_ba_solve_reduced(self._h, int(robust), float(huber_delta), float(lam), _dp(x))
+        if rc < 0:
+            self._check(rc)
+        return x, rc
+
+    def optimise_inner_and_outer_window(self, pb, num_iters, robust=True, huber_delta=1.0):
+        """SlamGraph::optimize in one call from host buffers; returns (iters, poses, psi, stats)."""
+        k = self._arrays(pb)
+        k["pose_qt"] = k["pose_qt"].copy()
+        k["psi"] = k["psi"].copy()
+        args, cam = self._prob_args(pb, k)
+        st = SvsBaStats()
+        it = lib().svs_optimiseInnerAndOuterWindow(self._h, *args, int(num_iters), int(robust), float(huber_delta),
+                                                   C.byref(st))
+        if it <= -100:
+            raise SvsError(it + 100, lib().svs_last_error(self._h).decode())
+        self.P, self.L = pb.P, pb.L
+        return it, k["pose_qt"], k["psi"], st.as_dict()

@@ -1,0 +1,613 @@
+// ba_host.cu -- host side of the BA path: problem regrouping, symbolic analysis of the reduced
+// camera system, the Levenberg-Marquardt driver and the C ABI (include/svs_b200.h).
+//
+// Mirrors SlamGraph::optimize (slam_graph.cpp:319-355): copyDataToG2o -> optimizer.optimize(n)
+// -> restoreDataFromG2o, with g2o's numerics replaced by the kernels in ba_kernels.cu.
+// There is no CPU fallback: every entry point fails with SVS_ERR_NOGPU / SVS_ERR_CUDA
+// when the device path is unavailable.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/svs_b200.h"
+#include "ba_kernels.cuh"
+
+using namespace svs;
+
+struct svs_ba {
+  int device = 0;
+  int flags = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool has_problem = false;
+  BaDev d{};
+  std::vector<void*> allocs;
+  LmCtl* h_ctl = nullptr;  // pinned
+  double* d_pose0 = nullptr;
+  double* d_psi0 = nullptr;
+  std::vector<int> lm_to_user;  // internal landmark -> caller's index
+  int Kmax = 1;
+  int nnzb_S = 0;
+  int C_edges = 0;
+  cudaEvent_t ev[8] = {};
+  // last optimize() settings
+};
+
+namespace {
+
+struct CudaErr {
+  cudaError_t e;
+  const char* what;
+};
+
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) {                                            \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+      return SVS_ERR_CUDA;                                              \
+    }                                                                   \
+  } while (0)
+
+template <typename T>
+int dev_alloc(svs_ba* h, T** p, size_t n) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return SVS_OK;
+}
+
+template <typename T>
+int dev_upload(svs_ba* h, const T** p, const std::vector<T>& v) {
+  T* q = nullptr;
+  int rc = dev_alloc(h, &q, v.size());
+  if (rc) return rc;
+  if (!v.empty()) CK(cudaMemcpyAsync(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  *p = q;
+  return SVS_OK;
+}
+
+void free_problem(svs_ba* h) {
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  h->has_problem = false;
+  h->d = BaDev{};
+}
+
+// Symbolic analysis of the reduced camera system: elimination order (greedy minimum degree on
+// the pose graph, the role AMD plays inside LinearSolverCSparse), block fill, and the update
+// lists of the right-looking block Cholesky.
+struct Symbolic {
+  std::vector<int> perm, pos, col_ptr, row_idx, upd_ptr, upd_dst, upd_ab, tbl;
+  int nblk = 0;
+};
+
+void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, Symbolic& sy) {
+  std::vector<std::set<int>> G(P);
+  for (int i = 0; i < P; ++i)
+    for (int j : adj_in[i])
+      if (j != i) G[i].insert(j);
+  sy.perm.assign(P, 0);
+  sy.pos.assign(P, 0);
+  std::vector<std::vector<int>> cols(P);  // by position: higher-position neighbours (as poses, fixed up later)
+  std::vector<char> done(P, 0);
+  // degree buckets via ordered set (degree, pose)
+  std::set<std::pair<int, int>> pq;
+  if (!natural)
+    for (int i = 0; i < P; ++i) pq.insert({(int)G[i].size(), i});
+  for (int step = 0; step < P; ++step) {
+    int v;
+    if (natural) {
+      v = step;
+    } else {
+      v = pq.begin()->second;
+      pq.erase(pq.begin());
+    }
+    done[v] = 1;
+    sy.perm[step] = v;
+    sy.pos[v] = step;
+    std::vector<int> nb(G[v].begin(), G[v].end());
+    cols[step] = nb;
+    for (int a : nb) {
+      if (!natural) pq.erase({(int)G[a].size(), a});
+      G[a].erase(v);
+    }
+    for (size_t x = 0; x < nb.size(); ++x)
+      for (size_t y = x + 1; y < nb.size(); ++y) {
+        G[nb[x]].insert(nb[y]);
+        G[nb[y]].insert(nb[x]);
+      }
+    if (!natural)
+      for (int a : nb) pq.insert({(int)G[a].size(), a});
+    G[v].clear();
+  }
+  // column structures by position
+  sy.col_ptr.assign(P + 1, 0);
+  sy.row_idx.clear();
+  for (int j = 0; j < P; ++j) {
+    std::vector<int> rows;
+    for (int a : cols[j]) rows.push_back(sy.pos[a]);
+    std::sort(rows.begin(), rows.end());
+    sy.col_ptr[j] = (int)sy.row_idx.size();
+    sy.row_idx.push_back(j);
+    for (int r : rows) sy.row_idx.push_back(r);
+  }
+  sy.col_ptr[P] = (int)sy.row_idx.size();
+  sy.nblk = (int)sy.row_idx.size();
+  // table (row pose, col pose) -> block<<1 | transpose.  Block (i,j), i >= j in position, stores rows <-> i.
+  sy.tbl.assign((size_t)P * P, -1);
+  for (int j = 0; j < P; ++j)
+    for (int b = sy.col_ptr[j]; b < sy.col_ptr[j + 1]; ++b) {
+      const int i = sy.row_idx[b];
+      const int pi = sy.perm[i], pj = sy.perm[j];
+      sy.tbl[(size_t)pi * P + pj] = b << 1;             // rows <-> pi: as stored
+      if (i != j) sy.tbl[(size_t)pj * P + pi] = (b << 1) | 1;  // rows <-> pj: transpose on write
+    }
+  // update lists
+  sy.upd_ptr.assign(P + 1, 0);
+  sy.upd_dst.clear();
+  sy.upd_ab.clear();
+  for (int j = 0; j < P; ++j) {
+    sy.upd_ptr[j] = (int)sy.upd_dst.size();
+    const int base = sy.col_ptr[j] + 1, nb = sy.col_ptr[j + 1] - base;
+    for (int a = 0; a < nb; ++a)
+      for (int b = 0; b <= a; ++b) {
+        const int ia = sy.row_idx[base + a], ib = sy.row_idx[base + b];  // ia >= ib
+        const int t = sy.tbl[(size_t)sy.perm[ia] * P + sy.perm[ib]];
+        sy.upd_dst.push_back(t >> 1);
+        sy.upd_ab.push_back((a << 16) | b);
+      }
+  }
+  sy.upd_ptr[P] = (int)sy.upd_dst.size();
+}
+
+int fail(svs_ba* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+}  // namespace
+
+extern "C" {
+
+int svs_device_info(char* buf, int buflen) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    snprintf(buf, buflen, "no CUDA device");
+    return SVS_ERR_NOGPU;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp pr;
+  cudaGetDeviceProperties(&pr, dev);
+  snprintf(buf, buflen, "%s;sm_%d%d;SMs=%d;smem_optin=%zu;l2=%d", pr.name, pr.major, pr.minor,
+           pr.multiProcessorCount, pr.sharedMemPerBlockOptin, pr.l2CacheSize);
+  return SVS_OK;
+}
+
+int svs_ba_create(const svs_ba_opts* opts, svs_ba** out) {
+  if (!out) return SVS_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SVS_ERR_NOGPU;
+  svs_ba* h = new svs_ba();
+  h->flags = opts ? opts->flags : 0;
+  int dev = opts ? opts->device : -1;
+  if (dev < 0) cudaGetDevice(&dev);
+  h->device = dev;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&h->h_ctl, sizeof(LmCtl)) != cudaSuccess) {
+    delete h;
+    return SVS_ERR_CUDA;
+  }
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  *out = h;
+  return SVS_OK;
+}
+
+void svs_ba_destroy(svs_ba* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_problem(h);
+  for (auto& e : h->ev) cudaEventDestroy(e);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* svs_last_error(const svs_ba* h) { return h ? h->err.c_str() : "null handle"; }
+
+int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char* fixed, int L, const double* psi,
+                       int E, const int* e_point, const int* e_pose, const int* e_anchor, const double* e_obs,
+                       const double* e_info, int C, const int* c_i, const int* c_j, const double* c_T,
+                       const double* c_Lambda, const svs_cam* cam) {
+  if (!h) return SVS_ERR_INVALID;
+  if (P < 0 || L < 0 || E < 0 || C < 0 || !cam) return fail(h, SVS_ERR_INVALID, "negative size or null camera");
+  if ((P && !T_qt) || (L && !psi) || (E && (!e_point || !e_pose || !e_anchor || !e_obs || !e_info)) ||
+      (C && (!c_i || !c_j || !c_T || !c_Lambda)))
+    return fail(h, SVS_ERR_INVALID, "null array");
+  for (int e = 0; e < E; ++e)
+    if (e_point[e] < 0 || e_point[e] >= L || e_pose[e] < 0 || e_pose[e] >= P || e_anchor[e] < 0 || e_anchor[e] >= P)
+      return fail(h, SVS_ERR_INVALID, "observation edge index out of range");
+  for (int c = 0; c < C; ++c)
+    if (c_i[c] < 0 || c_i[c] >= P || c_j[c] < 0 || c_j[c] >= P || c_i[c] == c_j[c])
+      return fail(h, SVS_ERR_INVALID, "pose-pose edge index out of range");
+  cudaSetDevice(h->device);
+  free_problem(h);
+
+  // ---- group edges per landmark
+  std::vector<int> eptr(L + 1, 0);
+  for (int e = 0; e < E; ++e) eptr[e_point[e] + 1]++;
+  for (int l = 0; l < L; ++l) eptr[l + 1] += eptr[l];
+  std::vector<int> eord(E), fillp(eptr.begin(), eptr.end() - 1);
+  for (int e = 0; e < E; ++e) eord[fillp[e_point[e]]++] = e;
+  struct Lm { int user, anchor, K, self; std::vector<int> poses; };
+  std::vector<Lm> lms(L);
+  int Kmax = 1;
+  for (int l = 0; l < L; ++l) {
+    Lm& m = lms[l];
+    m.user = l; m.anchor = -1; m.self = 0; m.K = 0;
+    const int b = eptr[l], en = eptr[l + 1];
+    if (b == en) continue;
+    m.anchor = e_anchor[eord[b]];
+    for (int k = b; k < en; ++k) {
+      const int e = eord[k];
+      if (e_anchor[e] != m.anchor)
+        return fail(h, SVS_ERR_UNSUPPORTED, "edges of one point name different anchor frames");
+      if (e_pose[e] == m.anchor) m.self++;
+      else m.poses.push_back(e_pose[e]);
+    }
+    std::sort(m.poses.begin(), m.poses.end());
+    if (m.self > 1 || std::adjacent_find(m.poses.begin(), m.poses.end()) != m.poses.end())
+      return fail(h, SVS_ERR_UNSUPPORTED, "a point is observed twice by the same frame");
+    m.K = 1 + (int)m.poses.size();
+    if (m.K > kMaxTrack) return fail(h, SVS_ERR_UNSUPPORTED, "landmark track longer than 31 frames + anchor");
+    Kmax = std::max(Kmax, m.K);
+  }
+  // internal landmark order: by (anchor, pose set) so that neighbours in a CTA hit the same blocks
+  std::vector<int> order(L);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const Lm &x = lms[a], &y = lms[b];
+    if (x.anchor != y.anchor) return x.anchor < y.anchor;
+    if (x.self != y.self) return x.self > y.self;
+    return x.poses < y.poses;
+  });
+  h->lm_to_user = order;
+  std::vector<int> lm_eptr(L + 1, 0), lm_sptr(L + 1, 0), lm_anchor(L, 0), ie_pose(E);
+  std::vector<unsigned char> lm_self(L, 0);
+  std::vector<double> ie_obs(3 * (size_t)E), ie_w(3 * (size_t)E), ipsi(3 * (size_t)L);
+  int ne = 0, ns = 0;
+  for (int li = 0; li < L; ++li) {
+    const Lm& m = lms[order[li]];
+    lm_eptr[li] = ne; lm_sptr[li] = ns;
+    for (int q = 0; q < 3; ++q) ipsi[3 * (size_t)li + q] = psi[3 * (size_t)m.user + q];
+    if (m.anchor < 0) continue;
+    lm_anchor[li] = m.anchor; lm_self[li] = (unsigned char)m.self;
+    // self edge first, then observers by ascending pose index
+    std::vector<int> es(eord.begin() + eptr[m.user], eord.begin() + eptr[m.user + 1]);
+    std::sort(es.begin(), es.end(), [&](int a, int b) {
+      const int ka = e_pose[a] == m.anchor ? -1 : e_pose[a], kb = e_pose[b] == m.anchor ? -1 : e_pose[b];
+      return ka < kb;
+    });
+    for (int e : es) {
+      ie_pose[ne] = e_pose[e];
+      for (int q = 0; q < 3; ++q) {
+        ie_obs[(size_t)q * E + ne] = e_obs[3 * (size_t)e + q];
+        ie_w[(size_t)q * E + ne] = e_info[3 * (size_t)e + q];
+      }
+      ++ne;
+    }
+    ns += m.K;
+  }
+  lm_eptr[L] = ne; lm_sptr[L] = ns;
+
+  // ---- pose graph of the reduced system
+  std::vector<std::vector<int>> adj(P);
+  {
+    std::vector<std::set<int>> A(P);
+    for (int l = 0; l < L; ++l) {
+      const Lm& m = lms[l];
+      if (m.anchor < 0) continue;
+      std::vector<int> ps = m.poses;
+      ps.push_back(m.anchor);
+      for (size_t x = 0; x < ps.size(); ++x)
+        for (size_t y = x + 1; y < ps.size(); ++y) { A[ps[x]].insert(ps[y]); A[ps[y]].insert(ps[x]); }
+    }
+    for (int c = 0; c < C; ++c) { A[c_i[c]].insert(c_j[c]); A[c_j[c]].insert(c_i[c]); }
+    int nnz = P;
+    for (int i = 0; i < P; ++i) { adj[i].assign(A[i].begin(), A[i].end()); nnz += (int)A[i].size(); }
+    h->nnzb_S = (nnz - P) / 2 + P;
+  }
+  Symbolic sy;
+  analyse(P, adj, (h->flags & SVS_BA_NATURAL_ORDER) != 0, sy);
+  if (sy.nblk >= (1 << 20)) return fail(h, SVS_ERR_UNSUPPORTED, "reduced system factor has more than 2^20 blocks");
+
+  // ---- upload
+  BaDev& d = h->d;
+  d.P = P; d.L = L; d.E = E; d.C = C; d.nslots = ns; d.nblk = sy.nblk; d.flags = h->flags;
+  d.f = cam->f; d.px = cam->px; d.py = cam->py; d.b = cam->b;
+  int rc;
+  std::vector<unsigned char> fx(P, 0);
+  if (fixed) fx.assign(fixed, fixed + P);
+#define UP(field, vec) if ((rc = dev_upload(h, &d.field, vec))) return rc
+  UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self);
+  UP(e_pose, ie_pose); UP(e_obs, ie_obs); UP(e_w, ie_w);
+  UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
+  UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab);
+  {
+    std::vector<int> ci(c_i, c_i + C), cj(c_j, c_j + C);
+    std::vector<double> cT(c_T, c_T + 7 * (size_t)C), cL(c_Lambda, c_Lambda + 36 * (size_t)C);
+    UP(c_i, ci); UP(c_j, cj); UP(c_T, cT); UP(c_Lam, cL);
+  }
+#undef UP
+#define AL(field, n) if ((rc = dev_alloc(h, &d.field, (size_t)(n)))) return rc
+  for (int b = 0; b < 2; ++b) { AL(pose[b], 7 * (size_t)P); AL(Rt[b], 12 * (size_t)P); AL(psi[b], 3 * (size_t)L); }
+  AL(W, 18 * (size_t)ns); AL(Dbl, 12 * (size_t)L); AL(chi_l, L); AL(chi_new_l, L); AL(scale_l, L);
+  AL(S, 36 * (size_t)sy.nblk); AL(bp, 6 * (size_t)P); AL(bc, 6 * (size_t)P); AL(x, 6 * (size_t)P);
+  AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
+  AL(ctl, 1);
+#undef AL
+  if ((rc = dev_alloc(h, &h->d_pose0, 7 * (size_t)P))) return rc;
+  if ((rc = dev_alloc(h, &h->d_psi0, 3 * (size_t)L))) return rc;
+  if (P) CK(cudaMemcpyAsync(h->d_pose0, T_qt, 7 * (size_t)P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (L) CK(cudaMemcpyAsync(h->d_psi0, ipsi.data(), 3 * (size_t)L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(d.chi_c, 0, std::max(C, 1) * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(d.chi_c_new, 0, std::max(C, 1) * sizeof(double), h->stream));
+  h->Kmax = Kmax;
+  h->C_edges = C;
+  h->has_problem = true;
+  CK(cudaStreamSynchronize(h->stream));   // host staging vectors die here
+  return svs_ba_reset_state(h);
+}
+
+int svs_ba_reset_state(svs_ba* h) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  BaDev& d = h->d;
+  CK(cudaMemcpyAsync(d.pose[0], h->d_pose0, 7 * (size_t)d.P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(d.psi[0], h->d_psi0, 3 * (size_t)d.L * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  LmCtl z{};
+  *h->h_ctl = z;
+  CK(cudaMemcpyAsync(d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
+  launch_prep(d, 0, h->stream);
+  CK(cudaGetLastError());
+  return SVS_OK;
+}
+
+static int clear_system(svs_ba* h) {
+  BaDev& d = h->d;
+  CK(cudaMemsetAsync(d.S, 0, 36 * (size_t)d.nblk * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(d.bp, 0, 6 * (size_t)std::max(d.P, 1) * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(d.bc, 0, 6 * (size_t)std::max(d.P, 1) * sizeof(double), h->stream));
+  return SVS_OK;
+}
+
+int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, double lambda_init, int max_trials,
+                    svs_ba_stats* st) {
+  if (!h) return -100 + SVS_ERR_INVALID;
+  if (!h->has_problem) { h->err = "no problem set"; return -100 + SVS_ERR_STATE; }
+  if (st) memset(st, 0, sizeof *st);
+  BaDev& d = h->d;
+  if (d.P == 0) return -1;   // g2o: "0 vertices to optimize"
+  cudaSetDevice(h->device);
+  int rc;
+#define CKO(call)                                                       \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) {                                            \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+      return -100 + SVS_ERR_CUDA;                                       \
+    }                                                                   \
+  } while (0)
+  // LM state is not carried across calls (slam_graph.cpp:338-342); the accepted
+  // state stays where the previous call (or set_problem) left it.
+  CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+  CKO(cudaStreamSynchronize(h->stream));
+  {
+    const int cur = h->h_ctl->cur;
+    LmCtl z{};
+    z.cur = cur; z.lambda = lambda_init; z.ni = 2; z.max_trials = max_trials;
+    *h->h_ctl = z;
+    CKO(cudaMemcpyAsync(d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
+  }
+  if ((rc = clear_system(h))) return -100 + rc;
+  float ms[4] = {0, 0, 0, 0};
+  int launches = 0;
+  CKO(cudaEventRecord(h->ev[0], h->stream));
+  int it = 0;
+  bool ok = true;
+  while (it < num_iters && ok) {
+    // one Levenberg trial: build (at the accepted state, current lambda) -> solve -> update -> decide
+    CKO(cudaEventRecord(h->ev[1], h->stream));
+    launch_build(d, 0, d.L, h->Kmax, robust, huber_delta, h->stream);
+    CKO(cudaEventRecord(h->ev[2], h->stream));
+    launch_solve(d, h->stream);
+    CKO(cudaEventRecord(h->ev[3], h->stream));
+    launch_update(d, robust, huber_delta, h->stream);
+    CKO(cudaEventRecord(h->ev[4], h->stream));
+    launch_decide(d, h->stream);
+    CKO(cudaEventRecord(h->ev[5], h->stream));
+    launches += 4;
+    CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+    CKO(cudaStreamSynchronize(h->stream));
+    CKO(cudaGetLastError());
+    for (int k = 0; k < 4; ++k) {
+      float t = 0;
+      cudaEventElapsedTime(&t, h->ev[1 + k], h->ev[2 + k]);
+      ms[k] += t;
+    }
+    it = h->h_ctl->iter;
+    if (!h->h_ctl->again && h->h_ctl->stop) ok = false;
+  }
+  CKO(cudaEventRecord(h->ev[6], h->stream));
+  CKO(cudaStreamSynchronize(h->stream));
+  if (st) {
+    const LmCtl& c = *h->h_ctl;
+    st->iterations = c.iter;
+    st->trials_total = c.trials_total;
+    st->chi2_init = c.chi_init;
+    st->chi2_final = c.chi_cur;
+    st->lambda_final = c.lambda;
+    for (int i = 0; i < c.iter && i < SVS_BA_MAX_ITERS; ++i) {
+      st->chi2_iter[i] = c.chi_iter[i];
+      st->lambda_iter[i] = c.lambda_iter[i];
+      st->trials_iter[i] = c.trials_iter[i];
+    }
+    st->num_frames = d.P; st->num_points = d.L; st->num_point_edges = d.E; st->num_frame_edges = d.C;
+    st->nnzb_S = h->nnzb_S; st->nnzb_L = d.nblk; st->max_track = h->Kmax;
+    cudaEventElapsedTime(&st->ms_total, h->ev[0], h->ev[6]);
+    st->ms_build = ms[0]; st->ms_solve = ms[1]; st->ms_update = ms[2]; st->ms_control = ms[3];
+    st->launches = launches;
+  }
+  return h->h_ctl->iter;
+#undef CKO
+}
+
+static int current_buffer(svs_ba* h, int* cur) {
+  CK(cudaMemcpyAsync(h->h_ctl, h->d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *cur = h->h_ctl->cur;
+  return SVS_OK;
+}
+
+int svs_ba_get_poses(svs_ba* h, double* T_qt) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  int cur, rc;
+  if ((rc = current_buffer(h, &cur))) return rc;
+  if (h->d.P)
+    CK(cudaMemcpyAsync(T_qt, h->d.pose[cur], 7 * (size_t)h->d.P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVS_OK;
+}
+
+int svs_ba_get_points(svs_ba* h, double* psi) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  int cur, rc;
+  if ((rc = current_buffer(h, &cur))) return rc;
+  const int L = h->d.L;
+  std::vector<double> tmp(3 * (size_t)L);
+  if (L) CK(cudaMemcpyAsync(tmp.data(), h->d.psi[cur], 3 * (size_t)L * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int li = 0; li < L; ++li)
+    for (int q = 0; q < 3; ++q) psi[3 * (size_t)h->lm_to_user[li] + q] = tmp[3 * (size_t)li + q];
+  return SVS_OK;
+}
+
+int svs_optimiseInnerAndOuterWindow(svs_ba* h, int P, double* T_qt, const unsigned char* fixed, int L, double* psi,
+                                    int E, const int* e_point, const int* e_pose, const int* e_anchor,
+                                    const double* e_obs, const double* e_info, int C, const int* c_i, const int* c_j,
+                                    const double* c_T, const double* c_Lambda, const svs_cam* cam, int num_iters,
+                                    int robust, double huber_delta, svs_ba_stats* stats) {
+  int rc = svs_ba_set_problem(h, P, T_qt, fixed, L, psi, E, e_point, e_pose, e_anchor, e_obs, e_info, C, c_i, c_j,
+                              c_T, c_Lambda, cam);
+  if (rc) return -100 + rc;
+  // lambda0 = 50, 5 trials: slam_graph.cpp:338, :1073
+  const int it = svs_ba_optimize(h, num_iters, robust, huber_delta, 50., 5, stats);
+  if (it <= -100) return it;
+  if ((rc = svs_ba_get_poses(h, T_qt))) return -100 + rc;
+  if ((rc = svs_ba_get_points(h, psi))) return -100 + rc;
+  return it;
+}
+
+int svs_ba_chi2(svs_ba* h, int robust, double huber_delta, double* chi2) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  BaDev& d = h->d;
+  launch_chi2(d, robust, huber_delta, h->stream);
+  std::vector<double> a(d.L), c(d.C);
+  if (d.L) CK(cudaMemcpyAsync(a.data(), d.chi_l, d.L * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (d.C) CK(cudaMemcpyAsync(c.data(), d.chi_c, d.C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  double s = 0;
+  for (double v : a) s += v;
+  for (double v : c) s += v;
+  *chi2 = s;
+  return SVS_OK;
+}
+
+static int set_lambda(svs_ba* h, double lambda) {
+  CK(cudaMemcpyAsync(h->h_ctl, h->d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->h_ctl->lambda = lambda;
+  CK(cudaMemcpyAsync(h->d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
+  return SVS_OK;
+}
+
+int svs_ba_reduced_system(svs_ba* h, int robust, double huber_delta, double lambda, double* Sd, double* bs,
+                          double* chi2) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  BaDev& d = h->d;
+  int rc;
+  if ((rc = set_lambda(h, lambda))) return rc;
+  if ((rc = clear_system(h))) return rc;
+  launch_build(d, 0, d.L, h->Kmax, robust, huber_delta, h->stream);
+  const int P = d.P, n = 6 * P;
+  std::vector<double> S(36 * (size_t)d.nblk), bp(n), bc(n), chl(d.L), chc(d.C);
+  std::vector<int> colp(P + 1), rowi(d.nblk), perm(P);
+  std::vector<unsigned char> fx(P);
+  CK(cudaMemcpyAsync(S.data(), d.S, S.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (P) {
+    CK(cudaMemcpyAsync(bp.data(), d.bp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(bc.data(), d.bc, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(perm.data(), d.perm, P * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(fx.data(), d.fixed, P, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaMemcpyAsync(colp.data(), d.col_ptr, (P + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(rowi.data(), d.row_idx, d.nblk * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (d.L) CK(cudaMemcpyAsync(chl.data(), d.chi_l, d.L * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (d.C) CK(cudaMemcpyAsync(chc.data(), d.chi_c, d.C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if ((rc = clear_system(h))) return rc;
+  std::fill(Sd, Sd + (size_t)n * n, 0.);
+  for (int j = 0; j < P; ++j)
+    for (int b = colp[j]; b < colp[j + 1]; ++b) {
+      const int pi = perm[rowi[b]], pj = perm[j];
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+          double v = S[36 * (size_t)b + r * 6 + c];
+          if (pi == pj && r == c) v += lambda + (fx[pi] ? 1. : 0.);
+          Sd[(size_t)(6 * pi + r) * n + 6 * pj + c] = v;
+          Sd[(size_t)(6 * pj + c) * n + 6 * pi + r] = v;
+        }
+    }
+  for (int i = 0; i < n; ++i) bs[i] = bp[i] - bc[i];
+  if (chi2) {
+    double s = 0;
+    for (double v : chl) s += v;
+    for (double v : chc) s += v;
+    *chi2 = s;
+  }
+  return SVS_OK;
+}
+
+int svs_ba_solve_reduced(svs_ba* h, int robust, double huber_delta, double lambda, double* x) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  BaDev& d = h->d;
+  int rc;
+  if ((rc = set_lambda(h, lambda))) return rc;
+  if ((rc = clear_system(h))) return rc;
+  launch_build(d, 0, d.L, h->Kmax, robust, huber_delta, h->stream);
+  launch_solve(d, h->stream);
+  if (d.P) CK(cudaMemcpyAsync(x, d.x, 6 * (size_t)d.P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  const int failed = h->h_ctl->chol_fail;
+  if ((rc = clear_system(h))) return rc;
+  return failed ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// ba_types.cuh -- device-side view of one double-window BA problem.
+// Layout follows what SlamGraph::copyDataToG2o (slam_graph.cpp:985-1032) hands to g2o,
+// regrouped for the GPU: landmarks sorted by (anchor, pose set), edges grouped per landmark
+// (self-anchor observation first), per-slot Hpl blocks in SoA.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace svs {
+
+constexpr int kMaxIters = 64;
+constexpr int kMaxTrack = 32;  // slots per landmark (anchor + observers) the fused kernel stages in smem
+
+// Levenberg-Marquardt control block, lives in device memory; mirrors the locals of
+// g2o::OptimizationAlgorithmLevenberg::solve (configured at slam_graph.cpp:336-346,1071-1073).
+struct LmCtl {
+  double lambda, ni;
+  double chi_cur, chi_new, rho, scale_pose;
+  int cur;         // index of the accepted state buffer
+  int iter;        // outer iterations finished
+  int qmax;        // trials in the running iteration
+  int again;       // 1: run another trial of this iteration
+  int stop;        // 1: Terminate (qmax == max_trials or rho == 0)
+  int chol_fail;   // reduced system not positive definite in this trial
+  int trials_total;
+  int max_trials;
+  double chi_init;
+  double chi_iter[kMaxIters];
+  double lambda_iter[kMaxIters];
+  int trials_iter[kMaxIters];
+};
+
+struct BaDev {
+  int P, L, E, C, nslots, nblk;
+  int flags;
+  double f, px, py, b;
+  // state, double buffered (index ctl->cur = accepted, the other = trial)
+  double* pose[2];  // [P][7]
+  double* Rt[2];    // [P][12]  row-major R, then t
+  double* psi[2];   // [L][3]   internal landmark order
+  const unsigned char* fixed;  // [P]
+  // landmarks (internal order)
+  const int* lm_eptr;            // [L+1]
+  const int* lm_sptr;            // [L+1]
+  const int* lm_anchor;          // [L]
+  const unsigned char* lm_self;  // [L] first edge is the observation in the anchor frame
+  // edges (internal order)
+  const int* e_pose;    // [E]
+  const double* e_obs;  // [3][E]
+  const double* e_w;    // [3][E] diagonal of Lambda
+  // per-trial products of the fused kernel
+  double* W;          // [18][nslots]  Hpl blocks (6x3 row-major), slot 0 of a landmark = anchor
+  double* Dbl;        // [L][12]  Hll upper (d00 d01 d02 d11 d12 d22), b_l (3), pad
+  double* chi_l;      // [L]  robust chi2 of the landmark's edges at the accepted state
+  double* chi_new_l;  // [L]  ... at the trial state
+  double* scale_l;    // [L]  sum dpsi (lambda dpsi + b_l)
+  // reduced camera system
+  double* S;       // [nblk][36] lower blocks in elimination order, pattern of the factor
+  const int* tbl;  // [P*P] (block << 1 | transpose) for (row pose, col pose), -1 if absent
+  double* bp;      // [6P] -J^T W e  (g2o _b, pose part)
+  double* bc;      // [6P] Hpl Hll^-1 b_l
+  double* x;       // [6P] pose increments, natural pose order
+  // pose-pose constraints (G2oEdgeSE3)
+  const int* c_i; const int* c_j; const double* c_T; const double* c_Lam;
+  double* chi_c; double* chi_c_new;
+  // factorisation structure (positions = elimination order)
+  const int* perm; const int* pos;
+  const int* col_ptr;  // [P+1] first block of column j is its diagonal block
+  const int* row_idx;  // [nblk] row position of each block
+  const int* upd_ptr;  // [P+1]
+  const int* upd_dst;  // destination block of each (a>=b) pair of a column
+  const int* upd_ab;   // (a << 16 | b): indices into the column's sub-diagonal list
+  double* Linv;        // [P][36] inverse of the diagonal factor blocks
+  double* ywork;       // [6P]
+  LmCtl* ctl;
+};
+
+}  // namespace svs
