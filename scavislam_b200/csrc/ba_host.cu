@@ -25,7 +25,10 @@ struct svs_ba {
   std::string err;
   bool has_problem = false;
   BaDev d{};
-  std::vector<void*> allocs;
+  // one device arena + one pinned staging arena, grown on demand and reused across set_problem calls
+  char* arena = nullptr; size_t arena_cap = 0, arena_off = 0;
+  char* stage = nullptr; size_t stage_cap = 0;
+  bool measuring = false;
   LmCtl* h_ctl = nullptr;  // pinned
   double* d_pose0 = nullptr;
   double* d_psi0 = nullptr;
@@ -33,6 +36,7 @@ struct svs_ba {
   int Kmax = 1;
   int nnzb_S = 0;
   int C_edges = 0;
+  int max_col_blocks = 0;
   cudaEvent_t ev[8] = {};
   // last optimize() settings
 };
@@ -53,30 +57,59 @@ struct CudaErr {
     }                                                                   \
   } while (0)
 
+constexpr size_t kAlign = 256;
+
 template <typename T>
 int dev_alloc(svs_ba* h, T** p, size_t n) {
-  void* q = nullptr;
-  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
-  h->allocs.push_back(q);
-  *p = static_cast<T*>(q);
+  const size_t bytes = ((std::max<size_t>(n, 1) * sizeof(T) + kAlign - 1) / kAlign) * kAlign;
+  if (!h->measuring) *p = reinterpret_cast<T*>(h->arena + h->arena_off);
+  h->arena_off += bytes;
   return SVS_OK;
 }
 
+// Uploads are laid out at the front of the arena, mirrored in the pinned staging buffer, and
+// shipped with a single H2D copy (finish_upload).
 template <typename T>
-int dev_upload(svs_ba* h, const T** p, const std::vector<T>& v) {
+int dev_upload(svs_ba* h, const T** p, const T* src, size_t n) {
+  const size_t off = h->arena_off;
   T* q = nullptr;
-  int rc = dev_alloc(h, &q, v.size());
-  if (rc) return rc;
-  if (!v.empty()) CK(cudaMemcpyAsync(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-  *p = q;
+  dev_alloc(h, &q, n);
+  if (!h->measuring) {
+    if (n) memcpy(h->stage + off, src, n * sizeof(T));
+    *p = q;
+  }
+  return SVS_OK;
+}
+template <typename T>
+int dev_upload(svs_ba* h, const T** p, const std::vector<T>& v) { return dev_upload(h, p, v.data(), v.size()); }
+
+int arena_reserve(svs_ba* h, size_t total, size_t upload) {
+  if (total > h->arena_cap) {
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr; h->arena_cap = 0;
+    const size_t want = total + total / 4;
+    CK(cudaMalloc((void**)&h->arena, want));
+    h->arena_cap = want;
+  }
+  if (upload > h->stage_cap) {
+    if (h->stage) cudaFreeHost(h->stage);
+    h->stage = nullptr; h->stage_cap = 0;
+    const size_t want = upload + upload / 4;
+    CK(cudaMallocHost((void**)&h->stage, want));
+    h->stage_cap = want;
+  }
   return SVS_OK;
 }
 
 void free_problem(svs_ba* h) {
-  for (void* p : h->allocs) cudaFree(p);
-  h->allocs.clear();
   h->has_problem = false;
   h->d = BaDev{};
+}
+
+void free_arena(svs_ba* h) {
+  if (h->arena) cudaFree(h->arena);
+  if (h->stage) cudaFreeHost(h->stage);
+  h->arena = nullptr; h->stage = nullptr; h->arena_cap = h->stage_cap = 0;
 }
 
 // Symbolic analysis of the reduced camera system: elimination order (greedy minimum degree on
@@ -215,6 +248,7 @@ void svs_ba_destroy(svs_ba* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   free_problem(h);
+  free_arena(h);
   for (auto& e : h->ev) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -239,6 +273,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     if (c_i[c] < 0 || c_i[c] >= P || c_j[c] < 0 || c_j[c] >= P || c_i[c] == c_j[c])
       return fail(h, SVS_ERR_INVALID, "pose-pose edge index out of range");
   cudaSetDevice(h->device);
+  CK(cudaStreamSynchronize(h->stream));   // the arena and the staging buffer are about to be reused
   free_problem(h);
 
   // ---- group edges per landmark
@@ -329,41 +364,54 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   analyse(P, adj, (h->flags & SVS_BA_NATURAL_ORDER) != 0, sy);
   if (sy.nblk >= (1 << 20)) return fail(h, SVS_ERR_UNSUPPORTED, "reduced system factor has more than 2^20 blocks");
 
-  // ---- upload
+  // ---- device image: constant arrays (uploaded in one copy) followed by work buffers
   BaDev& d = h->d;
   d.P = P; d.L = L; d.E = E; d.C = C; d.nslots = ns; d.nblk = sy.nblk; d.flags = h->flags;
   d.f = cam->f; d.px = cam->px; d.py = cam->py; d.b = cam->b;
-  int rc;
   std::vector<unsigned char> fx(P, 0);
   if (fixed) fx.assign(fixed, fixed + P);
-#define UP(field, vec) if ((rc = dev_upload(h, &d.field, vec))) return rc
-  UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self);
-  UP(e_pose, ie_pose); UP(e_obs, ie_obs); UP(e_w, ie_w);
-  UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
-  UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab);
-  {
-    std::vector<int> ci(c_i, c_i + C), cj(c_j, c_j + C);
-    std::vector<double> cT(c_T, c_T + 7 * (size_t)C), cL(c_Lambda, c_Lambda + 36 * (size_t)C);
-    UP(c_i, ci); UP(c_j, cj); UP(c_T, cT); UP(c_Lam, cL);
-  }
+  const double* d_pose0c = nullptr;
+  const double* d_psi0c = nullptr;
+  size_t upload_bytes = 0;
+  auto lay = [&]() {
+    h->arena_off = 0;
+#define UP(field, vec) dev_upload(h, &d.field, vec)
+    UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self);
+    UP(e_pose, ie_pose); UP(e_obs, ie_obs); UP(e_w, ie_w);
+    UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
+    UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab);
+    dev_upload(h, &d.c_i, c_i, (size_t)C); dev_upload(h, &d.c_j, c_j, (size_t)C);
+    dev_upload(h, &d.c_T, c_T, 7 * (size_t)C); dev_upload(h, &d.c_Lam, c_Lambda, 36 * (size_t)C);
+    dev_upload(h, &d_pose0c, T_qt, 7 * (size_t)P);
+    dev_upload(h, &d_psi0c, ipsi.data(), 3 * (size_t)L);
 #undef UP
-#define AL(field, n) if ((rc = dev_alloc(h, &d.field, (size_t)(n)))) return rc
-  for (int b = 0; b < 2; ++b) { AL(pose[b], 7 * (size_t)P); AL(Rt[b], 12 * (size_t)P); AL(psi[b], 3 * (size_t)L); }
-  AL(W, 18 * (size_t)ns); AL(Dbl, 12 * (size_t)L); AL(chi_l, L); AL(chi_new_l, L); AL(scale_l, L);
-  AL(S, 36 * (size_t)sy.nblk); AL(bp, 6 * (size_t)P); AL(bc, 6 * (size_t)P); AL(x, 6 * (size_t)P);
-  AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
-  AL(ctl, 1);
+    upload_bytes = h->arena_off;
+#define AL(field, n) dev_alloc(h, &d.field, (size_t)(n))
+    for (int b = 0; b < 2; ++b) { AL(pose[b], 7 * (size_t)P); AL(Rt[b], 12 * (size_t)P); AL(psi[b], 3 * (size_t)L); }
+    AL(W, 18 * (size_t)ns); AL(Dbl, 12 * (size_t)L); AL(chi_l, L); AL(chi_new_l, L); AL(scale_l, L);
+    AL(S, 36 * (size_t)sy.nblk); AL(bp, 6 * (size_t)P); AL(bc, 6 * (size_t)P); AL(x, 6 * (size_t)P);
+    AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
+    AL(ctl, 1);
+    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1);
 #undef AL
-  if ((rc = dev_alloc(h, &h->d_pose0, 7 * (size_t)P))) return rc;
-  if ((rc = dev_alloc(h, &h->d_psi0, 3 * (size_t)L))) return rc;
-  if (P) CK(cudaMemcpyAsync(h->d_pose0, T_qt, 7 * (size_t)P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (L) CK(cudaMemcpyAsync(h->d_psi0, ipsi.data(), 3 * (size_t)L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  };
+  h->measuring = true;
+  lay();
+  h->measuring = false;
+  int rc;
+  if ((rc = arena_reserve(h, h->arena_off, upload_bytes))) return rc;
+  lay();
+  h->d_pose0 = const_cast<double*>(d_pose0c);
+  h->d_psi0 = const_cast<double*>(d_psi0c);
+  CK(cudaMemcpyAsync(h->arena, h->stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
+  h->max_col_blocks = 0;
+  for (int j = 0; j < P; ++j) h->max_col_blocks = std::max(h->max_col_blocks, sy.col_ptr[j + 1] - sy.col_ptr[j] - 1);
   CK(cudaMemsetAsync(d.chi_c, 0, std::max(C, 1) * sizeof(double), h->stream));
   CK(cudaMemsetAsync(d.chi_c_new, 0, std::max(C, 1) * sizeof(double), h->stream));
   h->Kmax = Kmax;
   h->C_edges = C;
   h->has_problem = true;
-  CK(cudaStreamSynchronize(h->stream));   // host staging vectors die here
   return svs_ba_reset_state(h);
 }
 
@@ -418,7 +466,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     CKO(cudaMemcpyAsync(d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
   }
   if ((rc = clear_system(h))) return -100 + rc;
-  float ms[4] = {0, 0, 0, 0};
+  float ms[4] = {0, 0, 0, 0};  // build, solve, update(+decision)
   int launches = 0;
   CKO(cudaEventRecord(h->ev[0], h->stream));
   int it = 0;
@@ -428,17 +476,15 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     CKO(cudaEventRecord(h->ev[1], h->stream));
     launch_build(d, 0, d.L, h->Kmax, robust, huber_delta, h->stream);
     CKO(cudaEventRecord(h->ev[2], h->stream));
-    launch_solve(d, h->stream);
+    launch_solve(d, h->max_col_blocks, h->stream);
     CKO(cudaEventRecord(h->ev[3], h->stream));
     launch_update(d, robust, huber_delta, h->stream);
     CKO(cudaEventRecord(h->ev[4], h->stream));
-    launch_decide(d, h->stream);
-    CKO(cudaEventRecord(h->ev[5], h->stream));
-    launches += 4;
+    launches += 3;
     CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
     CKO(cudaStreamSynchronize(h->stream));
     CKO(cudaGetLastError());
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 3; ++k) {
       float t = 0;
       cudaEventElapsedTime(&t, h->ev[1 + k], h->ev[2 + k]);
       ms[k] += t;
@@ -600,7 +646,7 @@ int svs_ba_solve_reduced(svs_ba* h, int robust, double huber_delta, double lambd
   if ((rc = set_lambda(h, lambda))) return rc;
   if ((rc = clear_system(h))) return rc;
   launch_build(d, 0, d.L, h->Kmax, robust, huber_delta, h->stream);
-  launch_solve(d, h->stream);
+  launch_solve(d, h->max_col_blocks, h->stream);
   if (d.P) CK(cudaMemcpyAsync(x, d.x, 6 * (size_t)d.P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));

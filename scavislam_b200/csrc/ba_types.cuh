@@ -71,6 +71,8 @@ struct BaDev {
   const int* upd_ab;   // (a << 16 | b): indices into the column's sub-diagonal list
   double* Linv;        // [P][36] inverse of the diagonal factor blocks
   double* ywork;       // [6P]
+  double* part;        // [update grid][3] per-CTA partial sums (chi2 accepted, chi2 trial, scale)
+  unsigned* ticket;    // last-CTA-done counter of k_update
   LmCtl* ctl;
 };
 

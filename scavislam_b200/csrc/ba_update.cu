@@ -1,0 +1,251 @@
+// ba_update.cu -- k_update (landmark back-substitution, point update, trial chi2, LM decision),
+// k_chi2, k_prep.
+#include "ba_dev.cuh"
+#include "ba_kernels.cuh"
+
+namespace svs {
+
+// ------------------------------------------------------------------ k_update (+ LM decision)
+
+// g2o::OptimizationAlgorithmLevenberg::solve, the part after the linear solve: rho test, lambda
+// update, accept (swap state buffers) or reject (keep), trial-loop and Terminate conditions.
+__device__ void lm_decide(LmCtl* ctl, double chi_cur, double chi_new, double scale_pts) {
+  const int fail = ctl->chol_fail;
+  double currentChi = chi_cur;
+  const double tempChi = fail ? 1.7976931348623157e308 : chi_new;
+  if (ctl->iter == 0 && ctl->qmax == 0) ctl->chi_init = currentChi;
+  double lambda = ctl->lambda, ni = ctl->ni;
+  double rho = currentChi - tempChi;
+  double scale = fail ? 0. : ctl->scale_pose + scale_pts;   // computeScale(): sum x (lambda x + b)
+  scale += 1e-3;
+  rho /= scale;
+  int cur = ctl->cur;
+  if (rho > 0 && isfinite(tempChi)) {
+    const double u = 2 * rho - 1;
+    double alpha = 1. - u * u * u;
+    alpha = fmin(alpha, 2. / 3.);
+    const double sf = fmax(1. / 3., alpha);
+    lambda *= sf;
+    ni = 2;
+    currentChi = tempChi;
+    cur ^= 1;
+  } else {
+    lambda *= ni;
+    ni *= 2;
+  }
+  int qmax = ctl->qmax + 1;
+  ctl->trials_total += 1;
+  const int again = (rho < 0 && qmax < ctl->max_trials) ? 1 : 0;
+  ctl->lambda = lambda; ctl->ni = ni; ctl->cur = cur; ctl->rho = rho;
+  ctl->chi_cur = currentChi; ctl->chi_new = tempChi;
+  ctl->again = again;
+  if (!again) {
+    const int it = ctl->iter;
+    if (it < kMaxIters) { ctl->chi_iter[it] = currentChi; ctl->lambda_iter[it] = lambda; ctl->trials_iter[it] = qmax; }
+    ctl->stop = (qmax == ctl->max_trials || rho == 0) ? 1 : 0;
+    ctl->iter = it + 1;
+    qmax = 0;
+  }
+  ctl->qmax = qmax;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_update(BaDev d, int robust, double delta, int n_lm_blocks) {
+  __shared__ double sPart[WARPS][3];
+  __shared__ int sLast;
+  LmCtl* ctl = d.ctl;
+  const int cur = ctl->cur, trial = 1 - cur;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // every CTA helps clearing the reduced system for the next build
+  {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gn = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = gid; i < (size_t)d.nblk * 36; i += gn) d.S[i] = 0.;
+    for (size_t i = gid; i < (size_t)6 * d.P; i += gn) { d.bp[i] = 0.; d.bc[i] = 0.; }
+  }
+  double part_cur = 0, part_new = 0, part_scale = 0;   // this warp's share (valid on lane 0)
+  if ((int)blockIdx.x >= n_lm_blocks) {
+    const int c = ((int)blockIdx.x - n_lm_blocks) * (WARPS * 32) + (int)threadIdx.x;
+    double a = 0, b = 0;
+    if (c < d.C) {
+      b = constraint_chi2(d, d.pose[trial], c);
+      d.chi_c_new[c] = b;
+      a = d.chi_c[c];
+    }
+    part_cur = warp_sum(a);
+    part_new = warp_sum(b);
+  } else {
+    const int li = (int)blockIdx.x * WARPS + warp;
+    if (li < d.L) {
+      const double lambda = ctl->lambda;
+      const int e0 = d.lm_eptr[li], k = d.lm_eptr[li + 1] - e0;
+      const int s0 = d.lm_sptr[li], K = d.lm_sptr[li + 1] - s0;
+      const double* psi = d.psi[cur] + 3 * (size_t)li;
+      double* psin = d.psi[trial] + 3 * (size_t)li;
+      if (k == 0 || ctl->chol_fail) {
+        if (lane < 3) psin[lane] = psi[lane];
+        part_cur = (k == 0) ? 0. : d.chi_l[li];
+      } else {
+        part_cur = d.chi_l[li];
+        const int off = d.lm_self[li] ? 0 : 1;
+        const int ia = d.lm_anchor[li];
+        // c = b_l - sum_slots B_s^T x_s
+        double c3[3] = {0, 0, 0};
+        for (int s = lane; s < K; s += 32) {
+          const int p = (s == 0) ? ia : d.e_pose[e0 + s - off];
+          const double* xs = d.x + 6 * p;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            const double xr = xs[r];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) c3[q] -= d.W[(size_t)(r * 3 + q) * d.nslots + s0 + s] * xr;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) c3[q] = warp_sum(c3[q]);
+        const double* Dbl = d.Dbl + 12 * (size_t)li;
+        const double bl[3] = {Dbl[6], Dbl[7], Dbl[8]};
+        double Di[9];
+        inv3_sym_lambda(Dbl, lambda, Di);
+        const double cc[3] = {bl[0] + c3[0], bl[1] + c3[1], bl[2] + c3[2]};
+        double dpsi[3], pn[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          dpsi[q] = Di[q * 3] * cc[0] + Di[q * 3 + 1] * cc[1] + Di[q * 3 + 2] * cc[2];
+          pn[q] = psi[q] + dpsi[q];
+        }
+        if (lane < 3) psin[lane] = pn[lane];
+        part_scale = dpsi[0] * (lambda * dpsi[0] + bl[0]) + dpsi[1] * (lambda * dpsi[1] + bl[1]) +
+                     dpsi[2] * (lambda * dpsi[2] + bl[2]);
+        // robust chi2 of this landmark's observations at the trial state
+        const double* __restrict__ Rt = d.Rt[trial];
+        double Ra[9], ta[3];
+        load12(Rt, ia, Ra, ta);
+        const double ipz = 1. / pn[2];
+        const double xa[3] = {pn[0] * ipz, pn[1] * ipz, ipz};
+        double chi = 0;
+        for (int i = lane; i < k; i += 32) {
+          const int e = e0 + i;
+          const double obs[3] = {__ldg(d.e_obs + e), __ldg(d.e_obs + (size_t)d.E + e), __ldg(d.e_obs + 2 * (size_t)d.E + e)};
+          const double om[3] = {__ldg(d.e_w + e), __ldg(d.e_w + (size_t)d.E + e), __ldg(d.e_w + 2 * (size_t)d.E + e)};
+          chi += edge_cost(d, Rt, d.e_pose[e], Ra, ta, xa, obs, om, robust, delta);
+        }
+        part_new = warp_sum(chi);
+      }
+    }
+  }
+  // CTA partials in a fixed order -> part[blockIdx][3]; the last CTA to finish reduces them
+  if (lane == 0) { sPart[warp][0] = part_cur; sPart[warp][1] = part_new; sPart[warp][2] = part_scale; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int w = 0; w < WARPS; ++w) { a += sPart[w][0]; b += sPart[w][1]; c += sPart[w][2]; }
+    double* pp = d.part + 3 * (size_t)blockIdx.x;
+    pp[0] = a; pp[1] = b; pp[2] = c;
+    __threadfence();
+    const unsigned ticket = atomicAdd(d.ticket, 1u);
+    sLast = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  // deterministic final reduction (fixed partition, fixed order)
+  double acc[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += WARPS * 32) {
+    const double* pp = d.part + 3 * (size_t)i;
+    acc[0] += __ldcg(pp); acc[1] += __ldcg(pp + 1); acc[2] += __ldcg(pp + 2);
+  }
+  __shared__ double sFin[WARPS * 32][3];
+  sFin[threadIdx.x][0] = acc[0]; sFin[threadIdx.x][1] = acc[1]; sFin[threadIdx.x][2] = acc[2];
+  __syncthreads();
+  for (int w = WARPS * 16; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      sFin[threadIdx.x][0] += sFin[threadIdx.x + w][0];
+      sFin[threadIdx.x][1] += sFin[threadIdx.x + w][1];
+      sFin[threadIdx.x][2] += sFin[threadIdx.x + w][2];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *d.ticket = 0;
+    lm_decide(ctl, sFin[0][0], sFin[0][1], sFin[0][2]);
+  }
+}
+
+void launch_update(const BaDev& d, int robust, double delta, cudaStream_t st) {
+  constexpr int WARPS = 8;
+  const int n_lm_blocks = (d.L + WARPS - 1) / WARPS;
+  const int n_c_blocks = (d.C + WARPS * 32 - 1) / (WARPS * 32);
+  int nb = n_lm_blocks + n_c_blocks;
+  if (nb == 0) nb = 1;   // still clears the reduced system and takes the LM decision
+  k_update<WARPS><<<nb, WARPS * 32, 0, st>>>(d, robust, delta, n_lm_blocks);
+}
+int update_grid_blocks(int L, int C) {
+  constexpr int WARPS = 8;
+  const int nb = (L + WARPS - 1) / WARPS + (C + WARPS * 32 - 1) / (WARPS * 32);
+  return nb > 0 ? nb : 1;
+}
+
+// ------------------------------------------------------------------ k_chi2 (state cur)
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_chi2(BaDev d, int robust, double delta, int n_lm_blocks) {
+  const int cur = d.ctl->cur;
+  if ((int)blockIdx.x >= n_lm_blocks) {
+    const int c = ((int)blockIdx.x - n_lm_blocks) * (WARPS * 32) + (int)threadIdx.x;
+    if (c < d.C) d.chi_c[c] = constraint_chi2(d, d.pose[cur], c);
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int li = (int)blockIdx.x * WARPS + warp;
+  if (li >= d.L) return;
+  const int e0 = d.lm_eptr[li], k = d.lm_eptr[li + 1] - e0;
+  double chi = 0;
+  if (k > 0) {
+    const double* __restrict__ Rt = d.Rt[cur];
+    const double* psi = d.psi[cur] + 3 * (size_t)li;
+    double Ra[9], ta[3];
+    load12(Rt, d.lm_anchor[li], Ra, ta);
+    const double ipz = 1. / psi[2];
+    const double xa[3] = {psi[0] * ipz, psi[1] * ipz, ipz};
+    for (int i = lane; i < k; i += 32) {
+      const int e = e0 + i;
+      const double obs[3] = {__ldg(d.e_obs + e), __ldg(d.e_obs + (size_t)d.E + e), __ldg(d.e_obs + 2 * (size_t)d.E + e)};
+      const double om[3] = {__ldg(d.e_w + e), __ldg(d.e_w + (size_t)d.E + e), __ldg(d.e_w + 2 * (size_t)d.E + e)};
+      chi += edge_cost(d, Rt, d.e_pose[e], Ra, ta, xa, obs, om, robust, delta);
+    }
+    chi = warp_sum(chi);
+  }
+  if (lane == 0) d.chi_l[li] = chi;
+}
+
+void launch_chi2(const BaDev& d, int robust, double delta, cudaStream_t st) {
+  constexpr int WARPS = 8;
+  const int n_lm_blocks = (d.L + WARPS - 1) / WARPS;
+  const int n_c_blocks = (d.C + WARPS * 32 - 1) / (WARPS * 32);
+  if (n_lm_blocks + n_c_blocks == 0) return;
+  k_chi2<WARPS><<<n_lm_blocks + n_c_blocks, WARPS * 32, 0, st>>>(d, robust, delta, n_lm_blocks);
+}
+
+// ------------------------------------------------------------------ k_prep: quaternion poses -> R,t
+
+__global__ void k_prep(BaDev d, int buf) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.P) return;
+  double T[7], R[9];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) T[r] = d.pose[buf][7 * (size_t)p + r];
+  quat_to_R(T, R);
+#pragma unroll
+  for (int r = 0; r < 9; ++r) d.Rt[buf][12 * (size_t)p + r] = R[r];
+  d.Rt[buf][12 * (size_t)p + 9] = T[4];
+  d.Rt[buf][12 * (size_t)p + 10] = T[5];
+  d.Rt[buf][12 * (size_t)p + 11] = T[6];
+}
+
+void launch_prep(const BaDev& d, int buf, cudaStream_t st) {
+  if (d.P == 0) return;
+  k_prep<<<(d.P + 127) / 128, 128, 0, st>>>(d, buf);
+}
+}  // namespace svs

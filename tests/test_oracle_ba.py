@@ -1,0 +1,244 @@
+"""CPU tests pinning the BA oracle (oracle/ba_oracle.c) with independent checks:
+finite differences, a numpy Schur complement, and committed golden vectors.
+
+The reference ships no tests or golden vectors for this path, so these
+are the secondary pins: invariants derived from the reference code itself.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from scavislam_b200 import synth
+
+CAM = np.array([synth.CAM_F, synth.CAM_PX, synth.CAM_PY, synth.CAM_B])
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ba_golden.npz")
+
+
+def rand_pose(rng, scale=0.3):
+    from oracle import pyoracle as po
+    return po.se3_exp(rng.normal(0, scale, 6))
+
+
+def test_se3_exp_log_roundtrip(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        d = rng.normal(0, 0.5, 6)
+        T = oracle.se3_exp(d)
+        assert abs(np.linalg.norm(T[:4]) - 1) < 1e-14
+        np.testing.assert_allclose(oracle.se3_log(T), d, atol=1e-12)
+    # tiny rotation branch (theta < 1e-10)
+    d = np.array([0.1, -0.2, 0.3, 1e-12, 0, 0])
+    np.testing.assert_allclose(oracle.se3_log(oracle.se3_exp(d)), d, atol=1e-12)
+
+
+def test_se3_group_laws(oracle):
+    rng = np.random.default_rng(1)
+    A, B = rand_pose(rng), rand_pose(rng)
+    x = rng.normal(0, 1, 3)
+    np.testing.assert_allclose(oracle.se3_act(oracle.se3_mul(A, B), x), oracle.se3_act(A, oracle.se3_act(B, x)), atol=1e-13)
+    I = oracle.se3_mul(A, oracle.se3_inv(A))
+    np.testing.assert_allclose(I, [0, 0, 0, 1, 0, 0, 0], atol=1e-14)
+    # Adj: A exp(d) A^-1 = exp(Adj d)
+    d = rng.normal(0, 0.1, 6)
+    lhs = oracle.se3_mul(oracle.se3_mul(A, oracle.se3_exp(d)), oracle.se3_inv(A))
+    rhs = oracle.se3_exp(oracle.se3_adj(A) @ d)
+    np.testing.assert_allclose(lhs, rhs, atol=1e-12)
+
+
+def test_invert_depth_involution(oracle):
+    # maths_utils.h:66: invert_depth(invert_depth(x)) == x
+    from oracle import pyoracle as po
+    import ctypes as C
+    x = np.array([0.3, -0.2, 4.0])
+    y, z = np.zeros(3), np.zeros(3)
+    po.lib().oba_invert_depth(x.ctypes.data_as(po.c_dp), y.ctypes.data_as(po.c_dp))
+    po.lib().oba_invert_depth(y.ctypes.data_as(po.c_dp), z.ctypes.data_as(po.c_dp))
+    np.testing.assert_allclose(z, x, rtol=1e-15)
+
+
+def _fd_edge(oracle, Tp, Ta, psi, obs, h=1e-6):
+    """Numeric Jacobians of the error wrt psi (additive) and both poses (T <- exp(d) T)."""
+    def err(Tp_, Ta_, psi_):
+        return oracle.edge_error(CAM, Tp_, Ta_, psi_, obs)
+    Jpsi, Jp, Ja = np.zeros((3, 3)), np.zeros((3, 6)), np.zeros((3, 6))
+    for k in range(3):
+        d = np.zeros(3); d[k] = h
+        Jpsi[:, k] = (err(Tp, Ta, psi + d) - err(Tp, Ta, psi - d)) / (2 * h)
+    for k in range(6):
+        d = np.zeros(6); d[k] = h
+        Jp[:, k] = (err(oracle.se3_mul(oracle.se3_exp(d), Tp), Ta, psi) -
+                    err(oracle.se3_mul(oracle.se3_exp(-d), Tp), Ta, psi)) / (2 * h)
+        Ja[:, k] = (err(Tp, oracle.se3_mul(oracle.se3_exp(d), Ta), psi) -
+                    err(Tp, oracle.se3_mul(oracle.se3_exp(-d), Ta), psi)) / (2 * h)
+    return Jpsi, Jp, Ja
+
+
+def test_edge_jacobians_vs_finite_differences(oracle):
+    """linearizeOplus (anchored_points.cpp:168-189) against numeric differentiation of
+    computeError (:148-166) -- the check the reference's numeric-Jacobian defaults
+    (transformations.h:320-383) make implicitly."""
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        Tp, Ta = rand_pose(rng), rand_pose(rng)
+        z = rng.uniform(2, 15)
+        psi = np.array([rng.uniform(-0.4, 0.4), rng.uniform(-0.3, 0.3), 1 / z])
+        obs = rng.uniform(0, 400, 3)
+        Jpsi, Jp, Ja = oracle.edge_jacobians(CAM, Tp, Ta, psi)
+        Fpsi, Fp, Fa = _fd_edge(oracle, Tp, Ta, psi, obs)
+        for A, F in ((Jpsi, Fpsi), (Jp, Fp), (Ja, Fa)):
+            assert np.abs(A - F).max() <= 1e-5 * max(1.0, np.abs(F).max())
+
+
+def test_self_anchor_edge_jacobians_cancel(oracle):
+    # pose == anchor  =>  J_pose = -J_anchor (anchored_points.cpp:187-188 with T_ca = I)
+    rng = np.random.default_rng(3)
+    T = rand_pose(rng)
+    psi = np.array([0.1, -0.05, 0.2])
+    _, Jp, Ja = oracle.edge_jacobians(CAM, T, T, psi)
+    np.testing.assert_allclose(Jp, -Ja, atol=1e-9 * np.abs(Jp).max())
+
+
+def test_posepose_jacobians_vs_finite_differences(oracle):
+    rng = np.random.default_rng(4)
+    T1, T2 = rand_pose(rng), rand_pose(rng)
+    # measurement close to the true relative pose so that the BCH truncation in third() is accurate
+    T21 = oracle.se3_mul(oracle.se3_exp(rng.normal(0, 0.01, 6)), oracle.se3_mul(T2, oracle.se3_inv(T1)))
+    e = oracle.posepose_error(T21, T1, T2)
+    Ji, Jj = oracle.posepose_jacobians(T21, e)
+    h = 1e-6
+    Fi, Fj = np.zeros((6, 6)), np.zeros((6, 6))
+    for k in range(6):
+        d = np.zeros(6); d[k] = h
+        Fi[:, k] = (oracle.posepose_error(T21, oracle.se3_mul(oracle.se3_exp(d), T1), T2) -
+                    oracle.posepose_error(T21, oracle.se3_mul(oracle.se3_exp(-d), T1), T2)) / (2 * h)
+        Fj[:, k] = (oracle.posepose_error(T21, T1, oracle.se3_mul(oracle.se3_exp(d), T2)) -
+                    oracle.posepose_error(T21, T1, oracle.se3_mul(oracle.se3_exp(-d), T2))) / (2 * h)
+    # third() is a 2nd-order BCH approximation: agreement to O(|e|^3)
+    assert np.abs(Ji - Fi).max() < 5e-3 and np.abs(Jj - Fj).max() < 5e-3
+
+
+def _small_problem(seed=7, self_edges=True):
+    pb = synth.make_window(6, 40, seed=seed)
+    if not self_edges:
+        keep = pb.e_pose != pb.e_anchor
+        for k in ("e_point", "e_pose", "e_anchor", "e_obs", "e_info"):
+            setattr(pb, k, np.ascontiguousarray(getattr(pb, k)[keep]))
+        pb.E = int(keep.sum())
+    return pb
+
+
+def test_full_system_is_gauss_newton_of_fd_residuals(oracle):
+    """H = J^T W J and b = -J^T W e with J from finite differences of the stacked residual
+    (no self-anchor edges, so g2o's duplicate-vertex quirk does not enter)."""
+    pb = _small_problem(self_edges=False)
+    pb.C = 0
+    pb.c_i = pb.c_i[:0]; pb.c_j = pb.c_j[:0]; pb.c_T = pb.c_T[:0]; pb.c_Lambda = pb.c_Lambda[:0]
+    H, b, chi = oracle.full_system(pb, robust=False)
+    P, L, E = pb.P, pb.L, pb.E
+    n = 6 * P + 3 * L
+
+    def residual(dx):
+        r = np.zeros(3 * E)
+        poses = np.array([oracle.se3_mul(oracle.se3_exp(dx[6 * i:6 * i + 6]), pb.pose_qt[i]) for i in range(P)])
+        psi = pb.psi + dx[6 * P:].reshape(L, 3)
+        for e in range(E):
+            r[3 * e:3 * e + 3] = oracle.edge_error(CAM, poses[pb.e_pose[e]], poses[pb.e_anchor[e]], psi[pb.e_point[e]],
+                                                   pb.e_obs[e])
+        return r
+    r0 = residual(np.zeros(n))
+    J = np.zeros((3 * E, n))
+    h = 1e-6
+    for k in range(n):
+        d = np.zeros(n); d[k] = h
+        J[:, k] = (residual(d) - residual(-d)) / (2 * h)
+    W = pb.e_info.reshape(-1)
+    Hfd = J.T @ (W[:, None] * J)
+    bfd = -J.T @ (W * r0)
+    assert abs(chi - r0 @ (W * r0)) <= 1e-10 * chi
+    assert np.abs(H - Hfd).max() <= 2e-5 * np.abs(Hfd).max()
+    assert np.abs(b - bfd).max() <= 2e-5 * np.abs(bfd).max()
+
+
+def test_self_anchor_quirk_adds_J1WJ1_to_anchor_pose(oracle):
+    """an observation made in the anchor frame itself leaves +J1^T W J1 on the
+    anchor pose's diagonal block and nothing in Hpl / b for that pose."""
+    pb = _small_problem(self_edges=True)
+    pb.C = 0
+    pb.c_i = pb.c_i[:0]; pb.c_j = pb.c_j[:0]; pb.c_T = pb.c_T[:0]; pb.c_Lambda = pb.c_Lambda[:0]
+    H, b, _ = oracle.full_system(pb, robust=False)
+    pb2 = _small_problem(self_edges=False)
+    pb2.C = 0
+    pb2.c_i = pb2.c_i[:0]; pb2.c_j = pb2.c_j[:0]; pb2.c_T = pb2.c_T[:0]; pb2.c_Lambda = pb2.c_Lambda[:0]
+    H2, b2, _ = oracle.full_system(pb2, robust=False)
+    dH = H - H2
+    P = pb.P
+    expect = np.zeros_like(dH)
+    bexp = np.zeros_like(b)
+    for e in np.nonzero(pb.e_pose == pb.e_anchor)[0]:
+        a, l = pb.e_pose[e], pb.e_point[e]
+        Jpsi, Jp, _ = oracle.edge_jacobians(CAM, pb.pose_qt[a], pb.pose_qt[a], pb.psi[l])
+        W = np.diag(pb.e_info[e])
+        err = oracle.edge_error(CAM, pb.pose_qt[a], pb.pose_qt[a], pb.psi[l], pb.e_obs[e])
+        expect[6 * a:6 * a + 6, 6 * a:6 * a + 6] += Jp.T @ W @ Jp
+        sl = slice(6 * P + 3 * l, 6 * P + 3 * l + 3)
+        expect[sl, sl] += Jpsi.T @ W @ Jpsi
+        bexp[sl] += -Jpsi.T @ W @ err
+    assert np.abs(dH - expect).max() <= 1e-9 * np.abs(H).max()
+    assert np.abs((b - b2) - bexp).max() <= 1e-9 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("lam", [50.0, 0.01])
+def test_reduced_system_is_schur_complement(oracle, lam):
+    pb = synth.make_config("C1")
+    H, b, chi = oracle.full_system(pb, robust=True)
+    S, bs, chi2 = oracle.reduced_system(pb, True, 1.0, lam)
+    assert chi == chi2
+    n = 6 * pb.P
+    Hl = H + lam * np.eye(H.shape[0])
+    Hpp, Hpl, Hll = Hl[:n, :n], Hl[:n, n:], Hl[n:, n:]
+    X = np.linalg.solve(Hll, np.concatenate([Hpl.T, b[n:, None]], 1))
+    Sref = Hpp - Hpl @ X[:, :-1]
+    bref = b[:n] - Hpl @ X[:, -1]
+    assert np.abs(S - Sref).max() <= 1e-10 * np.abs(Sref).max()
+    assert np.abs(bs - bref).max() <= 1e-9 * np.abs(bref).max()
+
+
+def test_lm_converges_to_truth_without_noise(oracle):
+    pb = synth.make_window(8, 300, seed=11, obs_sigma=0.0, outlier_frac=0.0)
+    pb.C = 0   # the synthetic pose-pose measurements carry noise of their own
+    pb.c_i = pb.c_i[:0]; pb.c_j = pb.c_j[:0]; pb.c_T = pb.c_T[:0]; pb.c_Lambda = pb.c_Lambda[:0]
+    poses, psi, st = oracle.optimize(pb, 30, robust=True)
+    assert st["chi2_final"] < 1e-8 * st["chi2_init"]
+    # gauge is free (no fixed pose): compare relative poses
+    from oracle import pyoracle as po
+    for i in range(1, pb.P):
+        rel = po.se3_mul(poses[i], po.se3_inv(poses[0]))
+        rel_t = po.se3_mul(pb.truth_pose_qt[i], po.se3_inv(pb.truth_pose_qt[0]))
+        assert np.abs(po.se3_log(po.se3_mul(rel, po.se3_inv(rel_t)))).max() < 1e-4
+
+
+def test_lm_bookkeeping(oracle):
+    pb = synth.make_config("C1")
+    poses, psi, st = oracle.optimize(pb, 5)
+    assert st["iterations"] == 5 and st["trials_total"] == sum(st["trials_iter"])
+    assert all(a > b for a, b in zip([st["chi2_init"]] + st["chi2_iter"][:-1], st["chi2_iter"]))
+    # accepted first trial with rho ~ 1: lambda shrinks by 1/3 (goodStepLowerScale)
+    np.testing.assert_allclose(st["lambda_iter"][0], 50.0 / 3)
+    # empty problem: g2o returns -1
+    assert oracle.optimize(synth.make_window(0, 0, seed=1), 3)[2]["iterations"] == -1
+
+
+def test_golden_vectors(oracle):
+    """Committed outputs of the oracle (scripts/make_golden.py) on the seeded C1 window: pins the
+    oracle against silent drift and is what the GPU tests compare against on the box."""
+    g = np.load(GOLDEN)
+    pb = synth.make_config("C1")
+    assert pb.E == int(g["E"]) and pb.C == int(g["C"])
+    np.testing.assert_allclose(pb.e_obs, g["e_obs"], rtol=0, atol=1e-9)
+    p1, s1, st1 = oracle.optimize(pb, 1)
+    p5, s5, st5 = oracle.optimize(pb, 5)
+    np.testing.assert_allclose(p1, g["poses_it1"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(p5, g["poses_it5"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(s5, g["psi_it5"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(st5["chi2_iter"], g["chi2_iter5"], rtol=1e-10)
