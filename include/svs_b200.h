@@ -141,6 +141,48 @@ int svs_ba_reduced_system(svs_ba *h, int robust, double huber_delta, double lamb
  * (LinearSolverCSparse::solve, slam_graph.cpp:55-60).  Returns 1 if not positive definite. */
 int svs_ba_solve_reduced(svs_ba *h, int robust, double huber_delta, double lambda, double *x);
 
+/* ------------------------------------------------------------------ FAST grid detector */
+
+typedef struct svs_fast svs_fast;
+
+/* FastGridCell (keyframes.h:30-43): cv::Range urange [u0,u1), vrange [v0,v1), fast_thr */
+typedef struct {
+  int u0, u1, v0, v1, thr;
+} svs_fast_cell;
+
+/* Private members of FastGrid (fast_grid.h:52-63) */
+typedef struct {
+  int grid_w, grid_h, fast_min, fast_max;
+  int min_inner, min_outer, max_inner, max_outer;
+} svs_fast_grid_params;
+
+int svs_fast_create(int device, int max_w, int max_h, int max_keypoints, svs_fast **out);
+void svs_fast_destroy(svs_fast *h);
+const char *svs_fast_last_error(const svs_fast *h);
+
+/* FastGrid::FastGrid (fast_grid.cpp:23-58): fills the band limits and grid_w*grid_h cells. */
+int svs_fast_grid_init(int img_w, int img_h, int num_features_per_cell, int boundary_per_cell, int fast_thr,
+                       int grid_w, int grid_h, int fast_min, int fast_max, svs_fast_grid_params *grid,
+                       svs_fast_cell *cells);
+
+/* The uint8 pyramid level the detector runs on (cv::Mat img of FastGrid::detect*).  Host buffer
+ * (copied H2D) or a device buffer already resident (copied D2D into the handle's pitched image). */
+int svs_fast_set_image(svs_fast *h, const unsigned char *img, int pitch, int w, int height);
+int svs_fast_set_image_device(svs_fast *h, const unsigned char *d_img, int pitch, int w, int height);
+
+/* FastGrid::detect (fast_grid.cpp:60-83): cv::FastFeatureDetector(cell.thr, false) on every cell
+ * ROI.  out_xy[n][2] = (x + u0, y + v0) grouped by cell in list order, raster order inside a cell,
+ * so the reference's quadtree content (index within the cell) is i - cell_off[c].
+ * cell_off[ncells + 1].  Returns the total number of keypoints (may exceed max_out; only
+ * max_out are written) or a negative SVS_ERR_*. */
+int svs_fast_detect(svs_fast *h, const svs_fast_cell *cells, int ncells, int *out_xy, int max_out, int *cell_off);
+
+/* FastGrid::detectAdaptively (fast_grid.cpp:86-152): up to `trials` re-detections per cell with
+ * the threshold walk of the reference (state shared along a grid row); cells[].thr is updated in
+ * place like FastGrid::cell_grid2d_. */
+int svs_fast_detect_adaptively(svs_fast *h, const svs_fast_grid_params *grid, svs_fast_cell *cells, int trials,
+                               int *out_xy, int max_out, int *cell_off);
+
 /* Library/device info: writes "name;sm;SMs;..." into buf. */
 int svs_device_info(char *buf, int buflen);
 

@@ -70,6 +70,13 @@ def lib():
         L.oba_optimize.argtypes = [C.POINTER(OBAProblem), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                    c_dp, c_dp, C.POINTER(OBAStats)]
         L.oba_optimize.restype = C.c_int
+        L.ofast_detect_roi.argtypes = [c_up, C.c_int] + [C.c_int] * 5 + [c_ip, C.c_int]
+        L.ofast_detect.argtypes = [c_up, C.c_int, C.c_void_p, C.c_int, c_ip, C.c_int, c_ip]
+        L.ofast_detect_adaptively.argtypes = [c_up, C.c_int, C.c_void_p, C.c_int, c_ip, C.c_int, c_ip]
+        L.ofast_score.argtypes = [c_up, C.c_int, C.c_int, C.c_int]
+        L.ofast_is_corner.argtypes = [c_up, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ofast_grid_init.argtypes = [C.c_void_p] + [C.c_int] * 9
+        L.ofast_grid_init.restype = None
     return _LIB
 
 
@@ -186,3 +193,68 @@ def optimize(pb, num_iters, robust=True, delta=1.0, lambda_init=50.0, max_trials
                  lambda_iter=list(st.lambda_iter[:max(it, 0)]), trials_iter=list(st.trials_iter[:max(it, 0)]),
                  nnzb_S=st.nnzb_S, nnzb_L=st.nnzb_L)
     return poses, psi, stats
+
+
+# ------------------------------------------------------------------ FAST grid (fast_oracle.c)
+
+class OFastCell(C.Structure):
+    _fields_ = [("u0", C.c_int), ("u1", C.c_int), ("v0", C.c_int), ("v1", C.c_int), ("thr", C.c_int)]
+
+
+OFAST_MAX_CELLS = 64
+
+
+class OFastGrid(C.Structure):
+    _fields_ = [("grid_w", C.c_int), ("grid_h", C.c_int), ("fast_min", C.c_int), ("fast_max", C.c_int),
+                ("min_inner", C.c_int), ("min_outer", C.c_int), ("max_inner", C.c_int), ("max_outer", C.c_int),
+                ("cells", OFastCell * OFAST_MAX_CELLS)]
+
+
+def fast_grid(img_w, img_h, num_features_per_cell, boundary_per_cell, fast_thr, grid_w, grid_h,
+              fast_min=10, fast_max=40):
+    g = OFastGrid()
+    lib().ofast_grid_init(C.byref(g), img_w, img_h, num_features_per_cell, boundary_per_cell, fast_thr,
+                          grid_w, grid_h, fast_min, fast_max)
+    return g
+
+
+def _u8(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    return img, img.ctypes.data_as(c_up), img.strides[0]
+
+
+def fast_detect_roi(img, u0, u1, v0, v1, thr, max_out=200000):
+    img, p, pitch = _u8(img)
+    out = np.zeros((max_out, 2), np.int32)
+    n = lib().ofast_detect_roi(p, pitch, u0, u1, v0, v1, thr, _ip(out), max_out)
+    return out[:min(n, max_out)].copy()
+
+
+def fast_detect(img, cells, max_out=200000):
+    """cells: list of (u0,u1,v0,v1,thr).  Returns (xy[n,2], cell_off[ncells+1])."""
+    img, p, pitch = _u8(img)
+    arr = (OFastCell * len(cells))(*[OFastCell(*c) for c in cells])
+    out = np.zeros((max_out, 2), np.int32)
+    off = np.zeros(len(cells) + 1, np.int32)
+    n = lib().ofast_detect(p, pitch, arr, len(cells), _ip(out), max_out, _ip(off))
+    return out[:min(n, max_out)].copy(), off
+
+
+def fast_detect_adaptively(img, grid, trials, max_out=200000):
+    """Mutates grid (cell thresholds), like FastGrid::detectAdaptively."""
+    img, p, pitch = _u8(img)
+    out = np.zeros((max_out, 2), np.int32)
+    off = np.zeros(grid.grid_w * grid.grid_h + 1, np.int32)
+    n = lib().ofast_detect_adaptively(p, pitch, C.byref(grid), trials, _ip(out), max_out, _ip(off))
+    return out[:min(n, max_out)].copy(), off
+
+
+def fast_score_map(img):
+    img, p, pitch = _u8(img)
+    h, w = img.shape
+    s = np.full((h, w), -1, np.int32)
+    L = lib()
+    for y in range(3, h - 3):
+        for x in range(3, w - 3):
+            s[y, x] = L.ofast_score(p, pitch, x, y)
+    return s

@@ -53,10 +53,21 @@ class SvsBaStats(C.Structure):
         return d
 
 
+class SvsFastCell(C.Structure):
+    _fields_ = [("u0", C.c_int), ("u1", C.c_int), ("v0", C.c_int), ("v1", C.c_int), ("thr", C.c_int)]
+
+
+class SvsFastGridParams(C.Structure):
+    _fields_ = [("grid_w", C.c_int), ("grid_h", C.c_int), ("fast_min", C.c_int), ("fast_max", C.c_int),
+                ("min_inner", C.c_int), ("min_outer", C.c_int), ("max_inner", C.c_int), ("max_outer", C.c_int)]
+
+
 EXPORTS = [
     "svs_ba_create", "svs_ba_destroy", "svs_last_error", "svs_ba_set_problem", "svs_ba_optimize",
     "svs_ba_get_poses", "svs_ba_get_points", "svs_ba_reset_state", "svs_optimiseInnerAndOuterWindow",
     "svs_ba_chi2", "svs_ba_reduced_system", "svs_ba_solve_reduced", "svs_device_info",
+    "svs_fast_create", "svs_fast_destroy", "svs_fast_last_error", "svs_fast_grid_init", "svs_fast_set_image",
+    "svs_fast_set_image_device", "svs_fast_detect", "svs_fast_detect_adaptively",
 ]
 
 
@@ -86,6 +97,17 @@ def lib():
     L.svs_ba_reduced_system.argtypes = [vp, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp]
     L.svs_ba_solve_reduced.argtypes = [vp, C.c_int, C.c_double, C.c_double, c_dp]
     L.svs_device_info.argtypes = [C.c_char_p, C.c_int]
+    L.svs_fast_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.svs_fast_destroy.argtypes = [vp]
+    L.svs_fast_destroy.restype = None
+    L.svs_fast_last_error.argtypes = [vp]
+    L.svs_fast_last_error.restype = C.c_char_p
+    L.svs_fast_grid_init.argtypes = [C.c_int] * 9 + [C.POINTER(SvsFastGridParams), C.POINTER(SvsFastCell)]
+    L.svs_fast_set_image.argtypes = [vp, c_up, C.c_int, C.c_int, C.c_int]
+    L.svs_fast_set_image_device.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.svs_fast_detect.argtypes = [vp, C.POINTER(SvsFastCell), C.c_int, c_ip, C.c_int, c_ip]
+    L.svs_fast_detect_adaptively.argtypes = [vp, C.POINTER(SvsFastGridParams), C.POINTER(SvsFastCell), C.c_int,
+                                             c_ip, C.c_int, c_ip]
     _LIB = L
     return L
 
@@ -217,3 +239,77 @@ class BundleAdjuster:
             raise SvsError(it + 100, lib().svs_last_error(self._h).decode())
         self.P, self.L = pb.P, pb.L
         return it, k["pose_qt"], k["psi"], st.as_dict()
+
+
+class FastGrid:
+    """Host-side mirror of ScaViSLAM's FastGrid (reference fast_grid.h:30-64): same constructor
+    arguments, detect / detectAdaptively on the GPU through the C ABI.  Keypoints come back as
+    (xy[n,2] int32, cell_off[ncells+1]); the quadtree content of keypoint i in cell c is
+    i - cell_off[c]."""
+
+    def __init__(self, img_w, img_h, num_features_per_cell, boundary_per_cell, fast_thr, grid_w, grid_h,
+                 fast_min=10, fast_max=40, device=-1, max_keypoints=200000):
+        self._h = C.c_void_p()
+        rc = lib().svs_fast_create(device, img_w, img_h, max_keypoints, C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_fast_create failed (no CUDA device? there is no CPU fallback)")
+        self.params = SvsFastGridParams()
+        self.cells = (SvsFastCell * (grid_w * grid_h))()
+        rc = lib().svs_fast_grid_init(img_w, img_h, num_features_per_cell, boundary_per_cell, fast_thr, grid_w,
+                                      grid_h, fast_min, fast_max, C.byref(self.params), self.cells)
+        if rc != 0:
+            raise SvsError(rc, "svs_fast_grid_init")
+        self.max_kp = max_keypoints
+        self.ncells = grid_w * grid_h
+
+    def close(self):
+        if self._h:
+            lib().svs_fast_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, rc):
+        raise SvsError(rc, lib().svs_fast_last_error(self._h).decode())
+
+    def set_image(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        rc = lib().svs_fast_set_image(self._h, img.ctypes.data_as(c_up), img.strides[0], img.shape[1], img.shape[0])
+        if rc != 0:
+            self._err(rc)
+
+    def set_image_device(self, ptr, pitch, w, h):
+        rc = lib().svs_fast_set_image_device(self._h, C.c_void_p(ptr), pitch, w, h)
+        if rc != 0:
+            self._err(rc)
+
+    def cell_list(self):
+        return [(c.u0, c.u1, c.v0, c.v1, c.thr) for c in self.cells]
+
+    def detect(self, cells=None):
+        """FastGrid::detect(img, cell_grid2d, qt) with static per-cell thresholds."""
+        if cells is None:
+            arr, n = self.cells, self.ncells
+        else:
+            n = len(cells)
+            arr = (SvsFastCell * n)(*[SvsFastCell(*c) for c in cells])
+        out = np.zeros((self.max_kp, 2), np.int32)
+        off = np.zeros(n + 1, np.int32)
+        tot = lib().svs_fast_detect(self._h, arr, n, _ip(out), self.max_kp, _ip(off))
+        if tot < 0:
+            self._err(tot)
+        return out[:min(tot, self.max_kp)].copy(), off
+
+    def detect_adaptively(self, trials):
+        """FastGrid::detectAdaptively(img, trials, qt); updates the per-cell thresholds in place."""
+        out = np.zeros((self.max_kp, 2), np.int32)
+        off = np.zeros(self.ncells + 1, np.int32)
+        tot = lib().svs_fast_detect_adaptively(self._h, C.byref(self.params), self.cells, int(trials), _ip(out),
+                                               self.max_kp, _ip(off))
+        if tot < 0:
+            self._err(tot)
+        return out[:min(tot, self.max_kp)].copy(), off
