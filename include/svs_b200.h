@@ -183,6 +183,104 @@ int svs_fast_detect(svs_fast *h, const svs_fast_cell *cells, int ncells, int *ou
 int svs_fast_detect_adaptively(svs_fast *h, const svs_fast_grid_params *grid, svs_fast_cell *cells, int trials,
                                int *out_xy, int max_out, int *cell_off);
 
+/* ------------------------------------------------------------------ dense photometric tracker */
+
+typedef struct svs_dt svs_dt;
+
+#define SVS_DT_MAX_LEVELS 8
+/* Bilinear taps with exact float weights instead of the texture unit's 8-fractional-bit weights
+ * (the reference binds the images as linearly filtered textures, gpu/dense_tracking.cu:285-287). */
+#define SVS_DT_EXACT_BILINEAR 1
+
+typedef struct {
+  double chi2[SVS_DT_MAX_LEVELS];   /* final photometric chi2 per level */
+  int passes[SVS_DT_MAX_LEVELS];    /* fused (chi2 + J^T J + J^T r) pixel passes per level */
+  int launches;
+  float ms_total;
+} svs_dt_stats;
+
+/* Replaces GpuTracker::GpuTracker (gpu/dense_tracking.cu:265-299) + the GpuMat members of
+ * DenseTracker / FrameData: device images for `nlevels` pyramid levels of a w0 x h0 frame. */
+int svs_dt_create(int device, int w0, int h0, int nlevels, int flags, svs_dt **out);
+void svs_dt_destroy(svs_dt *h);
+const char *svs_dt_last_error(const svs_dt *h);
+
+/* GpuIntrinsics::set (gpu/dense_tracking.cuh:28-41) of level l (cam_vec[l], dense_tracking.cpp:82-84) */
+int svs_dt_set_intrinsics(svs_dt *h, int level, float focal_length, float px, float py);
+/* The float images GpuTracker::bindTexture / jacobianReduction take (dense_tracking.cpp:88-104):
+ * previous-frame intensity, current intensity and its x/y derivatives; host buffers with
+ * `stride_floats` floats per row; NULL keeps the resident plane. */
+int svs_dt_set_images(svs_dt *h, int level, const float *prev, const float *cur, const float *dx,
+                      const float *dy, int stride_floats);
+/* frame_data_.gpu_disp_32f (level-0 disparity) for computePointCloud */
+int svs_dt_set_disparity(svs_dt *h, const float *disp, int stride_floats, int w, int height);
+/* DenseTracker::computeDensePointCloudGpu (dense_tracking.cpp:195-216): cams[nlevels] are the
+ * per-level StereoCamera parameters (frame_grabber-impl.cpp:50-59). */
+int svs_dt_compute_point_cloud(svs_dt *h, const double T_cur_from_actkey[7], const svs_cam *cams);
+/* dev_ref_dense_points_[level] as packed float4 (w*h*4 floats) */
+int svs_dt_set_point_cloud(svs_dt *h, int level, const float *cloud_xyzw);
+int svs_dt_get_point_cloud(svs_dt *h, int level, float *cloud_xyzw);
+/* GpuTracker::chi2 (gpu/dense_tracking.cu:455-491) */
+int svs_dt_chi2(svs_dt *h, int level, const double T_cur_from_prev[7], double *chi2);
+/* GpuTracker::jacobianReduction (gpu/dense_tracking.cu:318-356): Hessian in GpuSymMatrix6 packing
+ * (21 values: for r: for c <= r), jacobian_times_res (6) */
+int svs_dt_jacobian_reduction(svs_dt *h, int level, const double T_cur_from_prev[7], double H21[21],
+                              double b6[6], double *chi2);
+/* DenseTracker::denseTrackingGpu (dense_tracking.cpp:62-193): coarse-to-fine LM, T updated in place */
+int svs_dt_track(svs_dt *h, double T_cur_from_actkey[7], svs_dt_stats *stats);
+
+/* ------------------------------------------------------------------ guided patch matcher */
+
+typedef struct svs_matcher svs_matcher;
+#define SVS_MATCH_MAX_LEVELS 4
+
+/* cam_vec[level] (LinearCamera part of StereoCamera): image size, focal length, principal point */
+typedef struct {
+  int w, h;
+  double f, px, py;
+} svs_match_level;
+
+/* CandidatePoint<3> (data_structures.h): anchor keyframe (slot given to svs_matcher_set_keyframe,
+ * -1 = not in vertex_map), xyz in the anchor frame, its (u, v) observation at anchor_level */
+typedef struct {
+  int keyframe;
+  int anchor_level;
+  double xyz_anchor[3];
+  double anchor_obs_pyr[2];
+} svs_match_point;
+
+/* One entry per candidate point, in input order.  matched == 1 entries, in order, are what the
+ * reference appends to TrackData::obs_list / point_list / ba2globalptr. */
+typedef struct {
+  int predicted;       /* computePrediction succeeded */
+  int textured;        /* key patch passed the thr_std test */
+  int matched;         /* a candidate beat thr_mean and the disparity is valid */
+  int n_candidates;    /* FAST corners inside the search window */
+  int index;           /* quadtree content of the best candidate, -1 = none */
+  int min_dist;        /* its score (literal formula of matcher.cpp:73) */
+  int uv_pyr[2];       /* its position at anchor_level */
+  double obs[3];       /* (u, v, u_right) at level 0 */
+  double xyz_actkey[3];
+} svs_match_result;
+
+int svs_matcher_create(int device, int nlevels, const svs_match_level *levels, int max_keyframes, int max_points,
+                     int max_keypoints, svs_matcher **out);
+void svs_matcher_destroy(svs_matcher *h);
+const char *svs_matcher_last_error(const svs_matcher *h);
+/* keyframe_map[id].pyr + vertex_map[id].T_me_from_w for one anchor keyframe (uint8 pyramid, host) */
+int svs_matcher_set_keyframe(svs_matcher *h, int slot, const double T_me_from_w[7], const unsigned char *const *pyr,
+                           const int *pitch);
+/* cur_frame.pyr + cur_frame.disp (level-0 float disparity, may be NULL to keep) */
+int svs_matcher_set_current(svs_matcher *h, const unsigned char *const *pyr, const int *pitch, const float *disp,
+                          int disp_pitch_floats);
+/* feature_tree.at(level): the FAST corners (x, y) and their quadtree content (index within the cell) */
+int svs_matcher_set_features(svs_matcher *h, int level, const int *xy, const int *content, int n);
+/* GuidedMatcher<StereoCamera>::match (matcher.cpp:312-398).  T_actkey_from_w replaces
+ * vertex_map[actkey_id].  Returns the number of matched points or a negative SVS_ERR_*. */
+int svs_match(svs_matcher *h, const double T_cur_from_actkey[7], const double T_actkey_from_w[7],
+              const svs_match_point *pts, int n, int search_radius, int thr_mean, int thr_std,
+              svs_match_result *out);
+
 /* Library/device info: writes "name;sm;SMs;..." into buf. */
 int svs_device_info(char *buf, int buflen);
 

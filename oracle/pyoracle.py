@@ -20,6 +20,37 @@ c_ip = C.POINTER(C.c_int)
 c_up = C.POINTER(C.c_ubyte)
 
 
+c_fp = C.POINTER(C.c_float)
+ODT_MAX_LEVELS = 8
+
+
+class ODtLevel(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("stride", C.c_int), ("cloud_stride", C.c_int),
+                ("f", C.c_float), ("px", C.c_float), ("py", C.c_float),
+                ("prev", c_fp), ("cur", c_fp), ("dx", c_fp), ("dy", c_fp), ("cloud", c_fp)]
+
+
+class ODtStats(C.Structure):
+    _fields_ = [("chi2", C.c_double * ODT_MAX_LEVELS), ("passes", C.c_int * ODT_MAX_LEVELS)]
+
+
+OMATCH_MAX_LEVELS = 4
+
+
+class OMatchLevel(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("f", C.c_double), ("px", C.c_double), ("py", C.c_double)]
+
+
+class OMatchFrame(C.Structure):
+    _fields_ = [("levels", OMatchLevel * OMATCH_MAX_LEVELS), ("pyr", c_up * OMATCH_MAX_LEVELS),
+                ("pitch", C.c_int * OMATCH_MAX_LEVELS), ("disp", c_fp), ("disp_pitch", C.c_int),
+                ("trees", C.c_void_p * OMATCH_MAX_LEVELS)]
+
+
+class OMatchKeyframe(C.Structure):
+    _fields_ = [("T_me_from_w", C.c_double * 7), ("pyr", c_up * OMATCH_MAX_LEVELS), ("pitch", C.c_int * OMATCH_MAX_LEVELS)]
+
+
 class OBAProblem(C.Structure):
     _fields_ = [("P", C.c_int), ("L", C.c_int), ("E", C.c_int), ("C", C.c_int),
                 ("pose_qt", c_dp), ("fixed", c_up), ("psi", c_dp),
@@ -77,6 +108,24 @@ def lib():
         L.ofast_is_corner.argtypes = [c_up, C.c_int, C.c_int, C.c_int, C.c_int]
         L.ofast_grid_init.argtypes = [C.c_void_p] + [C.c_int] * 9
         L.ofast_grid_init.restype = None
+        c_fp = C.POINTER(C.c_float)
+        L.odt_pass.argtypes = [C.POINTER(ODtLevel), c_dp, C.c_int, c_dp, c_dp, c_dp, c_ip]
+        L.odt_pass.restype = None
+        L.odt_track.argtypes = [C.POINTER(ODtLevel), C.c_int, c_dp, C.c_int, C.POINTER(ODtStats)]
+        L.odt_track.restype = None
+        L.odt_point_cloud.argtypes = [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]
+        L.odt_point_cloud.restype = None
+        L.odt_make_TQ.argtypes = [c_dp, C.c_double, C.c_double, C.c_double, C.c_double, c_fp]
+        L.odt_make_TQ.restype = None
+        L.omatch_tree_build.argtypes = [C.c_int, C.c_int, c_ip, c_ip, C.c_int]
+        L.omatch_tree_build.restype = C.c_void_p
+        L.omatch_tree_free.argtypes = [C.c_void_p]
+        L.omatch_tree_free.restype = None
+        L.omatch_tree_query.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.c_int]
+        L.omatch_warp_affine.argtypes = [c_up, C.c_int, C.POINTER(OMatchLevel), c_dp, C.c_double, c_dp, C.c_int, c_up]
+        L.omatch_warp_affine.restype = None
+        L.omatch_match.argtypes = [C.POINTER(OMatchFrame), C.POINTER(OMatchKeyframe), C.c_int, c_dp, c_dp, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p]
     return _LIB
 
 
@@ -258,3 +307,110 @@ def fast_score_map(img):
         for x in range(3, w - 3):
             s[y, x] = L.ofast_score(p, pitch, x, y)
     return s
+
+
+# ------------------------------------------------------------------ dense tracker (dt_oracle.c)
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def dt_levels(levels):
+    """levels: list of dicts(prev, cur, dx, dy, cloud[h,w,4], f, px, py).  Returns (array, keepalive)."""
+    arr = (ODtLevel * len(levels))()
+    keep = []
+    for i, lv in enumerate(levels):
+        ims = {k: _f32(lv[k]) for k in ("prev", "cur", "dx", "dy", "cloud")}
+        keep.append(ims)
+        h, w = ims["prev"].shape
+        arr[i] = ODtLevel(w, h, w, w, float(lv["f"]), float(lv["px"]), float(lv["py"]),
+                          *[ims[k].ctypes.data_as(c_fp) for k in ("prev", "cur", "dx", "dy", "cloud")])
+    return arr, keep
+
+
+def dt_pass(level, T, exact=False, want_jac=True):
+    arr, keep = dt_levels([level])
+    T = np.ascontiguousarray(T, np.float64)
+    chi = C.c_double()
+    n = C.c_int()
+    H, b = np.zeros(21), np.zeros(6)
+    lib().odt_pass(arr, _dp(T), int(exact), C.byref(chi), _dp(H) if want_jac else None, _dp(b) if want_jac else None,
+                   C.byref(n))
+    return chi.value, H, b, n.value
+
+
+def dt_track(levels, T, exact=False):
+    arr, keep = dt_levels(levels)
+    T = np.ascontiguousarray(T, np.float64).copy()
+    st = ODtStats()
+    lib().odt_track(arr, len(levels), _dp(T), int(exact), C.byref(st))
+    return T, dict(chi2=list(st.chi2[:len(levels)]), passes=list(st.passes[:len(levels)]))
+
+
+def dt_point_cloud(T, cam, disp, level, w, h):
+    """cam = (f, px, py, b) of the level camera; disp = level-0 float disparity."""
+    TQ = np.zeros(16, np.float32)
+    T = np.ascontiguousarray(T, np.float64)
+    lib().odt_make_TQ(_dp(T), float(cam[0]), float(cam[1]), float(cam[2]), float(cam[3]), TQ.ctypes.data_as(c_fp))
+    d = _f32(disp)
+    out = np.zeros((h, w, 4), np.float32)
+    lib().odt_point_cloud(TQ.ctypes.data_as(c_fp), d.ctypes.data_as(c_fp), w, h, d.shape[1], w, 1 << level,
+                          out.ctypes.data_as(c_fp))
+    return out
+
+
+# ------------------------------------------------------------------ guided matcher (match_oracle.c)
+
+MATCH_RESULT_DTYPE = np.dtype([("predicted", "i4"), ("textured", "i4"), ("matched", "i4"), ("n_candidates", "i4"),
+                               ("index", "i4"), ("min_dist", "i4"), ("uv_pyr", "i4", 2), ("obs", "f8", 3),
+                               ("xyz_actkey", "f8", 3)])
+MATCH_POINT_DTYPE = np.dtype([("keyframe", "i4"), ("anchor_level", "i4"), ("xyz_anchor", "f8", 3),
+                              ("anchor_obs_pyr", "f8", 2)])
+
+
+class QuadTree:
+    """QuadTree<int>(Rectangle(0, 0, w, h), 1) filled with (x, y) -> content (quadtree.h)."""
+
+    def __init__(self, w, h, xy, content=None):
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        c = None if content is None else np.ascontiguousarray(content, np.int32)
+        self.ptr = lib().omatch_tree_build(w, h, _ip(xy), None if c is None else _ip(c), len(xy))
+
+    def query(self, x, y, w, h, max_out=4096):
+        out = np.zeros((max_out, 3), np.int32)
+        n = lib().omatch_tree_query(self.ptr, x, y, w, h, _ip(out), max_out)
+        return out[:min(n, max_out)].copy()
+
+    def __del__(self):
+        try:
+            lib().omatch_tree_free(self.ptr)
+        except Exception:
+            pass
+
+
+def match(levels, cur_pyr, disp, trees, keyframes, T_cur_from_actkey, T_actkey_from_w, points, search_radius,
+          thr_mean, thr_std):
+    """levels: [(w,h,f,px,py)], cur_pyr: uint8 images, trees: [QuadTree], keyframes: [(T, pyr)]."""
+    fr = OMatchFrame()
+    keep = []
+    for l, (w, h, f, px, py) in enumerate(levels):
+        fr.levels[l] = OMatchLevel(int(w), int(h), float(f), float(px), float(py))
+        im = np.ascontiguousarray(cur_pyr[l], np.uint8); keep.append(im)
+        fr.pyr[l] = im.ctypes.data_as(c_up); fr.pitch[l] = im.strides[0]
+        fr.trees[l] = trees[l].ptr
+    d = _f32(disp); keep.append(d)
+    fr.disp = d.ctypes.data_as(c_fp); fr.disp_pitch = d.shape[1]
+    kfs = (OMatchKeyframe * len(keyframes))()
+    for k, (T, pyr) in enumerate(keyframes):
+        for i in range(7):
+            kfs[k].T_me_from_w[i] = float(T[i])
+        for l in range(len(levels)):
+            im = np.ascontiguousarray(pyr[l], np.uint8); keep.append(im)
+            kfs[k].pyr[l] = im.ctypes.data_as(c_up); kfs[k].pitch[l] = im.strides[0]
+    pts = np.ascontiguousarray(points, MATCH_POINT_DTYPE)
+    out = np.zeros(len(pts), MATCH_RESULT_DTYPE)
+    Ta = np.ascontiguousarray(T_cur_from_actkey, np.float64)
+    Tb = np.ascontiguousarray(T_actkey_from_w, np.float64)
+    lib().omatch_match(C.byref(fr), kfs, len(keyframes), _dp(Ta), _dp(Tb), pts.ctypes.data, len(pts),
+                       int(search_radius), int(thr_mean), int(thr_std), out.ctypes.data)
+    return out

@@ -62,12 +62,48 @@ class SvsFastGridParams(C.Structure):
                 ("min_inner", C.c_int), ("min_outer", C.c_int), ("max_inner", C.c_int), ("max_outer", C.c_int)]
 
 
+SVS_DT_MAX_LEVELS = 8
+SVS_DT_EXACT_BILINEAR = 1
+
+
+class SvsDtStats(C.Structure):
+    _fields_ = [("chi2", C.c_double * SVS_DT_MAX_LEVELS), ("passes", C.c_int * SVS_DT_MAX_LEVELS),
+                ("launches", C.c_int), ("ms_total", C.c_float)]
+
+
+class SvsMatchLevel(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("f", C.c_double), ("px", C.c_double), ("py", C.c_double)]
+
+
+class SvsMatchPoint(C.Structure):
+    _fields_ = [("keyframe", C.c_int), ("anchor_level", C.c_int), ("xyz_anchor", C.c_double * 3),
+                ("anchor_obs_pyr", C.c_double * 2)]
+
+
+class SvsMatchResult(C.Structure):
+    _fields_ = [("predicted", C.c_int), ("textured", C.c_int), ("matched", C.c_int), ("n_candidates", C.c_int),
+                ("index", C.c_int), ("min_dist", C.c_int), ("uv_pyr", C.c_int * 2), ("obs", C.c_double * 3),
+                ("xyz_actkey", C.c_double * 3)]
+
+
+MATCH_RESULT_DTYPE = np.dtype([("predicted", "i4"), ("textured", "i4"), ("matched", "i4"), ("n_candidates", "i4"),
+                               ("index", "i4"), ("min_dist", "i4"), ("uv_pyr", "i4", 2), ("obs", "f8", 3),
+                               ("xyz_actkey", "f8", 3)])
+MATCH_POINT_DTYPE = np.dtype([("keyframe", "i4"), ("anchor_level", "i4"), ("xyz_anchor", "f8", 3),
+                              ("anchor_obs_pyr", "f8", 2)])
+
+
 EXPORTS = [
     "svs_ba_create", "svs_ba_destroy", "svs_last_error", "svs_ba_set_problem", "svs_ba_optimize",
     "svs_ba_get_poses", "svs_ba_get_points", "svs_ba_reset_state", "svs_optimiseInnerAndOuterWindow",
     "svs_ba_chi2", "svs_ba_reduced_system", "svs_ba_solve_reduced", "svs_device_info",
     "svs_fast_create", "svs_fast_destroy", "svs_fast_last_error", "svs_fast_grid_init", "svs_fast_set_image",
     "svs_fast_set_image_device", "svs_fast_detect", "svs_fast_detect_adaptively",
+    "svs_dt_create", "svs_dt_destroy", "svs_dt_last_error", "svs_dt_set_intrinsics", "svs_dt_set_images",
+    "svs_dt_set_disparity", "svs_dt_compute_point_cloud", "svs_dt_set_point_cloud", "svs_dt_get_point_cloud",
+    "svs_dt_chi2", "svs_dt_jacobian_reduction", "svs_dt_track",
+    "svs_matcher_create", "svs_matcher_destroy", "svs_matcher_last_error", "svs_matcher_set_keyframe",
+    "svs_matcher_set_current", "svs_matcher_set_features", "svs_match",
 ]
 
 
@@ -108,6 +144,32 @@ def lib():
     L.svs_fast_detect.argtypes = [vp, C.POINTER(SvsFastCell), C.c_int, c_ip, C.c_int, c_ip]
     L.svs_fast_detect_adaptively.argtypes = [vp, C.POINTER(SvsFastGridParams), C.POINTER(SvsFastCell), C.c_int,
                                              c_ip, C.c_int, c_ip]
+    c_fp = C.POINTER(C.c_float)
+    L.svs_dt_create.argtypes = [C.c_int] * 5 + [C.POINTER(vp)]
+    L.svs_dt_destroy.argtypes = [vp]
+    L.svs_dt_destroy.restype = None
+    L.svs_dt_last_error.argtypes = [vp]
+    L.svs_dt_last_error.restype = C.c_char_p
+    L.svs_dt_set_intrinsics.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.c_float]
+    L.svs_dt_set_images.argtypes = [vp, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_int]
+    L.svs_dt_set_disparity.argtypes = [vp, c_fp, C.c_int, C.c_int, C.c_int]
+    L.svs_dt_compute_point_cloud.argtypes = [vp, c_dp, C.POINTER(SvsCam)]
+    L.svs_dt_set_point_cloud.argtypes = [vp, C.c_int, c_fp]
+    L.svs_dt_get_point_cloud.argtypes = [vp, C.c_int, c_fp]
+    L.svs_dt_chi2.argtypes = [vp, C.c_int, c_dp, c_dp]
+    L.svs_dt_jacobian_reduction.argtypes = [vp, C.c_int, c_dp, c_dp, c_dp, c_dp]
+    L.svs_dt_track.argtypes = [vp, c_dp, C.POINTER(SvsDtStats)]
+    ucpp = C.POINTER(C.POINTER(C.c_ubyte))
+    L.svs_matcher_create.argtypes = [C.c_int, C.c_int, C.POINTER(SvsMatchLevel), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.svs_matcher_destroy.argtypes = [vp]
+    L.svs_matcher_destroy.restype = None
+    L.svs_matcher_last_error.argtypes = [vp]
+    L.svs_matcher_last_error.restype = C.c_char_p
+    L.svs_matcher_set_keyframe.argtypes = [vp, C.c_int, c_dp, ucpp, c_ip]
+    L.svs_matcher_set_current.argtypes = [vp, ucpp, c_ip, c_fp, C.c_int]
+    L.svs_matcher_set_features.argtypes = [vp, C.c_int, c_ip, c_ip, C.c_int]
+    L.svs_match.argtypes = [vp, c_dp, c_dp, C.POINTER(SvsMatchPoint), C.c_int, C.c_int, C.c_int, C.c_int,
+                            C.POINTER(SvsMatchResult)]
     _LIB = L
     return L
 
@@ -313,3 +375,145 @@ class FastGrid:
         if tot < 0:
             self._err(tot)
         return out[:min(tot, self.max_kp)].copy(), off
+
+
+class DenseTracker:
+    """Host-side mirror of DenseTracker / GpuTracker (reference dense_tracking.h:40-96,
+    gpu/dense_tracking.cuh:276-342) on top of the C ABI."""
+
+    def __init__(self, w0, h0, nlevels=3, flags=0, device=-1):
+        self._h = C.c_void_p()
+        rc = lib().svs_dt_create(device, w0, h0, nlevels, flags, C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_dt_create failed (no CUDA device? there is no CPU fallback)")
+        self.w0, self.h0, self.nlevels = w0, h0, nlevels
+
+    def close(self):
+        if self._h:
+            lib().svs_dt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SvsError(rc, lib().svs_dt_last_error(self._h).decode())
+
+    @staticmethod
+    def _fp(a):
+        return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def set_intrinsics(self, level, f, px, py):
+        self._ck(lib().svs_dt_set_intrinsics(self._h, level, f, px, py))
+
+    def set_images(self, level, prev=None, cur=None, dx=None, dy=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float32) for a in (prev, cur, dx, dy)]
+        w = self.w0 >> level
+        self._ck(lib().svs_dt_set_images(self._h, level, *[self._fp(a) for a in arrs], w))
+
+    def set_disparity(self, disp):
+        d = np.ascontiguousarray(disp, np.float32)
+        self._ck(lib().svs_dt_set_disparity(self._h, self._fp(d), d.shape[1], d.shape[1], d.shape[0]))
+
+    def compute_point_cloud(self, T, cams):
+        arr = (SvsCam * len(cams))(*[SvsCam(*map(float, c)) for c in cams])
+        T = np.ascontiguousarray(T, np.float64)
+        self._ck(lib().svs_dt_compute_point_cloud(self._h, _dp(T), arr))
+
+    def set_point_cloud(self, level, cloud):
+        c = np.ascontiguousarray(cloud, np.float32)
+        self._ck(lib().svs_dt_set_point_cloud(self._h, level, self._fp(c)))
+
+    def get_point_cloud(self, level):
+        out = np.zeros((self.h0 >> level, self.w0 >> level, 4), np.float32)
+        self._ck(lib().svs_dt_get_point_cloud(self._h, level, self._fp(out)))
+        return out
+
+    def chi2(self, level, T):
+        T = np.ascontiguousarray(T, np.float64)
+        v = C.c_double()
+        self._ck(lib().svs_dt_chi2(self._h, level, _dp(T), C.byref(v)))
+        return v.value
+
+    def jacobian_reduction(self, level, T):
+        T = np.ascontiguousarray(T, np.float64)
+        H, b, v = np.zeros(21), np.zeros(6), C.c_double()
+        self._ck(lib().svs_dt_jacobian_reduction(self._h, level, _dp(T), _dp(H), _dp(b), C.byref(v)))
+        return H, b, v.value
+
+    def track(self, T):
+        T = np.ascontiguousarray(T, np.float64).copy()
+        st = SvsDtStats()
+        self._ck(lib().svs_dt_track(self._h, _dp(T), C.byref(st)))
+        return T, dict(chi2=list(st.chi2[:self.nlevels]), passes=list(st.passes[:self.nlevels]),
+                       launches=st.launches, ms_total=st.ms_total)
+
+
+class GuidedMatcher:
+    """Host-side mirror of GuidedMatcher<StereoCamera> (reference matcher.hpp:62-186)."""
+
+    def __init__(self, levels, max_keyframes=8, max_points=8192, max_keypoints=65536, device=-1):
+        """levels: list of (w, h, f, px, py) per pyramid level (cam_vec)."""
+        self._h = C.c_void_p()
+        arr = (SvsMatchLevel * len(levels))(*[SvsMatchLevel(int(w), int(h), float(f), float(px), float(py))
+                                              for (w, h, f, px, py) in levels])
+        rc = lib().svs_matcher_create(device, len(levels), arr, max_keyframes, max_points, max_keypoints,
+                                      C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_matcher_create failed (no CUDA device? there is no CPU fallback)")
+        self.nlevels = len(levels)
+
+    def close(self):
+        if self._h:
+            lib().svs_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SvsError(rc, lib().svs_matcher_last_error(self._h).decode())
+
+    def _pyr_args(self, pyr):
+        ims = [np.ascontiguousarray(p, np.uint8) for p in pyr]
+        ptrs = (C.POINTER(C.c_ubyte) * len(ims))(*[im.ctypes.data_as(c_up) for im in ims])
+        pitch = np.array([im.strides[0] for im in ims], np.int32)
+        return ims, ptrs, pitch
+
+    def set_keyframe(self, slot, T_me_from_w, pyr):
+        ims, ptrs, pitch = self._pyr_args(pyr)
+        T = np.ascontiguousarray(T_me_from_w, np.float64)
+        self._ck(lib().svs_matcher_set_keyframe(self._h, slot, _dp(T), ptrs, _ip(pitch)))
+
+    def set_current(self, pyr, disp=None):
+        ims, ptrs, pitch = self._pyr_args(pyr)
+        d = None if disp is None else np.ascontiguousarray(disp, np.float32)
+        self._ck(lib().svs_matcher_set_current(self._h, ptrs, _ip(pitch),
+                                               None if d is None else d.ctypes.data_as(C.POINTER(C.c_float)),
+                                               0 if d is None else d.shape[1]))
+
+    def set_features(self, level, xy, content):
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        content = np.ascontiguousarray(content, np.int32)
+        self._ck(lib().svs_matcher_set_features(self._h, level, _ip(xy), _ip(content), len(xy)))
+
+    def match(self, T_cur_from_actkey, T_actkey_from_w, points, search_radius, thr_mean, thr_std):
+        """points: structured array with MATCH_POINT_DTYPE.  Returns a MATCH_RESULT_DTYPE array."""
+        pts = np.ascontiguousarray(points, MATCH_POINT_DTYPE)
+        out = np.zeros(len(pts), MATCH_RESULT_DTYPE)
+        Ta = np.ascontiguousarray(T_cur_from_actkey, np.float64)
+        Tb = np.ascontiguousarray(T_actkey_from_w, np.float64)
+        rc = lib().svs_match(self._h, _dp(Ta), _dp(Tb), pts.ctypes.data_as(C.POINTER(SvsMatchPoint)), len(pts),
+                             int(search_radius), int(thr_mean), int(thr_std),
+                             out.ctypes.data_as(C.POINTER(SvsMatchResult)))
+        if rc < 0:
+            self._ck(rc)
+        return out

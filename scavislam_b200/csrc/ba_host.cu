@@ -7,6 +7,7 @@
 // when the device path is unavailable.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <set>
@@ -116,48 +117,43 @@ void free_arena(svs_ba* h) {
 // the pose graph, the role AMD plays inside LinearSolverCSparse), block fill, and the update
 // lists of the right-looking block Cholesky.
 struct Symbolic {
-  std::vector<int> perm, pos, col_ptr, row_idx, upd_ptr, upd_dst, upd_ab, tbl;
+  std::vector<int> perm, pos, col_ptr, row_idx, upd_ptr, upd_dst, upd_ab, urg_dst, tbl;
   int nblk = 0;
 };
 
 void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, Symbolic& sy) {
-  std::vector<std::set<int>> G(P);
+  // elimination graph as a byte matrix: P is a window of poses (hundreds to a few thousand)
+  std::vector<unsigned char> G((size_t)P * P, 0);
+  std::vector<int> deg(P, 0);
   for (int i = 0; i < P; ++i)
     for (int j : adj_in[i])
-      if (j != i) G[i].insert(j);
+      if (j != i && !G[(size_t)i * P + j]) { G[(size_t)i * P + j] = 1; ++deg[i]; }
   sy.perm.assign(P, 0);
   sy.pos.assign(P, 0);
-  std::vector<std::vector<int>> cols(P);  // by position: higher-position neighbours (as poses, fixed up later)
+  std::vector<std::vector<int>> cols(P);  // by position: neighbours still alive when eliminated (as poses)
   std::vector<char> done(P, 0);
-  // degree buckets via ordered set (degree, pose)
-  std::set<std::pair<int, int>> pq;
-  if (!natural)
-    for (int i = 0; i < P; ++i) pq.insert({(int)G[i].size(), i});
+  std::vector<int> nb;
   for (int step = 0; step < P; ++step) {
-    int v;
-    if (natural) {
-      v = step;
-    } else {
-      v = pq.begin()->second;
-      pq.erase(pq.begin());
+    int v = step;
+    if (!natural) {   // greedy minimum degree, ties to the lowest index
+      int best = 1 << 30;
+      for (int i = 0; i < P; ++i)
+        if (!done[i] && deg[i] < best) { best = deg[i]; v = i; }
     }
     done[v] = 1;
     sy.perm[step] = v;
     sy.pos[v] = step;
-    std::vector<int> nb(G[v].begin(), G[v].end());
+    nb.clear();
+    const unsigned char* row = G.data() + (size_t)v * P;
+    for (int j = 0; j < P; ++j)
+      if (row[j] && !done[j]) nb.push_back(j);
     cols[step] = nb;
-    for (int a : nb) {
-      if (!natural) pq.erase({(int)G[a].size(), a});
-      G[a].erase(v);
-    }
+    for (int a : nb) { G[(size_t)a * P + v] = 0; --deg[a]; }
     for (size_t x = 0; x < nb.size(); ++x)
       for (size_t y = x + 1; y < nb.size(); ++y) {
-        G[nb[x]].insert(nb[y]);
-        G[nb[y]].insert(nb[x]);
+        const int p = nb[x], q = nb[y];
+        if (!G[(size_t)p * P + q]) { G[(size_t)p * P + q] = 1; G[(size_t)q * P + p] = 1; ++deg[p]; ++deg[q]; }
       }
-    if (!natural)
-      for (int a : nb) pq.insert({(int)G[a].size(), a});
-    G[v].clear();
   }
   // column structures by position
   sy.col_ptr.assign(P + 1, 0);
@@ -188,8 +184,9 @@ void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, S
   for (int j = 0; j < P; ++j) {
     sy.upd_ptr[j] = (int)sy.upd_dst.size();
     const int base = sy.col_ptr[j] + 1, nb = sy.col_ptr[j + 1] - base;
-    for (int a = 0; a < nb; ++a)
-      for (int b = 0; b <= a; ++b) {
+    // b-major: the pairs (a, 0) that land in the next column to be factored come first
+    for (int b = 0; b < nb; ++b)
+      for (int a = b; a < nb; ++a) {
         const int ia = sy.row_idx[base + a], ib = sy.row_idx[base + b];  // ia >= ib
         const int t = sy.tbl[(size_t)sy.perm[ia] * P + sy.perm[ib]];
         sy.upd_dst.push_back(t >> 1);
@@ -197,6 +194,12 @@ void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, S
       }
   }
   sy.upd_ptr[P] = (int)sy.upd_dst.size();
+  // urg_dst[col_ptr[j] + 1 + a] = destination of pair (a, 0) of column j
+  sy.urg_dst.assign(sy.nblk, 0);
+  for (int j = 0; j < P; ++j) {
+    const int base = sy.col_ptr[j] + 1, nb = sy.col_ptr[j + 1] - base;
+    for (int a = 0; a < nb; ++a) sy.urg_dst[base + a] = sy.upd_dst[sy.upd_ptr[j] + a];
+  }
 }
 
 int fail(svs_ba* h, int code, const std::string& msg) {
@@ -276,62 +279,74 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   CK(cudaStreamSynchronize(h->stream));   // the arena and the staging buffer are about to be reused
   free_problem(h);
 
-  // ---- group edges per landmark
+  // ---- group edges per landmark (counting sort), flat arrays only: this runs on the caller's
+  //      thread inside the end-to-end time, like g2o's buildStructure does in the reference
   std::vector<int> eptr(L + 1, 0);
   for (int e = 0; e < E; ++e) eptr[e_point[e] + 1]++;
   for (int l = 0; l < L; ++l) eptr[l + 1] += eptr[l];
   std::vector<int> eord(E), fillp(eptr.begin(), eptr.end() - 1);
   for (int e = 0; e < E; ++e) eord[fillp[e_point[e]]++] = e;
-  struct Lm { int user, anchor, K, self; std::vector<int> poses; };
-  std::vector<Lm> lms(L);
+  // per landmark: anchor, self-observation flag, observer edges sorted by pose index (in place in eord)
+  std::vector<int> l_anchor(L, -1), l_K(L, 0);
+  std::vector<unsigned char> l_self(L, 0);
+  std::vector<unsigned long long> key(L);
   int Kmax = 1;
   for (int l = 0; l < L; ++l) {
-    Lm& m = lms[l];
-    m.user = l; m.anchor = -1; m.self = 0; m.K = 0;
     const int b = eptr[l], en = eptr[l + 1];
+    key[l] = ~0ull;   // landmarks without observations go last
     if (b == en) continue;
-    m.anchor = e_anchor[eord[b]];
+    const int anchor = e_anchor[eord[b]];
+    int nself = 0;
     for (int k = b; k < en; ++k) {
       const int e = eord[k];
-      if (e_anchor[e] != m.anchor)
+      if (e_anchor[e] != anchor)
         return fail(h, SVS_ERR_UNSUPPORTED, "edges of one point name different anchor frames");
-      if (e_pose[e] == m.anchor) m.self++;
-      else m.poses.push_back(e_pose[e]);
+      if (e_pose[e] == anchor) ++nself;
     }
-    std::sort(m.poses.begin(), m.poses.end());
-    if (m.self > 1 || std::adjacent_find(m.poses.begin(), m.poses.end()) != m.poses.end())
-      return fail(h, SVS_ERR_UNSUPPORTED, "a point is observed twice by the same frame");
-    m.K = 1 + (int)m.poses.size();
-    if (m.K > kMaxTrack) return fail(h, SVS_ERR_UNSUPPORTED, "landmark track longer than 31 frames + anchor");
-    Kmax = std::max(Kmax, m.K);
+    // insertion sort by (is-not-self, pose): the self edge first, then ascending pose index
+    for (int k = b + 1; k < en; ++k) {
+      const int e = eord[k];
+      const int ke = e_pose[e] == anchor ? -1 : e_pose[e];
+      int q = k - 1;
+      while (q >= b) {
+        const int f = eord[q];
+        const int kf = e_pose[f] == anchor ? -1 : e_pose[f];
+        if (kf <= ke) break;
+        eord[q + 1] = f;
+        --q;
+      }
+      eord[q + 1] = e;
+    }
+    for (int k = b + 1; k < en; ++k)
+      if (e_pose[eord[k]] == e_pose[eord[k - 1]])
+        return fail(h, SVS_ERR_UNSUPPORTED, "a point is observed twice by the same frame");
+    const int K = 1 + (en - b) - nself;
+    if (K > kMaxTrack) return fail(h, SVS_ERR_UNSUPPORTED, "landmark track longer than 31 frames + anchor");
+    l_anchor[l] = anchor; l_self[l] = (unsigned char)nself; l_K[l] = K;
+    Kmax = std::max(Kmax, K);
+    // locality key: anchor, then track shape (first and last observer), so that neighbouring warps
+    // of the fused kernel scatter into the same blocks of the reduced system
+    const unsigned long long first = (unsigned long long)(e_pose[eord[b + (nself ? 1 : 0) < en ? b + (nself ? 1 : 0) : b]] & 0xfffff);
+    const unsigned long long last = (unsigned long long)(e_pose[eord[en - 1]] & 0xfffff);
+    key[l] = ((unsigned long long)anchor << 44) | ((unsigned long long)(1 - nself) << 43) |
+             ((unsigned long long)K << 40) | (first << 20) | last;
   }
-  // internal landmark order: by (anchor, pose set) so that neighbours in a CTA hit the same blocks
   std::vector<int> order(L);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    const Lm &x = lms[a], &y = lms[b];
-    if (x.anchor != y.anchor) return x.anchor < y.anchor;
-    if (x.self != y.self) return x.self > y.self;
-    return x.poses < y.poses;
-  });
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
   h->lm_to_user = order;
   std::vector<int> lm_eptr(L + 1, 0), lm_sptr(L + 1, 0), lm_anchor(L, 0), ie_pose(E);
   std::vector<unsigned char> lm_self(L, 0);
   std::vector<double> ie_obs(3 * (size_t)E), ie_w(3 * (size_t)E), ipsi(3 * (size_t)L);
   int ne = 0, ns = 0;
   for (int li = 0; li < L; ++li) {
-    const Lm& m = lms[order[li]];
+    const int l = order[li];
     lm_eptr[li] = ne; lm_sptr[li] = ns;
-    for (int q = 0; q < 3; ++q) ipsi[3 * (size_t)li + q] = psi[3 * (size_t)m.user + q];
-    if (m.anchor < 0) continue;
-    lm_anchor[li] = m.anchor; lm_self[li] = (unsigned char)m.self;
-    // self edge first, then observers by ascending pose index
-    std::vector<int> es(eord.begin() + eptr[m.user], eord.begin() + eptr[m.user + 1]);
-    std::sort(es.begin(), es.end(), [&](int a, int b) {
-      const int ka = e_pose[a] == m.anchor ? -1 : e_pose[a], kb = e_pose[b] == m.anchor ? -1 : e_pose[b];
-      return ka < kb;
-    });
-    for (int e : es) {
+    for (int q = 0; q < 3; ++q) ipsi[3 * (size_t)li + q] = psi[3 * (size_t)l + q];
+    if (l_anchor[l] < 0) continue;
+    lm_anchor[li] = l_anchor[l]; lm_self[li] = l_self[l];
+    for (int k = eptr[l]; k < eptr[l + 1]; ++k) {
+      const int e = eord[k];
       ie_pose[ne] = e_pose[e];
       for (int q = 0; q < 3; ++q) {
         ie_obs[(size_t)q * E + ne] = e_obs[3 * (size_t)e + q];
@@ -339,26 +354,32 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
       }
       ++ne;
     }
-    ns += m.K;
+    ns += l_K[l];
   }
   lm_eptr[L] = ne; lm_sptr[L] = ns;
 
-  // ---- pose graph of the reduced system
+  // ---- pose graph of the reduced system: co-visibility (all pairs inside a track) + constraints
   std::vector<std::vector<int>> adj(P);
   {
-    std::vector<std::set<int>> A(P);
+    std::vector<unsigned char> A((size_t)P * P, 0);
     for (int l = 0; l < L; ++l) {
-      const Lm& m = lms[l];
-      if (m.anchor < 0) continue;
-      std::vector<int> ps = m.poses;
-      ps.push_back(m.anchor);
-      for (size_t x = 0; x < ps.size(); ++x)
-        for (size_t y = x + 1; y < ps.size(); ++y) { A[ps[x]].insert(ps[y]); A[ps[y]].insert(ps[x]); }
+      if (l_anchor[l] < 0) continue;
+      int ps[kMaxTrack + 1];
+      int n = 0;
+      ps[n++] = l_anchor[l];
+      for (int k = eptr[l] + l_self[l]; k < eptr[l + 1]; ++k) ps[n++] = e_pose[eord[k]];
+      for (int x = 0; x < n; ++x)
+        for (int y = x + 1; y < n; ++y) { A[(size_t)ps[x] * P + ps[y]] = 1; A[(size_t)ps[y] * P + ps[x]] = 1; }
     }
-    for (int c = 0; c < C; ++c) { A[c_i[c]].insert(c_j[c]); A[c_j[c]].insert(c_i[c]); }
-    int nnz = P;
-    for (int i = 0; i < P; ++i) { adj[i].assign(A[i].begin(), A[i].end()); nnz += (int)A[i].size(); }
-    h->nnzb_S = (nnz - P) / 2 + P;
+    for (int c = 0; c < C; ++c) { A[(size_t)c_i[c] * P + c_j[c]] = 1; A[(size_t)c_j[c] * P + c_i[c]] = 1; }
+    int nnz = 0;
+    for (int i = 0; i < P; ++i) {
+      const unsigned char* row = A.data() + (size_t)i * P;
+      for (int j = 0; j < P; ++j)
+        if (row[j] && j != i) adj[i].push_back(j);
+      nnz += (int)adj[i].size();
+    }
+    h->nnzb_S = nnz / 2 + P;
   }
   Symbolic sy;
   analyse(P, adj, (h->flags & SVS_BA_NATURAL_ORDER) != 0, sy);
@@ -379,7 +400,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self);
     UP(e_pose, ie_pose); UP(e_obs, ie_obs); UP(e_w, ie_w);
     UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
-    UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab);
+    UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab); UP(urg_dst, sy.urg_dst);
     dev_upload(h, &d.c_i, c_i, (size_t)C); dev_upload(h, &d.c_j, c_j, (size_t)C);
     dev_upload(h, &d.c_T, c_T, 7 * (size_t)C); dev_upload(h, &d.c_Lam, c_Lambda, 36 * (size_t)C);
     dev_upload(h, &d_pose0c, T_qt, 7 * (size_t)P);
@@ -392,7 +413,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     AL(S, 36 * (size_t)sy.nblk); AL(bp, 6 * (size_t)P); AL(bc, 6 * (size_t)P); AL(x, 6 * (size_t)P);
     AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
     AL(ctl, 1);
-    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1);
+    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 24);
 #undef AL
   };
   h->measuring = true;
@@ -511,6 +532,15 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     cudaEventElapsedTime(&st->ms_total, h->ev[0], h->ev[6]);
     st->ms_build = ms[0]; st->ms_solve = ms[1]; st->ms_update = ms[2]; st->ms_control = ms[3];
     st->launches = launches;
+  }
+  if (getenv("SVS_SOLVE_TIMING")) {
+    long long dbg[24];
+    cudaMemcpy(dbg, d.dbg, sizeof dbg, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "k_solve cycles  panel:");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", dbg[i]);
+    fprintf(stderr, "\n                update:");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", dbg[12 + i]);
+    fprintf(stderr, "\n  slots: 0 prologue, 1 loop head, 2 urgent updates, 3 panel column, 4 updates, 5 column barrier, 6 refill, 7 backward\n");
   }
   return h->h_ctl->iter;
 #undef CKO

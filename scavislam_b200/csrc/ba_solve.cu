@@ -20,7 +20,7 @@
 
 namespace svs {
 
-constexpr int kSolveThreads = 256;
+constexpr int kSolveThreads = 512;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -69,16 +69,60 @@ __device__ __forceinline__ bool chol6_regs(const double* __restrict__ A, double 
   return ok;
 }
 
-constexpr int kUpdPf = 4;   // update-list entries per thread prefetched one column ahead
+constexpr int kUpdPf = 4;        // update-list entries per update thread prefetched one column ahead
+constexpr int kPanelThreads = 128;  // warps 0-3: factor the next column (look-ahead); warp 0 owns the pivot chain
+constexpr int kUpdThreads = kSolveThreads - kPanelThreads;
 
-// smem layout: [ring: cap*36 doubles][y: 6P doubles if y_in_smem][meta ints if meta_in_smem:
-//               col_ptr (P+1), upd_ptr (P+1), row_idx (nblk), fixed-by-position (P)]
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// 1/sqrt(a): hardware approximation + two Newton steps (the library rsqrt() carries special-case
+// handling that would sit on the pivot chain)
+__device__ __forceinline__ double fast_rsqrt(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  y = fma(y, fma(-h * y, y, 0.5), y);
+  y = fma(y, fma(-h * y, y, 0.5), y);
+  return y;
+}
+
+// Lower Cholesky of the 6x6 block at A (row-major, lower triangle read, dlam added to the
+// diagonal) in registers: l = packed lower factor (r*(r+1)/2 + c), rinv = 1 / diagonal.
+__device__ __forceinline__ bool chol6_lean(const double* __restrict__ A, double dlam, double l[21], double rinv[6]) {
+  double a[21];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) a[r * (r + 1) / 2 + c] = A[r * 6 + c] + (r == c ? dlam : 0.);
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const double dv = a[c * (c + 1) / 2 + c];
+    ok = ok && (dv > 0.);
+    rinv[c] = fast_rsqrt(dv);
+    l[c * (c + 1) / 2 + c] = dv * rinv[c];
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) l[r * (r + 1) / 2 + c] = a[r * (r + 1) / 2 + c] * rinv[c];
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r)
+#pragma unroll
+      for (int c2 = c + 1; c2 <= r; ++c2)
+        a[r * (r + 1) / 2 + c2] -= l[r * (r + 1) / 2 + c] * l[c2 * (c2 + 1) / 2 + c];
+  }
+  return ok;
+}
+
+// smem layout: [ring: cap*36 doubles][y: 6P doubles if y_in_smem][meta ints: col_ptr (P+1),
+//               upd_ptr (P+1), row_idx (nblk), urg_dst (nblk), fixed-by-position (P)]
+// cap is a power of two >= 4 * (widest column + 1).
 __global__ void __launch_bounds__(kSolveThreads)
-k_solve(BaDev d, int cap, int y_in_smem, int meta_in_smem) {
+k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
   extern __shared__ __align__(16) double sm_solve[];
-  __shared__ int sFail;
+  __shared__ int sFailBuf[2];   // indexed by column parity: written by the panel warps, read after the column barrier
   __shared__ double sRed[kSolveThreads / 32];
+  __shared__ double sL[2][28];   // factor of the diagonal block of column j (l 21, rinv 6), double buffered
   double* ring = sm_solve;
+  const int mask = cap - 1;
   double* ysm = sm_solve + (size_t)cap * 36;
   double* yv = y_in_smem ? ysm : d.ywork;
   LmCtl* ctl = d.ctl;
@@ -86,30 +130,24 @@ k_solve(BaDev d, int cap, int y_in_smem, int meta_in_smem) {
   const int P = d.P, nblk = d.nblk;
   const double lambda = ctl->lambda;
   const int cur = ctl->cur;
-  if (t == 0) sFail = 0;
-  // index metadata: every use below sits on the per-column critical path, so keep it on chip
+  if (t == 0) { sFailBuf[0] = 0; sFailBuf[1] = 0; }
   int* meta = reinterpret_cast<int*>(ysm + (y_in_smem ? ((6 * (size_t)P + 1) / 2) * 2 : 0));
-  const int* col_ptr = d.col_ptr;
-  const int* upd_ptr = d.upd_ptr;
-  const int* row_idx = d.row_idx;
-  int* sfix = nullptr;
-  if (meta_in_smem) {
-    int* c = meta; int* u = meta + (P + 1); int* r = u + (P + 1); sfix = r + nblk;
-    for (int i = t; i <= P; i += nt) { c[i] = d.col_ptr[i]; u[i] = d.upd_ptr[i]; }
-    for (int i = t; i < nblk; i += nt) r[i] = d.row_idx[i];
-    for (int i = t; i < P; i += nt) sfix[i] = d.fixed[d.perm[i]];
-    col_ptr = c; upd_ptr = u; row_idx = r;
-  }
-
+  int* col_ptr = meta;
+  int* upd_ptr = col_ptr + (P + 1);
+  int* row_idx = upd_ptr + (P + 1);
+  int* urg_dst = row_idx + nblk;
+  int* sfix = urg_dst + nblk;
+  for (int i = t; i <= P; i += nt) { col_ptr[i] = d.col_ptr[i]; upd_ptr[i] = d.upd_ptr[i]; }
+  for (int i = t; i < nblk; i += nt) { row_idx[i] = d.row_idx[i]; urg_dst[i] = d.urg_dst[i]; }
+  for (int i = t; i < P; i += nt) sfix[i] = d.fixed[d.perm[i]];
   // initial ring fill: blocks [0, hi)
   int hi = min(nblk, cap);
   for (int c = t; c < hi * 18; c += nt) {
     const int id = c / 18, w = c - id * 18;
-    cp_async16(ring + (size_t)(id % cap) * 36 + 2 * w, d.S + (size_t)id * 36 + 2 * w);
+    cp_async16(ring + (size_t)(id & mask) * 36 + 2 * w, d.S + (size_t)id * 36 + 2 * w);
   }
   cp_async_commit();
-  // right-hand side in elimination order: bs = bp - bc
-  for (int i = t; i < 6 * P; i += nt) {
+  for (int i = t; i < 6 * P; i += nt) {   // right-hand side in elimination order: bs = bp - bc
     const int j = i / 6, r = i - 6 * j;
     const int p = d.perm[j];
     yv[i] = d.bp[6 * p + r] - d.bc[6 * p + r];
@@ -117,110 +155,181 @@ k_solve(BaDev d, int cap, int y_in_smem, int meta_in_smem) {
   cp_async_wait_all();
   __syncthreads();
 
-  int pf_ab[kUpdPf], pf_dst[kUpdPf];   // update-list entries of the column about to be processed
-  auto prefetch_upd = [&](int j) {
-    const int u0 = upd_ptr[j], nu = upd_ptr[j + 1] - u0;
+  // factor + scale the panel of column jn (panel warps only): chol by warp 0, rows by both
+  auto panel_column = [&](int jn) {
+    const int base = col_ptr[jn], nb = col_ptr[jn + 1] - base - 1;
+    double* sl = sL[jn & 1];
+    if (warp == 0) {
+      double l[21], rinv[6];
+      const bool ok = chol6_lean(ring + (size_t)(base & mask) * 36, lambda + (sfix[jn] ? 1. : 0.), l, rinv);
+      if (lane == 0) {
+        if (!ok) sFailBuf[jn & 1] = 1;
 #pragma unroll
-    for (int i = 0; i < kUpdPf; ++i) {
-      const int w = t + i * nt;
-      if (w < nu * 36) { pf_ab[i] = d.upd_ab[u0 + w / 36]; pf_dst[i] = d.upd_dst[u0 + w / 36]; }
+        for (int i = 0; i < 21; ++i) sl[i] = l[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sl[21 + i] = rinv[i];
+      }
+    }
+    bar_sync(1, kPanelThreads);
+    // row <- row * L^-T by forward substitution (block rows: L_ij ; rhs row: y = L^-1 b)
+    const int nrows = nb * 6 + 1;
+    for (int row = t; row < nrows; row += kPanelThreads) {
+      double* src;
+      double* gdst = nullptr;
+      if (row < nb * 6) {
+        const int a = row / 6, r = row - a * 6;
+        src = ring + (size_t)((base + 1 + a) & mask) * 36 + r * 6;
+        gdst = d.S + (size_t)(base + 1 + a) * 36 + r * 6;
+      } else {
+        src = yv + 6 * jn;
+      }
+      double o[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double s = src[c];
+#pragma unroll
+        for (int q = 0; q < c; ++q) s -= o[q] * sl[c * (c + 1) / 2 + q];
+        o[c] = s * sl[21 + c];
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) src[q] = o[q];
+      if (gdst) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) gdst[q] = o[q];   // final factor column, read by the backward solve
+      }
     }
   };
-  if (P > 0) prefetch_upd(0);
-  for (int j = 0; j < P; ++j) {
+
+  auto update_item = [&](int base, int w, int ab, int dst, int hi_res) {
+    const int pidx = w / 36, el = w - pidx * 36, r = el / 6, c = el - r * 6;
+    (void)pidx;
+    const double2* La = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab >> 16)) & mask) * 36 + r * 6);
+    const double2* Lb = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab & 0xffff)) & mask) * 36 + c * 6);
+    const double2 a0 = La[0], a1 = La[1], a2 = La[2], b0 = Lb[0], b1 = Lb[1], b2 = Lb[2];
+    const double s = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y);
+    if (dst < hi_res) ring[(size_t)(dst & mask) * 36 + el] -= s;
+    else d.S[(size_t)dst * 36 + el] -= s;
+  };
+
+  // number of "urgent" pairs of column j: those that land in column j+1 (pairs (a, 0) when the
+  // first sub-diagonal row of column j is j+1; the update list is ordered b-major)
+  auto urgent_of = [&](int j) {
     const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-    const double* diag = ring + (size_t)(base % cap) * 36;
-    int cu_ab[kUpdPf], cu_dst[kUpdPf];
+    return (nb > 0 && row_idx[base + 1] == j + 1) ? nb : 0;
+  };
+
+  long long tm[12];
 #pragma unroll
-    for (int i = 0; i < kUpdPf; ++i) { cu_ab[i] = pf_ab[i]; cu_dst[i] = pf_dst[i]; }
-    if (j + 1 < P) prefetch_upd(j + 1);   // in flight under this column's pivot chain
-    const int nrows = nb * 6 + 1;   // panel rows + the right-hand side row
-    // --- phase A+B: every thread that owns a row factors the diagonal block in registers, then
-    //     row <- row * L_jj^-T   (block rows: L_ij ; rhs row: y_j = L_jj^-1 b_j)
-    if (t < nrows || t == 0) {
-      double l[21], li[21];
-      const double dlam = lambda + ((sfix ? sfix[j] : (int)d.fixed[d.perm[j]]) ? 1. : 0.);
-      const bool ok = chol6_regs(diag, dlam, l, li);
-      if (!ok) sFail = 1;
-      if (t == 0) {
-        double* Lo = d.Linv + 36 * (size_t)j;
+  for (int i = 0; i < 12; ++i) tm[i] = 0;
+  long long t_prev = clock64();
+#define TICK(slot) { const long long now_ = clock64(); tm[slot] += now_ - t_prev; t_prev = now_; }
+  if (P > 0 && t < kPanelThreads) panel_column(0);
+  const int ut = t - kPanelThreads;   // index among the update threads
+  int pf_ab[kUpdPf], pf_dst[kUpdPf];
+  auto prefetch_upd = [&](int j) {
+    const int u0 = upd_ptr[j] + urgent_of(j), nitems = (upd_ptr[j + 1] - u0) * 36;
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
+    for (int i = 0; i < kUpdPf; ++i) {
+      const int w = ut + i * kUpdThreads;
+      if (w < nitems) { pf_ab[i] = d.upd_ab[u0 + w / 36]; pf_dst[i] = d.upd_dst[u0 + w / 36]; }
+    }
+  };
+  if (P > 0 && t >= kPanelThreads) prefetch_upd(0);
+  __syncthreads();
+  int failed = P > 0 ? sFailBuf[0] : 0;
+
+  TICK(0);
+  for (int j = 0; j < P && !failed; ++j) {
+    const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
+    const int urgent = urgent_of(j);
+    const int u0 = upd_ptr[j];
+    TICK(1);
+    if (t < kPanelThreads) {
+      // ---- panel warps: the part of column j's update that lands in column j+1, then factor it
+      if (urgent) {
+        if (warp == 0) {
+          for (int w = lane; w < 36; w += 32) update_item(base, w, 0, urg_dst[base + 1], 0x7fffffff);
+          if (lane < 6) {   // b_{j+1} -= L_{j+1,j} y_j
+            const double* La = ring + (size_t)((base + 1) & mask) * 36 + lane * 6;
+            const double* yj = yv + 6 * j;
+            double s = 0.;
 #pragma unroll
-          for (int c = 0; c < 6; ++c) Lo[r * 6 + c] = (c <= r) ? li[r * (r + 1) / 2 + c] : 0.;
-      }
-      for (int row = t; row < nrows; row += nt) {
-        double* src;
-        double* gdst = nullptr;
-        if (row < nb * 6) {
-          const int a = row / 6, r = row - a * 6;
-          src = ring + (size_t)((base + 1 + a) % cap) * 36 + r * 6;
-          gdst = d.S + (size_t)(base + 1 + a) * 36 + r * 6;
+            for (int q = 0; q < 6; ++q) s += La[q] * yj[q];
+            yv[6 * (j + 1) + lane] -= s;
+          }
+          __syncwarp();
         } else {
-          src = yv + 6 * j;
-        }
-        double v[6], o[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) v[q] = src[q];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          double s = 0.;
-#pragma unroll
-          for (int q = 0; q <= c; ++q) s += v[q] * li[c * (c + 1) / 2 + q];
-          o[c] = s;
-        }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) src[q] = o[q];
-        if (gdst) {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) gdst[q] = o[q];   // final factor column, read by the backward solve
+          for (int w = 36 + (t - 32); w < urgent * 36; w += kPanelThreads - 32) {
+            const int a = w / 36;
+            update_item(base, w, a << 16, urg_dst[base + 1 + a], 0x7fffffff);
+          }
         }
       }
+      TICK(2);
+      if (j + 1 < P) panel_column(j + 1);   // its barrier also orders warp 1's panel updates before the row scaling
+      TICK(3);
+    } else {
+      // ---- update warps: the rest of column j's trailing update
+      int cu_ab[kUpdPf], cu_dst[kUpdPf];
+#pragma unroll
+      for (int i = 0; i < kUpdPf; ++i) { cu_ab[i] = pf_ab[i]; cu_dst[i] = pf_dst[i]; }
+      if (j + 1 < P) prefetch_upd(j + 1);
+      const int uu = u0 + urgent, nitems = (upd_ptr[j + 1] - uu) * 36;
+#pragma unroll
+      for (int i = 0; i < kUpdPf; ++i) {
+        const int w = ut + i * kUpdThreads;
+        if (w < nitems) update_item(base, w, cu_ab[i], cu_dst[i], hi);
+      }
+      for (int w = ut + kUpdPf * kUpdThreads; w < nitems; w += kUpdThreads)
+        update_item(base, w, d.upd_ab[uu + w / 36], d.upd_dst[uu + w / 36], hi);
+      // b_a -= L_aj y_j for the rows the panel warps did not take
+      for (int w = ut + (urgent ? 6 : 0); w < nb * 6; w += kUpdThreads) {
+        const int a = w / 6, r = w - a * 6;
+        const double* La = ring + (size_t)((base + 1 + a) & mask) * 36 + r * 6;
+        const double* yj = yv + 6 * j;
+        double s = 0.;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) s += La[q] * yj[q];
+        yv[6 * row_idx[base + 1 + a] + r] -= s;
+      }
+      // inverse of column j's diagonal factor for the backward solve (off the critical path)
+      if (warp == kSolveThreads / 32 - 1 && lane < 6) {
+        const double* sl = sL[j & 1];
+        const int c = lane;
+        double col[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double v = (r == c) ? 1. : 0.;
+#pragma unroll
+          for (int q = 0; q < r; ++q) v -= (q >= c) ? sl[r * (r + 1) / 2 + q] * col[q] : 0.;
+          col[r] = (r < c) ? 0. : v * sl[21 + r];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) d.Linv[36 * (size_t)j + r * 6 + c] = col[r];
+      }
+      TICK(4);
     }
-    cp_async_wait_all();   // refills issued after the previous column's update
     __syncthreads();
-    if (sFail) break;
-    // --- phase C: S_ab -= L_aj L_bj^T for a >= b in column j ; b_a -= L_aj y_j
-    const int u0 = upd_ptr[j], nu = upd_ptr[j + 1] - u0;
-    auto update_item = [&](int w, int ab, int dst) {
-      const int pidx = w / 36, el = w - pidx * 36, r = el / 6, c = el - r * 6;
-      const double* La = ring + (size_t)((base + 1 + (ab >> 16)) % cap) * 36 + r * 6;
-      const double* Lb = ring + (size_t)((base + 1 + (ab & 0xffff)) % cap) * 36 + c * 6;
-      double s = 0.;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) s += La[q] * Lb[q];
-      if (dst < hi) ring[(size_t)(dst % cap) * 36 + el] -= s;
-      else d.S[(size_t)dst * 36 + el] -= s;
-    };
-#pragma unroll
-    for (int i = 0; i < kUpdPf; ++i) {   // entries prefetched during the previous column
-      const int w = t + i * nt;
-      if (w < nu * 36) update_item(w, cu_ab[i], cu_dst[i]);
+    TICK(5);
+    failed = sFailBuf[(j + 1) & 1];
+    // ---- every refill_period columns: reload the ring slots the finished columns freed.  Copies are
+    //      never in flight while updates run, so a destination is either resident (< hi) or in HBM.
+    if ((j + 1) % refill_period == 0 && hi < nblk) {
+      const int hi_new = min(nblk, col_ptr[j + 1] + cap);
+      for (int c = t; c < (hi_new - hi) * 18; c += nt) {
+        const int id = hi + c / 18, w = c % 18;
+        cp_async16(ring + (size_t)(id & mask) * 36 + 2 * w, d.S + (size_t)id * 36 + 2 * w);
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();
+      hi = hi_new;
+      TICK(6);
     }
-    for (int w = t + kUpdPf * nt; w < nu * 36; w += nt)   // wide columns: the rest from L2
-      update_item(w, d.upd_ab[u0 + w / 36], d.upd_dst[u0 + w / 36]);
-    for (int w = t; w < nb * 6; w += nt) {
-      const int a = w / 6, r = w - a * 6;
-      const double* La = ring + (size_t)((base + 1 + a) % cap) * 36 + r * 6;
-      const double* yj = yv + 6 * j;
-      double s = 0.;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) s += La[q] * yj[q];
-      yv[6 * row_idx[base + 1 + a] + r] -= s;
-    }
-    __syncthreads();
-    // --- refill the ring slots column j frees: blocks [hi, min(nblk, col_ptr[j+1] + cap))
-    const int hi_new = min(nblk, col_ptr[j + 1] + cap);
-    for (int c = t; c < (hi_new - hi) * 18; c += nt) {
-      const int id = hi + c / 18, w = c % 18;
-      cp_async16(ring + (size_t)(id % cap) * 36 + 2 * w, d.S + (size_t)id * 36 + 2 * w);
-    }
-    cp_async_commit();
-    hi = hi_new;
   }
   cp_async_wait_all();
   __syncthreads();
-  if (sFail) {
+  if (failed) {
     if (t == 0) { ctl->chol_fail = 1; ctl->scale_pose = 0; }
     for (int i = t; i < 7 * P; i += nt) d.pose[1 - cur][i] = d.pose[cur][i];
     for (int i = t; i < 12 * P; i += nt) d.Rt[1 - cur][i] = d.Rt[cur][i];
@@ -293,6 +402,10 @@ k_solve(BaDev d, int cap, int y_in_smem, int meta_in_smem) {
     }
   }
   __syncthreads();
+  TICK(7);
+  if (d.dbg && (t == 0 || t == kPanelThreads)) {
+    for (int i = 0; i < 12; ++i) d.dbg[(t ? 12 : 0) + i] = tm[i];
+  }
   // --- pose update (G2oVertexSE3::oplusImpl) into the trial buffer; scale = sum x (lambda x + b)
   double sc = 0;
   for (int p = t; p < P; p += nt) {
@@ -348,17 +461,24 @@ void launch_solve(const BaDev& d, int max_col_blocks, cudaStream_t st) {
   const size_t budget = (size_t)smem_optin - 1024 - 256;
   const int y_in_smem = (size_t)6 * d.P * 8 <= budget / 4;
   const size_t ybytes = y_in_smem ? (((size_t)6 * d.P * 8 + 15) / 16) * 16 : 0;
-  const size_t mbytes_want = ((size_t)(2 * (d.P + 1) + d.nblk + d.P) * 4 + 15) / 16 * 16;
-  const int meta_in_smem = mbytes_want <= (budget - ybytes) / 3;
-  const size_t mbytes = meta_in_smem ? mbytes_want : 0;
-  int cap = (int)((budget - ybytes - mbytes) / 288);
-  if (cap > d.nblk) cap = d.nblk > 0 ? d.nblk : 1;
-  if (max_col_blocks + 1 > cap) {
+  const size_t mbytes = ((size_t)(2 * (d.P + 1) + 2 * d.nblk + d.P) * 4 + 15) / 16 * 16;
+  int cap = 0;
+  if (ybytes + mbytes < budget) {
+    const int avail = (int)((budget - ybytes - mbytes) / 288);
+    for (cap = 1; cap * 2 <= avail; cap *= 2) {}
+    if (cap > avail) cap = 0;
+  }
+  // the look-ahead kernel keeps two columns live and never checks residency on them
+  if (d.P == 0 || cap < 4 * (max_col_blocks + 1)) {
     launch_solve_general(d, st);
     return;
   }
+  while (cap / 2 >= d.nblk && cap / 2 >= 4 * (max_col_blocks + 1)) cap /= 2;   // small problems: small ring
+  // columns j+1 and j+2 must stay resident between refills: cap >= (period + 3) * widest column
+  int period = cap / (max_col_blocks + 1) - 3;
+  period = period < 1 ? 1 : (period > 32 ? 32 : period);
   const size_t smem = (size_t)cap * 288 + ybytes + mbytes;
-  k_solve<<<1, kSolveThreads, smem, st>>>(d, cap, y_in_smem, meta_in_smem);
+  k_solve<<<1, kSolveThreads, smem, st>>>(d, cap, y_in_smem, period);
 }
 
 }  // namespace svs

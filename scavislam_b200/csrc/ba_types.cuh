@@ -68,11 +68,13 @@ struct BaDev {
   const int* row_idx;  // [nblk] row position of each block
   const int* upd_ptr;  // [P+1]
   const int* upd_dst;  // destination block of each (a>=b) pair of a column
-  const int* upd_ab;   // (a << 16 | b): indices into the column's sub-diagonal list
+  const int* upd_ab;   // (a << 16 | b): indices into the column's sub-diagonal list (b-major order)
+  const int* urg_dst;  // [nblk] destination of pair (a, 0) of column j at col_ptr[j] + 1 + a
   double* Linv;        // [P][36] inverse of the diagonal factor blocks
   double* ywork;       // [6P]
   double* part;        // [update grid][3] per-CTA partial sums (chi2 accepted, chi2 trial, scale)
   unsigned* ticket;    // last-CTA-done counter of k_update
+  long long* dbg;      // [24] per-phase cycle counters of k_solve (thread 0, thread 64)
   LmCtl* ctl;
 };
 

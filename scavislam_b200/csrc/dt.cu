@@ -1,0 +1,549 @@
+// dt.cu -- dense photometric SE3 tracker on sm_100a (ScaViSLAM GPU-path semantics).
+//   scavislam/gpu/dense_tracking.cu:82-148   pointcloud_kernel / computePointCloud
+//   scavislam/gpu/dense_tracking.cu:172-356  jacobianReduction_kernel + host-side final sum
+//   scavislam/gpu/dense_tracking.cu:376-491  chi2_kernel + host-side final sum
+//   scavislam/dense_tracking.cpp:62-216      DenseTracker::denseTrackingGpu / computeDensePointCloudGpu
+//
+// The reference launches a kernel, synchronises, copies per-block partials to the host and sums
+// them there, twice per Levenberg trial.  Here one cooperative, persistent kernel per pyramid
+// level runs the whole LM loop on the device: every trial is ONE fused pass over the pixels that
+// yields chi2, J^T J and J^T r at the trial pose (an accepted trial's J^T J / J^T r are exactly
+// what the reference's next jacobianReduction at the accepted pose would compute), a grid-wide
+// deterministic reduction, and a 6x6 solve + SE3 exp by one thread.  HBM/L2-bound image work:
+// ~20 B/pixel of compulsory reads (float4 cloud + previous intensity) plus 12 cached taps.
+//
+// Per-pixel arithmetic is IEEE single precision in the order the reference writes it (this
+// translation unit is compiled with -fmad=false so that it matches the CPU oracle bit for bit);
+// sums over pixels are accumulated in double (deviation D-DT1).
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "../../include/svs_b200.h"
+#include "se3_dev.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kMaxLevels = 8;
+constexpr int kThreads = 256;
+constexpr int kAcc = 28;   // 21 Hessian + 6 gradient + chi2
+
+struct DtLevel {
+  int w, h, stride, cloud_stride;
+  float f, px, py;
+  const float* prev;
+  const float* cur;
+  const float* dx;
+  const float* dy;
+  const float4* cloud;
+};
+
+struct DtCtl {
+  double T[7];       // accepted pose (T_cur_from_actkey)
+  double Teval[7];   // pose the next pass evaluates
+  double H[21], b[6], chi2;
+  double mu, nu;
+  int trial, stop, iter, phase, done, passes;
+  double chi2_level[kMaxLevels];
+  int passes_level[kMaxLevels];
+};
+
+__device__ __forceinline__ float bilinear(const float* __restrict__ img, int stride, float u, float v, int exact) {
+  const float x0 = floorf(u), y0 = floorf(v);
+  float a = u - x0, b = v - y0;
+  if (!exact) {   // texture-unit filtering: 8 fractional bits (dense_tracking.cu:285-287)
+    a = floorf(a * 256.f + 0.5f) / 256.f;
+    b = floorf(b * 256.f + 0.5f) / 256.f;
+  }
+  const int xi = (int)x0, yi = (int)y0;
+  const float* p = img + (size_t)yi * stride + xi;
+  const float t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + stride), t11 = __ldg(p + stride + 1);
+  return ((1.f - a) * (1.f - b)) * t00 + (a * (1.f - b)) * t10 + ((1.f - a) * b) * t01 + (a * b) * t11;
+}
+
+__device__ __forceinline__ void pose_to_m34(const double T[7], float m[12]) {
+  double R[9];
+  svs::quat_to_R(T, R);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) m[c * 3 + r] = (float)R[r * 3 + c];
+  m[9] = (float)T[4]; m[10] = (float)T[5]; m[11] = (float)T[6];
+}
+
+// one pixel of jacobianReduction_kernel / chi2_kernel (dense_tracking.cu:172-263, 376-453)
+__device__ __forceinline__ bool pixel_terms(const DtLevel& L, const float m[12], int u, int v, int exact, bool want_jac,
+                                            float& res, float jac[6]) {
+  const float4 p = __ldg(L.cloud + (size_t)v * L.cloud_stride + u);
+  if (!(p.w > 0)) return false;
+  const float cx = p.x * m[0] + p.y * m[3] + p.z * m[6] + p.w * m[9];
+  const float cy = p.x * m[1] + p.y * m[4] + p.z * m[7] + p.w * m[10];
+  const float cz = p.x * m[2] + p.y * m[5] + p.z * m[8] + p.w * m[11];
+  const float uc = L.f * cx / cz + L.px;
+  const float vc = L.f * cy / cz + L.py;
+  if (!(uc >= 1.f && vc >= 1.f && uc <= (float)(L.w - 2) && vc <= (float)(L.h - 2))) return false;
+  const float ip = __ldg(L.prev + (size_t)v * L.stride + u);
+  const float ic = bilinear(L.cur, L.stride, uc, vc, exact);
+  res = ip - ic;
+  if (want_jac) {
+    float dx = 0.5f * bilinear(L.dx, L.stride, uc, vc, exact);
+    float dy = 0.5f * bilinear(L.dy, L.stride, uc, vc, exact);
+    const float z_sq = cz * cz;   // frameJacobian (dense_tracking.cu:65-80), literally
+    dx *= L.f;
+    dy *= L.f;
+    jac[0] = (float)(-dx * (1. / cz));
+    jac[1] = (float)(-dy * 1. / cz);
+    jac[2] = (dx * cx / z_sq + dy * cy / z_sq);
+    jac[3] = (dx * (cx * cy) / z_sq + dy * (1.f + cy * cy / z_sq));
+    jac[4] = (-dx * (1.f + (cx * cx / z_sq)) - dy * (cx * cy) / z_sq);
+    jac[5] = (dx * cy / cz - dy * cx / cz);
+  }
+  return true;
+}
+
+// per-thread accumulation over a grid-stride pixel range, then a fixed-order CTA reduction;
+// partial[blockIdx][kAcc] (index 27 = chi2)
+__device__ void accumulate_pass(const DtLevel& L, const double T[7], int exact, bool want_jac, double* __restrict__ partial,
+                                double (*sred)[kAcc]) {
+  float m[12];
+  pose_to_m34(T, m);
+  double acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.;
+  const int npx = L.w * L.h;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npx; idx += gridDim.x * blockDim.x) {
+    const int v = idx / L.w, u = idx - v * L.w;
+    float res, jac[6];
+    if (!pixel_terms(L, m, u, v, exact, want_jac, res, jac)) continue;
+    acc[27] += (double)(res * res);
+    if (want_jac) {
+      int i = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) acc[i++] += (double)(jac[r] * jac[c]);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[21 + r] += (double)(jac[r] * res);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sred[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double s = 0;
+    for (int w = 0; w < kThreads / 32; ++w) s += sred[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * kAcc + threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// (H + mu diag(H)) x = -b by LDL^T (H.ldlt().solve(-b), dense_tracking.cpp:127-135)
+__device__ void solve6(const double H21[21], const double b6[6], double mu, double x[6]) {
+  double A[6][6];
+  int i = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c <= r; ++c) { A[r][c] = H21[i]; A[c][r] = H21[i]; ++i; }
+  for (int r = 0; r < 6; ++r) A[r][r] += mu * A[r][r];
+  double Lm[6][6], D[6];
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= Lm[j][k] * Lm[j][k] * D[k];
+    D[j] = d;
+    for (int r = j + 1; r < 6; ++r) {
+      double s = A[r][j];
+      for (int k = 0; k < j; ++k) s -= Lm[r][k] * Lm[j][k] * D[k];
+      Lm[r][j] = d != 0. ? s / d : 0.;
+    }
+  }
+  double y[6];
+  for (int r = 0; r < 6; ++r) {
+    double s = -b6[r];
+    for (int k = 0; k < r; ++k) s -= Lm[r][k] * y[k];
+    y[r] = s;
+  }
+  for (int r = 5; r >= 0; --r) {
+    double s = D[r] != 0. ? y[r] / D[r] : 0.;
+    for (int k = r + 1; k < 6; ++k) s -= Lm[k][r] * x[k];
+    x[r] = s;
+  }
+}
+
+__device__ void propose_step(DtCtl* c) {
+  double x[6], dT[7];
+  solve6(c->H, c->b, c->mu, x);
+  svs::se3_exp(x, dT);
+  svs::se3_mul(dT, c->T, c->Teval);
+}
+
+// The LM loop of DenseTracker::denseTrackingGpu for one level (dense_tracking.cpp:90-178).
+__global__ void __launch_bounds__(kThreads)
+k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, int exact, int level) {
+  __shared__ double sred[kThreads / 32][kAcc];
+  __shared__ double ssum[kAcc];
+  cg::grid_group grid = cg::this_grid();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int k = 0; k < 7; ++k) ctl->Teval[k] = ctl->T[k];
+    ctl->phase = 0; ctl->done = 0; ctl->passes = 0;
+  }
+  grid.sync();
+  for (;;) {
+    double Te[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Te[k] = __ldcg(&ctl->Teval[k]);
+    accumulate_pass(L, Te, exact, true, partial, sred);
+    grid.sync();
+    if (blockIdx.x == 0) {
+      if (threadIdx.x < kAcc) {
+        double s = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partial[(size_t)b * kAcc + threadIdx.x]);
+        ssum[threadIdx.x] = s;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        DtCtl* c = ctl;
+        c->passes += 1;
+        if (c->phase == 0) {   // chi2 and (H, b) at the incoming pose
+          for (int i = 0; i < 21; ++i) c->H[i] = ssum[i];
+          for (int i = 0; i < 6; ++i) c->b[i] = ssum[21 + i];
+          c->chi2 = ssum[27];
+          c->mu = (double)0.01f; c->nu = 2.; c->trial = 0; c->stop = 0; c->iter = 0; c->phase = 1;
+          propose_step(c);
+        } else {
+          const double chin = ssum[27];
+          const double rho = c->chi2 - chin;
+          bool finished = false;
+          if (rho > 0) {
+            for (int k = 0; k < 7; ++k) c->T[k] = c->Teval[k];
+            c->chi2 = chin;
+            double nm = 0;
+            for (int k = 0; k < 6; ++k) nm = fmax(nm, fabs(c->b[k]));
+            c->stop = nm <= 1e-10;   // norm_max(b) <= EPS
+            const double u = 2 * rho - 1;
+            c->mu *= fmax(1. / 3., 1 - u * u * u);
+            c->nu = 2.;
+            c->trial = 0;
+            for (int i = 0; i < 21; ++i) c->H[i] = ssum[i];
+            for (int i = 0; i < 6; ++i) c->b[i] = ssum[21 + i];
+            if (c->stop) finished = true;
+            else { c->iter += 1; if (c->iter >= 15) finished = true; }
+          } else {
+            c->mu *= c->nu;
+            c->nu *= 2.;
+            c->trial += 1;
+            if (c->trial == 2) { c->stop = 1; finished = true; }
+          }
+          if (finished) {
+            c->done = 1;
+            c->chi2_level[level] = c->chi2;
+            c->passes_level[level] = c->passes;
+          } else {
+            propose_step(c);
+          }
+        }
+        __threadfence();
+      }
+    }
+    grid.sync();
+    if (__ldcg(&ctl->done)) break;
+  }
+}
+
+// GpuTracker::chi2 / jacobianReduction as stand-alone launches (parity hooks)
+__global__ void __launch_bounds__(kThreads)
+k_dt_pass(DtLevel L, const double* T, double* partial, int exact, int want_jac) {
+  __shared__ double sred[kThreads / 32][kAcc];
+  double Te[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) Te[k] = T[k];
+  accumulate_pass(L, Te, exact, want_jac != 0, partial, sred);
+}
+
+// pointcloud_kernel (dense_tracking.cu:82-122)
+struct M4 { float m[16]; };
+__global__ void k_dt_pointcloud(M4 TQ, const float* __restrict__ disp, int width, int height, int stride_in, int stride_out,
+                                int factor, float4* __restrict__ cloud) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y * blockDim.y + threadIdx.y;
+  if (u >= width || v >= height) return;
+  const int idx_in = v * stride_in + u * factor;   // row not scaled by factor, as in the reference
+  const float d = disp[idx_in] * factor;
+  float4 pt;
+  if (d <= 0) {
+    pt = make_float4(0.f, 0.f, 0.f, -1.f);
+  } else {
+    const float uvd[4] = {(float)u, (float)v, d, 1.f};
+    float p[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      p[r] = uvd[0] * TQ.m[r] + uvd[1] * TQ.m[4 + r] + uvd[2] * TQ.m[8 + r] + uvd[3] * TQ.m[12 + r];
+    pt = make_float4(p[0] / p[3], p[1] / p[3], p[2] / p[3], 1.f);
+  }
+  cloud[(size_t)v * stride_out + u] = pt;
+}
+
+}  // namespace
+
+struct svs_dt {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int nlevels = 0, w0 = 0, h0 = 0, flags = 0;
+  DtLevel lv[kMaxLevels];
+  float* img[kMaxLevels][4] = {};   // prev cur dx dy
+  float4* cloud[kMaxLevels] = {};
+  float* disp = nullptr;
+  int disp_stride = 0, disp_w = 0, disp_h = 0;
+  DtCtl* d_ctl = nullptr;
+  DtCtl* h_ctl = nullptr;
+  double* d_partial = nullptr;
+  double* d_T = nullptr;
+  int max_blocks = 0;
+  float* stage = nullptr;   // pinned staging for image uploads
+  size_t stage_floats = 0;
+};
+
+#define DCK(call)                                                       \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) {                                            \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+      return SVS_ERR_CUDA;                                              \
+    }                                                                   \
+  } while (0)
+
+extern "C" {
+
+int svs_dt_create(int device, int w0, int h0, int nlevels, int flags, svs_dt** out) {
+  if (!out || w0 <= 0 || h0 <= 0 || nlevels <= 0 || nlevels > kMaxLevels) return SVS_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SVS_ERR_NOGPU;
+  svs_dt* h = new svs_dt();
+  if (device < 0) cudaGetDevice(&device);
+  h->device = device; h->nlevels = nlevels; h->w0 = w0; h->h0 = h0; h->flags = flags;
+  bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int l = 0; ok && l < nlevels; ++l) {
+    const int w = w0 >> l, hh = h0 >> l;
+    DtLevel& L = h->lv[l];
+    L.w = w; L.h = hh; L.stride = ((w + 63) / 64) * 64; L.cloud_stride = L.stride;
+    L.f = 1.f; L.px = 0.f; L.py = 0.f;
+    for (int k = 0; ok && k < 4; ++k) {
+      ok = cudaMalloc(&h->img[l][k], sizeof(float) * (size_t)L.stride * hh) == cudaSuccess &&
+           cudaMemset(h->img[l][k], 0, sizeof(float) * (size_t)L.stride * hh) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&h->cloud[l], sizeof(float4) * (size_t)L.cloud_stride * hh) == cudaSuccess &&
+         cudaMemset(h->cloud[l], 0, sizeof(float4) * (size_t)L.cloud_stride * hh) == cudaSuccess;
+    L.prev = h->img[l][0]; L.cur = h->img[l][1]; L.dx = h->img[l][2]; L.dy = h->img[l][3]; L.cloud = h->cloud[l];
+  }
+  h->disp_stride = ((w0 + 63) / 64) * 64;
+  ok = ok && cudaMalloc(&h->disp, sizeof(float) * (size_t)h->disp_stride * h0) == cudaSuccess;
+  int per_sm = 0, sms = 0;
+  if (ok) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dt_track_level, kThreads, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    h->max_blocks = std::max(1, per_sm * sms);
+  }
+  const int part_blocks = std::max(h->max_blocks, (w0 * h0 + kThreads - 1) / kThreads);
+  ok = ok && cudaMalloc(&h->d_ctl, sizeof(DtCtl)) == cudaSuccess && cudaMemset(h->d_ctl, 0, sizeof(DtCtl)) == cudaSuccess &&
+       cudaMalloc(&h->d_partial, sizeof(double) * kAcc * (size_t)part_blocks) == cudaSuccess &&
+       cudaMalloc(&h->d_T, sizeof(double) * 8) == cudaSuccess &&
+       cudaMallocHost(&h->h_ctl, sizeof(DtCtl)) == cudaSuccess;
+  h->stage_floats = (size_t)h->disp_stride * h0 * 4;
+  ok = ok && cudaMallocHost(&h->stage, sizeof(float) * h->stage_floats) == cudaSuccess;
+  if (!ok) {
+    svs_dt_destroy(h);
+    return SVS_ERR_CUDA;
+  }
+  *out = h;
+  return SVS_OK;
+}
+
+void svs_dt_destroy(svs_dt* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int l = 0; l < kMaxLevels; ++l) {
+    for (int k = 0; k < 4; ++k) cudaFree(h->img[l][k]);
+    cudaFree(h->cloud[l]);
+  }
+  cudaFree(h->disp); cudaFree(h->d_ctl); cudaFree(h->d_partial); cudaFree(h->d_T);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->stage) cudaFreeHost(h->stage);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* svs_dt_last_error(const svs_dt* h) { return h ? h->err.c_str() : "null handle"; }
+
+int svs_dt_set_intrinsics(svs_dt* h, int level, float focal_length, float px, float py) {
+  if (!h || level < 0 || level >= h->nlevels) return SVS_ERR_INVALID;
+  h->lv[level].f = focal_length; h->lv[level].px = px; h->lv[level].py = py;
+  return SVS_OK;
+}
+
+static int upload_plane(svs_dt* h, float* dst, int dst_stride, const float* src, int src_stride, int w, int hgt) {
+  DCK(cudaMemcpy2DAsync(dst, sizeof(float) * dst_stride, src, sizeof(float) * src_stride, sizeof(float) * w, hgt,
+                        cudaMemcpyHostToDevice, h->stream));
+  return SVS_OK;
+}
+
+int svs_dt_set_images(svs_dt* h, int level, const float* prev, const float* cur, const float* dx, const float* dy,
+                      int stride_floats) {
+  if (!h || level < 0 || level >= h->nlevels || stride_floats < h->lv[level].w) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const DtLevel& L = h->lv[level];
+  const float* src[4] = {prev, cur, dx, dy};
+  for (int k = 0; k < 4; ++k)
+    if (src[k]) {
+      int rc = upload_plane(h, h->img[level][k], L.stride, src[k], stride_floats, L.w, L.h);
+      if (rc) return rc;
+    }
+  return SVS_OK;
+}
+
+int svs_dt_set_disparity(svs_dt* h, const float* disp, int stride_floats, int w, int hgt) {
+  if (!h || !disp || w <= 0 || hgt <= 0 || w > h->w0 || hgt > h->h0 || stride_floats < w) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  h->disp_w = w; h->disp_h = hgt;
+  return upload_plane(h, h->disp, h->disp_stride, disp, stride_floats, w, hgt);
+}
+
+int svs_dt_set_point_cloud(svs_dt* h, int level, const float* cloud_xyzw) {
+  if (!h || level < 0 || level >= h->nlevels || !cloud_xyzw) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const DtLevel& L = h->lv[level];
+  DCK(cudaMemcpy2DAsync(h->cloud[level], sizeof(float4) * L.cloud_stride, cloud_xyzw, sizeof(float4) * L.w,
+                        sizeof(float4) * L.w, L.h, cudaMemcpyHostToDevice, h->stream));
+  return SVS_OK;
+}
+
+int svs_dt_get_point_cloud(svs_dt* h, int level, float* cloud_xyzw) {
+  if (!h || level < 0 || level >= h->nlevels || !cloud_xyzw) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const DtLevel& L = h->lv[level];
+  DCK(cudaMemcpy2DAsync(cloud_xyzw, sizeof(float4) * L.w, h->cloud[level], sizeof(float4) * L.cloud_stride,
+                        sizeof(float4) * L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+  DCK(cudaStreamSynchronize(h->stream));
+  return SVS_OK;
+}
+
+// DenseTracker::computeDensePointCloudGpu (dense_tracking.cpp:195-216): per level TQ = T^-1 Q(level camera)
+int svs_dt_compute_point_cloud(svs_dt* h, const double T_cur_from_actkey[7], const svs_cam* cams) {
+  if (!h || !T_cur_from_actkey || !cams) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  // T^-1 in double
+  const double* T = T_cur_from_actkey;
+  const double qi[4] = {-T[0], -T[1], -T[2], T[3]};
+  double R[9];
+  {
+    const double x = qi[0], y = qi[1], z = qi[2], w = qi[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+  }
+  double ti[3];
+  for (int r = 0; r < 3; ++r) ti[r] = -(R[r * 3] * T[4] + R[r * 3 + 1] * T[5] + R[r * 3 + 2] * T[6]);
+  for (int l = 0; l < h->nlevels; ++l) {
+    const svs_cam& c = cams[l];
+    double M[16] = {R[0], R[1], R[2], ti[0], R[3], R[4], R[5], ti[1], R[6], R[7], R[8], ti[2], 0, 0, 0, 1};
+    const double Q[16] = {1, 0, 0, -c.px, 0, 1, 0, -c.py, 0, 0, 0, c.f, 0, 0, 1. / c.b, 0};   // stereo_camera.cpp:24-34
+    M4 TQ;
+    for (int r = 0; r < 4; ++r)
+      for (int cc = 0; cc < 4; ++cc) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += M[r * 4 + k] * Q[k * 4 + cc];
+        TQ.m[cc * 4 + r] = (float)s;
+      }
+    const DtLevel& L = h->lv[l];
+    const dim3 blk(32, 8), grd((L.w + 31) / 32, (L.h + 7) / 8);
+    k_dt_pointcloud<<<grd, blk, 0, h->stream>>>(TQ, h->disp, L.w, L.h, h->disp_stride, L.cloud_stride, 1 << l, h->cloud[l]);
+  }
+  DCK(cudaGetLastError());
+  return SVS_OK;
+}
+
+static int run_pass(svs_dt* h, int level, const double T[7], int want_jac, double sums[kAcc]) {
+  if (!h || level < 0 || level >= h->nlevels || !T) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const DtLevel& L = h->lv[level];
+  const int blocks = std::min(h->max_blocks, std::max(1, (L.w * L.h + kThreads - 1) / kThreads));
+  DCK(cudaMemcpyAsync(h->d_T, T, sizeof(double) * 7, cudaMemcpyHostToDevice, h->stream));
+  k_dt_pass<<<blocks, kThreads, 0, h->stream>>>(L, h->d_T, h->d_partial, (h->flags & SVS_DT_EXACT_BILINEAR) ? 1 : 0, want_jac);
+  std::vector<double> part((size_t)blocks * kAcc);
+  DCK(cudaMemcpyAsync(part.data(), h->d_partial, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream));
+  DCK(cudaStreamSynchronize(h->stream));
+  DCK(cudaGetLastError());
+  for (int i = 0; i < kAcc; ++i) {
+    double s = 0;
+    for (int b = 0; b < blocks; ++b) s += part[(size_t)b * kAcc + i];
+    sums[i] = s;
+  }
+  return SVS_OK;
+}
+
+int svs_dt_chi2(svs_dt* h, int level, const double T[7], double* chi2) {
+  double s[kAcc];
+  int rc = run_pass(h, level, T, 0, s);
+  if (rc) return rc;
+  *chi2 = s[27];
+  return SVS_OK;
+}
+
+int svs_dt_jacobian_reduction(svs_dt* h, int level, const double T[7], double H21[21], double b6[6], double* chi2) {
+  double s[kAcc];
+  int rc = run_pass(h, level, T, 1, s);
+  if (rc) return rc;
+  memcpy(H21, s, sizeof(double) * 21);
+  memcpy(b6, s + 21, sizeof(double) * 6);
+  if (chi2) *chi2 = s[27];
+  return SVS_OK;
+}
+
+int svs_dt_track(svs_dt* h, double T[7], svs_dt_stats* st) {
+  if (!h || !T) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  DCK(cudaMemcpyAsync(h->d_ctl, T, sizeof(double) * 7, cudaMemcpyHostToDevice, h->stream));   // DtCtl::T is first
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, h->stream);
+  int exact = (h->flags & SVS_DT_EXACT_BILINEAR) ? 1 : 0;
+  for (int l = h->nlevels - 1; l >= 0; --l) {
+    DtLevel L = h->lv[l];
+    int blocks = std::min(h->max_blocks, std::max(1, (L.w * L.h + kThreads - 1) / kThreads));
+    DtCtl* ctl = h->d_ctl;
+    double* part = h->d_partial;
+    int level = l;
+    void* args[] = {&L, &ctl, &part, &exact, &level};
+    DCK(cudaLaunchCooperativeKernel((void*)k_dt_track_level, dim3(blocks), dim3(kThreads), args, 0, h->stream));
+  }
+  cudaEventRecord(e1, h->stream);
+  DCK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(DtCtl), cudaMemcpyDeviceToHost, h->stream));
+  DCK(cudaStreamSynchronize(h->stream));
+  DCK(cudaGetLastError());
+  memcpy(T, h->h_ctl->T, sizeof(double) * 7);
+  if (st) {
+    memset(st, 0, sizeof *st);
+    cudaEventElapsedTime(&st->ms_total, e0, e1);
+    for (int l = 0; l < h->nlevels && l < SVS_DT_MAX_LEVELS; ++l) {
+      st->chi2[l] = h->h_ctl->chi2_level[l];
+      st->passes[l] = h->h_ctl->passes_level[l];
+      st->launches += 1;
+    }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return SVS_OK;
+}
+
+}  // extern "C"
