@@ -1,7 +1,2 @@
-SVS_SOLVE_TIMING=1 python - <<'PY'
-import sys; sys.path.insert(0,'.')
-from scavislam_b200 import capi, synth
-pb = synth.make_config("C2"); ba = capi.BundleAdjuster(); ba.set_problem(pb)
-for i in range(2): ba.reset_state(); it, st = ba.optimize(2); print(st["ms_solve"]/st["trials_total"])
-PY
-python -m pytest tests/test_ba_gpu.py -x -q -m gpu 2>&1 | tail -3
+python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+python bench.py --steps 5 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','e2e','kernel_ms_per_step')})"
