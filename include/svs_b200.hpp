@@ -1,0 +1,235 @@
+// svs_b200.hpp -- header-only C++ host layer above the C ABI (svs_b200.h), dependency-free.
+//
+// Mirrors the reference's interfaces for the hot path so that a maintainer can swap the bodies
+// of the corresponding ScaViSLAM methods for calls into this header:
+//
+//   svs::OptParams / svs::Statistics   <->  ScaViSLAM::OptParams (slam_graph.hpp:36-50),
+//                                           SlamGraph::Statistics (slam_graph.hpp:366-386)
+//   svs::StereoGraph::optimize         <->  SlamGraph<SE3,StereoCamera,SE3XYZ_STEREO,3>::optimize
+//                                           (slam_graph.cpp:319-355) = copyDataToG2o + g2o + restore
+//   svs::FastGrid                      <->  ScaViSLAM::FastGrid (fast_grid.h:30-64)
+//   svs::DenseTracker                  <->  ScaViSLAM::DenseTracker / GpuTracker (dense_tracking.h:40-96)
+//   svs::GuidedMatcher                 <->  ScaViSLAM::GuidedMatcher<StereoCamera> (matcher.hpp:62-186)
+//
+// "We do not use C++ exceptions" (reference README:295): errors come back as bool / int; the
+// text is available from last_error().  There is no CPU fallback anywhere in this layer.
+#ifndef SVS_B200_HPP
+#define SVS_B200_HPP
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "svs_b200.h"
+
+namespace svs {
+
+struct SE3d {           // Sophus::SE3 as the C ABI carries it: unit quaternion (x y z w) + translation
+  double q[4] = {0, 0, 0, 1};
+  double t[3] = {0, 0, 0};
+};
+
+struct OptParams {      // slam_graph.hpp:36-50
+  OptParams(int num_iters, bool use_robust_kernel = false, double huber_kernel_width = 1)
+      : num_iters(num_iters), use_robust_kernel(use_robust_kernel), huber_kernel_width(huber_kernel_width) {}
+  int num_iters;
+  bool use_robust_kernel;
+  double huber_kernel_width;
+};
+
+struct Statistics {     // slam_graph.hpp:366-386
+  int num_frame_edges = 0, num_point_edges = 0, num_frames = 0, num_points = 0;
+  double calc_time = 0;
+};
+
+// The double window handed to the optimiser: what SlamGraph::copyDataToG2o walks
+// (slam_graph.cpp:985-1032).  Ids are the caller's (frame ids / point ids, any integers).
+class StereoGraph {
+ public:
+  StereoGraph() { svs_ba_opts o{-1, 0, {0, 0, 0, 0, 0, 0}}; ok_ = svs_ba_create(&o, &h_) == SVS_OK; }
+  ~StereoGraph() { if (h_) svs_ba_destroy(h_); }
+  StereoGraph(const StereoGraph&) = delete;
+  StereoGraph& operator=(const StereoGraph&) = delete;
+  bool valid() const { return ok_; }
+  const char* last_error() const { return h_ ? svs_last_error(h_) : "svs_ba_create failed (no CUDA device)"; }
+
+  void clear() { pose_id_.clear(); T_.clear(); fixed_.clear(); point_id_.clear(); psi_.clear(); ep_.clear(); ef_.clear();
+                 ea_.clear(); obs_.clear(); info_.clear(); ci_.clear(); cj_.clear(); cT_.clear(); cL_.clear(); }
+  void setCamera(double f, double px, double py, double b) { cam_ = svs_cam{f, px, py, b}; }
+  // addPoseToG2o (slam_graph-impl.cpp:29-42)
+  void addPose(int frame_id, const SE3d& T_me_from_w, bool fixed = false) {
+    pose_id_.push_back(frame_id); push7(T_, T_me_from_w); fixed_.push_back(fixed ? 1 : 0);
+  }
+  // addPointToG2o (slam_graph.cpp:907-920): xyz in the anchor frame; stored as psi = invert_depth(xyz)
+  void addPoint(int point_id, const double xyz_anchor[3]) {
+    point_id_.push_back(point_id);
+    psi_.push_back(xyz_anchor[0] / xyz_anchor[2]); psi_.push_back(xyz_anchor[1] / xyz_anchor[2]); psi_.push_back(1. / xyz_anchor[2]);
+  }
+  // addObsToG2o (slam_graph-impl.cpp:44-97): obs = (u, v, u_right), Lambda = diag(lambda)
+  void addObs(const double obs[3], const double lambda_diag[3], int point_id, int frame_id, int anchor_id) {
+    ep_.push_back(point_id); ef_.push_back(frame_id); ea_.push_back(anchor_id);
+    for (int k = 0; k < 3; ++k) { obs_.push_back(obs[k]); info_.push_back(lambda_diag[k]); }
+  }
+  // addConstraintToG2o (slam_graph-impl.cpp:99-126): Lambda row-major 6x6
+  void addConstraint(const SE3d& T_2_from_1, const double Lambda[36], int frame_id_1, int frame_id_2) {
+    ci_.push_back(frame_id_1); cj_.push_back(frame_id_2); push7(cT_, T_2_from_1);
+    cL_.insert(cL_.end(), Lambda, Lambda + 36);
+  }
+
+  // SlamGraph::optimize(const OptParams&, Statistics*) (slam_graph.cpp:319-355).  lambda0 = 50 and
+  // 5 trials as the reference configures g2o (:338, :1073).  Note the reference never applies
+  // huber_kernel_width (slam_graph-impl.cpp:86-90, delta stays 1): pass apply_huber_width = true
+  // for the corrected behaviour.  Returns g2o's optimize() value.
+  int optimize(const OptParams& p, Statistics* stats = nullptr, bool apply_huber_width = false) {
+    if (!ok_) return -100 + SVS_ERR_NOGPU;
+    std::vector<int> ep(ep_.size()), ef(ef_.size()), ea(ea_.size()), ci(ci_.size()), cj(cj_.size());
+    if (!remap(ep_, point_id_, ep) || !remap(ef_, pose_id_, ef) || !remap(ea_, pose_id_, ea) ||
+        !remap(ci_, pose_id_, ci) || !remap(cj_, pose_id_, cj))
+      return -100 + SVS_ERR_INVALID;
+    svs_ba_stats st;
+    const int it = svs_optimiseInnerAndOuterWindow(
+        h_, (int)pose_id_.size(), T_.data(), fixed_.data(), (int)point_id_.size(), psi_.data(), (int)ep.size(), ep.data(),
+        ef.data(), ea.data(), obs_.data(), info_.data(), (int)ci.size(), ci.data(), cj.data(), cT_.data(), cL_.data(), &cam_,
+        p.num_iters, p.use_robust_kernel ? 1 : 0, apply_huber_width ? p.huber_kernel_width : 1.0, &st);
+    if (stats && it > -100) {
+      stats->num_frames = st.num_frames; stats->num_points = st.num_points;
+      stats->num_point_edges = st.num_point_edges; stats->num_frame_edges = st.num_frame_edges;
+      stats->calc_time = st.ms_total * 1e-3;
+    }
+    last_ = st;
+    return it;
+  }
+  // restoreDataFromG2o (slam_graph.cpp:1037-1058)
+  SE3d pose(size_t i) const { SE3d T; memcpy(T.q, &T_[7 * i], 32); memcpy(T.t, &T_[7 * i + 4], 24); return T; }
+  void point_xyz_anchor(size_t i, double xyz[3]) const {   // invert_depth(psi)
+    xyz[0] = psi_[3 * i] / psi_[3 * i + 2]; xyz[1] = psi_[3 * i + 1] / psi_[3 * i + 2]; xyz[2] = 1. / psi_[3 * i + 2];
+  }
+  size_t num_poses() const { return pose_id_.size(); }
+  size_t num_points() const { return point_id_.size(); }
+  const svs_ba_stats& last_stats() const { return last_; }
+
+ private:
+  static void push7(std::vector<double>& v, const SE3d& T) { v.insert(v.end(), T.q, T.q + 4); v.insert(v.end(), T.t, T.t + 3); }
+  static bool remap(const std::vector<int>& ids, const std::vector<int>& table, std::vector<int>& out) {
+    // ids are small windows: sort-free lookup through a flat map over the id range would also do;
+    // a linear probe per distinct id keeps this header free of <unordered_map>
+    int lo = 0, hi = -1;
+    for (int id : table) { if (hi < lo) { lo = hi = id; } if (id < lo) lo = id; if (id > hi) hi = id; }
+    std::vector<int> lut(hi >= lo ? (size_t)(hi - lo + 1) : 0, -1);
+    for (size_t k = 0; k < table.size(); ++k) lut[(size_t)(table[k] - lo)] = (int)k;
+    for (size_t k = 0; k < ids.size(); ++k) {
+      if (ids[k] < lo || ids[k] > hi || lut[(size_t)(ids[k] - lo)] < 0) return false;
+      out[k] = lut[(size_t)(ids[k] - lo)];
+    }
+    return true;
+  }
+  svs_ba* h_ = nullptr;
+  bool ok_ = false;
+  svs_cam cam_{1, 0, 0, 0.5};
+  std::vector<int> pose_id_, point_id_, ep_, ef_, ea_, ci_, cj_;
+  std::vector<double> T_, psi_, obs_, info_, cT_, cL_;
+  std::vector<unsigned char> fixed_;
+  svs_ba_stats last_{};
+};
+
+// ScaViSLAM::FastGrid (fast_grid.h:30-64).  Keypoints come back as flat (x, y) pairs grouped by
+// cell; the quadtree content of keypoint i of cell c is i - cell_off[c].
+class FastGrid {
+ public:
+  FastGrid(int img_w, int img_h, int num_features_per_cell, int boundary_per_cell, int fast_thr, int grid_w, int grid_h,
+           int fast_min = 10, int fast_max = 40, int max_keypoints = 200000)
+      : cells_((size_t)grid_w * grid_h), max_kp_(max_keypoints) {
+    ok_ = svs_fast_create(-1, img_w, img_h, max_keypoints, &h_) == SVS_OK &&
+          svs_fast_grid_init(img_w, img_h, num_features_per_cell, boundary_per_cell, fast_thr, grid_w, grid_h, fast_min,
+                             fast_max, &grid_, cells_.data()) == SVS_OK;
+  }
+  ~FastGrid() { if (h_) svs_fast_destroy(h_); }
+  FastGrid(const FastGrid&) = delete;
+  FastGrid& operator=(const FastGrid&) = delete;
+  bool valid() const { return ok_; }
+  const std::vector<svs_fast_cell>& cell_grid2d() const { return cells_; }
+  // detectAdaptively(img, trials, qt)
+  int detectAdaptively(const unsigned char* img, int pitch, int w, int h, int trials, std::vector<int>* xy,
+                       std::vector<int>* cell_off) {
+    if (!ok_ || svs_fast_set_image(h_, img, pitch, w, h) != SVS_OK) return -1;
+    xy->resize(2 * (size_t)max_kp_); cell_off->resize(cells_.size() + 1);
+    const int n = svs_fast_detect_adaptively(h_, &grid_, cells_.data(), trials, xy->data(), max_kp_, cell_off->data());
+    if (n >= 0) xy->resize(2 * (size_t)(n < max_kp_ ? n : max_kp_));
+    return n;
+  }
+  // static FastGrid::detect(img, cell_grid2d, qt)
+  int detect(const unsigned char* img, int pitch, int w, int h, const std::vector<svs_fast_cell>& cells,
+             std::vector<int>* xy, std::vector<int>* cell_off) {
+    if (!ok_ || svs_fast_set_image(h_, img, pitch, w, h) != SVS_OK) return -1;
+    xy->resize(2 * (size_t)max_kp_); cell_off->resize(cells.size() + 1);
+    const int n = svs_fast_detect(h_, cells.data(), (int)cells.size(), xy->data(), max_kp_, cell_off->data());
+    if (n >= 0) xy->resize(2 * (size_t)(n < max_kp_ ? n : max_kp_));
+    return n;
+  }
+
+ private:
+  svs_fast* h_ = nullptr;
+  bool ok_ = false;
+  svs_fast_grid_params grid_{};
+  std::vector<svs_fast_cell> cells_;
+  int max_kp_;
+};
+
+// ScaViSLAM::DenseTracker (GPU path)
+class DenseTracker {
+ public:
+  DenseTracker(int w0, int h0, int nlevels = 3, int flags = 0) { ok_ = svs_dt_create(-1, w0, h0, nlevels, flags, &h_) == SVS_OK; }
+  ~DenseTracker() { if (h_) svs_dt_destroy(h_); }
+  DenseTracker(const DenseTracker&) = delete;
+  DenseTracker& operator=(const DenseTracker&) = delete;
+  bool valid() const { return ok_; }
+  svs_dt* handle() { return h_; }
+  // denseTrackingGpu(SE3 * T_cur_from_actkey)
+  bool denseTrackingGpu(SE3d* T_cur_from_actkey, svs_dt_stats* stats = nullptr) {
+    double T[7];
+    memcpy(T, T_cur_from_actkey->q, 32); memcpy(T + 4, T_cur_from_actkey->t, 24);
+    if (!ok_ || svs_dt_track(h_, T, stats) != SVS_OK) return false;
+    memcpy(T_cur_from_actkey->q, T, 32); memcpy(T_cur_from_actkey->t, T + 4, 24);
+    return true;
+  }
+  // computeDensePointCloudGpu(const SE3 & T_cur_from_actkey)
+  bool computeDensePointCloudGpu(const SE3d& T_cur_from_actkey, const svs_cam* level_cams) {
+    double T[7];
+    memcpy(T, T_cur_from_actkey.q, 32); memcpy(T + 4, T_cur_from_actkey.t, 24);
+    return ok_ && svs_dt_compute_point_cloud(h_, T, level_cams) == SVS_OK;
+  }
+
+ private:
+  svs_dt* h_ = nullptr;
+  bool ok_ = false;
+};
+
+// ScaViSLAM::GuidedMatcher<StereoCamera>
+class GuidedMatcher {
+ public:
+  GuidedMatcher(const std::vector<svs_match_level>& cam_vec, int max_keyframes = 8, int max_points = 8192,
+                int max_keypoints = 65536) {
+    ok_ = svs_matcher_create(-1, (int)cam_vec.size(), cam_vec.data(), max_keyframes, max_points, max_keypoints, &h_) == SVS_OK;
+  }
+  ~GuidedMatcher() { if (h_) svs_matcher_destroy(h_); }
+  GuidedMatcher(const GuidedMatcher&) = delete;
+  GuidedMatcher& operator=(const GuidedMatcher&) = delete;
+  bool valid() const { return ok_; }
+  svs_matcher* handle() { return h_; }
+  // match(keyframe_map, T_cur_from_actkey, cur_frame, feature_tree, cam_vec, actkey_id, vertex_map, ap_map,
+  //       SEARCHRADIUS, thr_mean, thr_std, track_data): frames/keyframes/features are set on the handle first
+  int match(const double T_cur_from_actkey[7], const double T_actkey_from_w[7], const std::vector<svs_match_point>& ap_map,
+            int SEARCHRADIUS, int thr_mean, int thr_std, std::vector<svs_match_result>* track_data) {
+    track_data->resize(ap_map.size());
+    if (!ok_) return -1;
+    return svs_match(h_, T_cur_from_actkey, T_actkey_from_w, ap_map.data(), (int)ap_map.size(), SEARCHRADIUS, thr_mean,
+                     thr_std, track_data->data());
+  }
+
+ private:
+  svs_matcher* h_ = nullptr;
+  bool ok_ = false;
+};
+
+}  // namespace svs
+#endif

@@ -21,7 +21,7 @@ size_t build_smem_bytes(int warps, int Kmax) {
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-k_build(BaDev d, int lm_begin, int lm_end, int Kmax, int robust, double delta, int n_lm_blocks) {
+k_build(BaDev d, const int* __restrict__ lm_list, int n_list, int Kmax, int robust, double delta, int n_lm_blocks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const LmCtl* __restrict__ ctl = d.ctl;
   const int cur = ctl->cur;
@@ -31,8 +31,9 @@ k_build(BaDev d, int lm_begin, int lm_end, int Kmax, int robust, double delta, i
     return;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = lm_begin + (int)blockIdx.x * WARPS + warp;
-  if (li >= lm_end) return;
+  const int idx = (int)blockIdx.x * WARPS + warp;
+  if (idx >= n_list) return;
+  const int li = lm_list ? lm_list[idx] : idx;
   const double lambda = ctl->lambda;
 
   const int wd = build_warp_doubles(Kmax);
@@ -76,71 +77,10 @@ k_build(BaDev d, int lm_begin, int lm_end, int Kmax, int robust, double delta, i
     const int e = e0 + lane;
     const int ip = d.e_pose[e];
     sPose[lane + off] = ip;   // for the self edge (lane 0, off 0) this rewrites the anchor
-    const double obs[3] = {__ldg(d.e_obs + e), __ldg(d.e_obs + (size_t)d.E + e), __ldg(d.e_obs + 2 * (size_t)d.E + e)};
-    const double om[3] = {__ldg(d.e_w + e), __ldg(d.e_w + (size_t)d.E + e), __ldg(d.e_w + 2 * (size_t)d.E + e)};
-    double Rc[9], tc[3], R[9], t[3], y[3], er[3];
-    load12(Rt, ip, Rc, tc);
-    rel_pose(Rc, tc, Ra, ta, R, t);
-    mat3_vec(R, xa, y);
-    y[0] += t[0]; y[1] += t[1]; y[2] += t[2];
-    stereo_residual(d, y, obs, er);
-    const double e2 = er[0] * er[0] * om[0] + er[1] * er[1] * om[1] + er[2] * er[2] * om[2];
-    double r0 = e2, r1 = 1.;
-    if (robust) huber(e2, delta, r0, r1);
-    chi = r0;
-    const double sw[3] = {sqrt(r1 * om[0]), sqrt(r1 * om[1]), sqrt(r1 * om[2])};   // sqrt(rho' Omega)
-    // d_stereoproj_d_y (transformations.h:62-71): rows (a 0 c0) (0 a c1) (a 0 c2)
-    const double iz = 1. / y[2];
-    const double a = d.f * iz;
-    const double c0 = -(d.f * y[0]) * iz * iz, c1 = -(d.f * y[1]) * iz * iz, c2 = -(d.f * (y[0] - d.b)) * iz * iz;
-    double* Jp = sJp + kSJ * lane;
-    double* Ja = sJa + kSJ * lane;
-    double* Js = sJs + 9 * lane;
-    // J_pose = -Jcam [I | -hat(y)]  (anchored_points.cpp:187, transformations.h:73-80)
-    const int fp = d.fixed[ip];
-    const double zp = fp ? 0. : 1.;
-    Jp[0] = zp * sw[0] * -a;  Jp[1] = 0;                 Jp[2] = zp * sw[0] * -c0;
-    Jp[3] = zp * sw[0] * (-c0 * y[1]);  Jp[4] = zp * sw[0] * (-a * y[2] + c0 * y[0]);  Jp[5] = zp * sw[0] * (a * y[1]);
-    Jp[6] = 0;                Jp[7] = zp * sw[1] * -a;   Jp[8] = zp * sw[1] * -c1;
-    Jp[9] = zp * sw[1] * (a * y[2] - c1 * y[1]);  Jp[10] = zp * sw[1] * (c1 * y[0]);  Jp[11] = zp * sw[1] * (-a * y[0]);
-    Jp[12] = zp * sw[2] * -a; Jp[13] = 0;                Jp[14] = zp * sw[2] * -c2;
-    Jp[15] = zp * sw[2] * (-c2 * y[1]); Jp[16] = zp * sw[2] * (-a * y[2] + c2 * y[0]); Jp[17] = zp * sw[2] * (a * y[1]);
-    // J_anchor = Jcam R [I | -hat(x_a)]  (anchored_points.cpp:188)
-    const double za = fa ? 0. : 1.;
-    double M[9];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      M[j] = a * R[j] + c0 * R[6 + j];
-      M[3 + j] = a * R[3 + j] + c1 * R[6 + j];
-      M[6 + j] = a * R[j] + c2 * R[6 + j];
-    }
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const double s = za * sw[q];
-      Ja[q * 6 + 0] = s * M[q * 3 + 0];
-      Ja[q * 6 + 1] = s * M[q * 3 + 1];
-      Ja[q * 6 + 2] = s * M[q * 3 + 2];
-      Ja[q * 6 + 3] = s * -(M[q * 3 + 1] * xa[2] - M[q * 3 + 2] * xa[1]);
-      Ja[q * 6 + 4] = s * -(-M[q * 3 + 0] * xa[2] + M[q * 3 + 2] * xa[0]);
-      Ja[q * 6 + 5] = s * -(M[q * 3 + 0] * xa[1] - M[q * 3 + 1] * xa[0]);
-    }
-    // J_psi = -Jcam d_Tinvpsi_d_psi (anchored_points.cpp:186, transformations.h:82-95)
-    double N[9];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      N[i * 3 + 0] = R[i * 3 + 0] * ipz;
-      N[i * 3 + 1] = R[i * 3 + 1] * ipz;
-      N[i * 3 + 2] = -(y[i] - t[i]) * ipz;
-    }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      Js[j] = -sw[0] * (a * N[j] + c0 * N[6 + j]);
-      Js[3 + j] = -sw[1] * (a * N[3 + j] + c1 * N[6 + j]);
-      Js[6 + j] = -sw[2] * (a * N[j] + c2 * N[6 + j]);
-    }
-    sE[3 * lane + 0] = sw[0] * er[0];
-    sE[3 * lane + 1] = sw[1] * er[1];
-    sE[3 * lane + 2] = sw[2] * er[2];
+    chi = linearize_edge(d, Rt, e, ip, Ra, ta, xa, ipz, fa, robust, delta, sJp + kSJ * lane, sJa + kSJ * lane,
+                         sJs + 9 * lane, sE + 3 * lane);
+    const double* Jp = sJp + kSJ * lane;
+    const double* Js = sJs + 9 * lane;
     // own Hpl block B = J~p^T J~psi (6x3); the self edge's block is cancelled by its anchor part
     if (!(has_self && lane == 0)) {
       double* B = sB + kSJ * (lane + off);
@@ -250,10 +190,14 @@ k_build(BaDev d, int lm_begin, int lm_end, int Kmax, int robust, double delta, i
   }
 }
 
-void launch_build(const BaDev& d, int lm_begin, int lm_end, int Kmax, int robust, double delta, cudaStream_t st) {
+void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st);
+
+// Dispatch: landmark groups with <= 8 frames go to k_build_wave (ba_build_wave.cu); the rest (long
+// tracks, landmarks without observations) and the pose-pose constraints to k_build.
+void launch_build(const BaDev& d, int Kmax, int robust, double delta, cudaStream_t st) {
   constexpr int WARPS = 8;
-  const int nl = lm_end - lm_begin;
-  const int n_lm_blocks = (nl + WARPS - 1) / WARPS;
+  launch_build_wave(d, robust, delta, st);
+  const int n_lm_blocks = (d.ngen + WARPS - 1) / WARPS;
   const int n_c_blocks = (d.C + WARPS * 32 - 1) / (WARPS * 32);
   const size_t smem = build_smem_bytes(WARPS, Kmax);
   static size_t configured = 0;
@@ -262,7 +206,7 @@ void launch_build(const BaDev& d, int lm_begin, int lm_end, int Kmax, int robust
     configured = smem;
   }
   if (n_lm_blocks + n_c_blocks == 0) return;
-  k_build<WARPS><<<n_lm_blocks + n_c_blocks, WARPS * 32, smem, st>>>(d, lm_begin, lm_end, Kmax, robust, delta, n_lm_blocks);
+  k_build<WARPS><<<n_lm_blocks + n_c_blocks, WARPS * 32, smem, st>>>(d, d.gen_lm, d.ngen, Kmax, robust, delta, n_lm_blocks);
 }
 
 }  // namespace svs

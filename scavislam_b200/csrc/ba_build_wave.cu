@@ -1,0 +1,301 @@
+// ba_build_wave.cu -- k_build_wave: the fused linearise + J^T W J + landmark elimination + Schur
+// scatter for landmark groups that share one (anchor, observer set) with at most 8 frames --
+// the bulk of a SLAM window.  Same mathematics as k_build (ba_build.cu), different mapping:
+//
+//   * a warp owns a TASK: up to `chunk` consecutive landmarks with identical slot lists, so all
+//     of them scatter into the same K(K+1)/2 blocks of the reduced camera system;
+//   * edges are linearised 32 at a time (one lane per edge, several landmarks per wave), which
+//     keeps every lane busy where one-warp-per-landmark leaves 3/4 of them idle;
+//   * the Schur products Y_m B_n^T (and the direct J^T W J terms) are accumulated over all
+//     landmarks of the task in registers -- each lane owns up to 7 (pair, row) units of 6 doubles --
+//     and flushed with ONE set of RED.F64 per task instead of one per landmark
+//     (measured on B200: 450 G coalesced FP64 reductions/s, scripts/ubench/lat.cu -- the
+//     per-landmark scatter alone would cost 39 us on the 200-keyframe window).
+//
+// Reference semantics: G2oEdgeProjectPSI2UVU::linearizeOplus (anchored_points.cpp:168-189), g2o
+// BaseMultiEdge::constructQuadraticForm, BlockSolver<6,3>::buildSystem / solve (Schur part).
+#include "ba_dev.cuh"
+#include "ba_kernels.cuh"
+
+namespace svs {
+
+constexpr int kWvWarps = 4;
+constexpr int kWvLm = 8;       // landmarks per wave
+constexpr int kWvSlots = 40;   // slots per wave
+constexpr int kWvJ = 19;       // row stride of the per-edge Jacobian rows (odd: conflict-free 64-bit stores)
+constexpr int kWvLmD = 56;     // per-landmark scratch: D(6) bl(3) Dinv(9) A_aa(36) + pad
+constexpr int kWvDoubles = 2 * 32 * kWvJ + 32 * 9 + 32 * 3 + 2 * kWvSlots * 18 + kWvLm * kWvLmD + 32;
+constexpr int kWvInts = 8 + 40;   // slot poses, pair table (36) padded
+
+size_t build_wave_smem_bytes() { return (size_t)kWvWarps * (kWvDoubles * 8 + kWvInts * 4); }
+
+__global__ void __launch_bounds__(kWvWarps * 32)
+k_build_wave(BaDev d, int robust, double delta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int task = (int)blockIdx.x * kWvWarps + warp;
+  if (task >= d.ntasks) return;
+  const LmCtl* __restrict__ ctl = d.ctl;
+  const int cur = ctl->cur;
+  const double lambda = ctl->lambda;
+  double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kWvDoubles;
+  double* sJp = sm;
+  double* sJa = sJp + 32 * kWvJ;
+  double* sJs = sJa + 32 * kWvJ;
+  double* sE = sJs + 32 * 9;
+  double* sB = sE + 32 * 3;
+  double* sY = sB + kWvSlots * 18;
+  double* sLm = sY + kWvSlots * 18;
+  double* sChi = sLm + kWvLm * kWvLmD;
+  int* si = reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw) + (size_t)kWvWarps * kWvDoubles) + warp * kWvInts;
+  int* sPose = si;
+  int* sPair = si + 8;
+
+  const int lm0 = d.task_lm[task], nlm = d.task_cnt[task];
+  const int e_base = d.lm_eptr[lm0], k = d.lm_eptr[lm0 + 1] - e_base;
+  const int s_base = d.lm_sptr[lm0], K = d.lm_sptr[lm0 + 1] - s_base;
+  const int has_self = d.lm_self[lm0];
+  const int off = has_self ? 0 : 1;
+  const int i_first = has_self ? 1 : 0;
+  const int ia = d.lm_anchor[lm0];
+  const int fa = d.fixed[ia];
+  const int skip_self = d.flags & 1;
+  const double* __restrict__ Rt = d.Rt[cur];
+  double Ra[9], ta[3];
+  load12(Rt, ia, Ra, ta);
+
+  // slot poses and the pair table, ordered by kind so that the 32 units of a round mostly share a
+  // code path: anchor-row pairs (0,n), diagonal pairs (m,m), (0,0), then the plain pairs
+  if (lane == 0) sPose[0] = ia;
+  if (lane < k && !(has_self && lane == 0)) sPose[lane + off] = d.e_pose[e_base + lane];
+  __syncwarp();
+  const int npairs = K * (K + 1) / 2;
+  for (int p = lane; p < npairs; p += 32) {
+    int m, n;
+    if (p < K - 1) { m = 0; n = 1 + p; }
+    else if (p < 2 * K - 2) { m = n = 1 + p - (K - 1); }
+    else if (p == 2 * K - 2) { m = n = 0; }
+    else {
+      int rem = p - (2 * K - 1);
+      m = 1;
+      while (rem >= K - 1 - m) { rem -= K - 1 - m; ++m; }
+      n = m + 1 + rem;
+    }
+    const int t = d.tbl[(size_t)sPose[m] * d.P + sPose[n]];
+    sPair[p] = ((t >> 1) << 11) | ((t & 1) << 10) | (m << 5) | n;
+  }
+  __syncwarp();
+
+  const int nunits = npairs * 6;
+  double acc[7][6];
+#pragma unroll
+  for (int q = 0; q < 7; ++q)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[q][c] = 0.;
+  double accg[2] = {0., 0.}, accc[2] = {0., 0.};
+
+  int nw_max = 32 / k;
+  if (nw_max > kWvSlots / K) nw_max = kWvSlots / K;
+  if (nw_max > kWvLm) nw_max = kWvLm;
+
+  for (int w0 = 0; w0 < nlm; w0 += nw_max) {
+    const int nw = min(nw_max, nlm - w0);
+    // ---- phase 1: one lane per edge of the wave
+    double chi = 0.;
+    if (lane < nw * k) {
+      const int j = lane / k, i = lane - j * k;
+      const int li = lm0 + w0 + j;
+      const int e = e_base + (w0 + j) * k + i;
+      const double* __restrict__ psi = d.psi[cur] + 3 * (size_t)li;
+      const double p0 = __ldg(psi), p1 = __ldg(psi + 1), p2 = __ldg(psi + 2);
+      const double ipz = 1. / p2;
+      const double xa[3] = {p0 * ipz, p1 * ipz, ipz};
+      const int ip = (has_self && i == 0) ? ia : sPose[i + off];
+      double* Jp = sJp + kWvJ * lane;
+      double* Js = sJs + 9 * lane;
+      chi = linearize_edge(d, Rt, e, ip, Ra, ta, xa, ipz, fa, robust, delta, Jp, sJa + kWvJ * lane, Js, sE + 3 * lane);
+      if (!(has_self && i == 0)) {   // own Hpl block B = J~p^T J~psi
+        double* B = sB + 18 * (j * K + i + off);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) B[r * 3 + c] = Jp[r] * Js[c] + Jp[6 + r] * Js[3 + c] + Jp[12 + r] * Js[6 + c];
+      }
+    }
+    sChi[lane] = chi;
+    __syncwarp();
+    if (lane < nw) {
+      double s = 0.;
+      for (int i = 0; i < k; ++i) s += sChi[lane * k + i];
+      d.chi_l[lm0 + w0 + lane] = s;
+    }
+    // ---- phase 2: per-landmark sums over its edges: anchor Hpl block (18), Hll (6), b_l (3), A_aa (21)
+    for (int it = lane; it < nw * 48; it += 32) {
+      const int j = it / 48, t = it - j * 48;
+      const int l0 = j * k;
+      double s = 0.;
+      if (t < 18) {
+        const int r = t / 3, c = t - r * 3;
+        for (int i = i_first; i < k; ++i) {
+          const double* Ja = sJa + kWvJ * (l0 + i);
+          const double* Js = sJs + 9 * (l0 + i);
+          s += Ja[r] * Js[c] + Ja[6 + r] * Js[3 + c] + Ja[12 + r] * Js[6 + c];
+        }
+        sB[18 * (j * K) + t] = s;
+      } else if (t < 24) {
+        const int u = t - 18;
+        const int r = u < 3 ? 0 : (u < 5 ? 1 : 2), c = u < 3 ? u : (u < 5 ? u - 2 : 2);
+        for (int i = 0; i < k; ++i) {
+          const double* Js = sJs + 9 * (l0 + i);
+          s += Js[r] * Js[c] + Js[3 + r] * Js[3 + c] + Js[6 + r] * Js[6 + c];
+        }
+        sLm[j * kWvLmD + u] = s;
+      } else if (t < 27) {
+        const int c = t - 24;
+        for (int i = 0; i < k; ++i) {
+          const double* Js = sJs + 9 * (l0 + i);
+          const double* Ee = sE + 3 * (l0 + i);
+          s -= Js[c] * Ee[0] + Js[3 + c] * Ee[1] + Js[6 + c] * Ee[2];
+        }
+        sLm[j * kWvLmD + 6 + c] = s;
+      } else {
+        // anchor diagonal: all edges' J~a^T J~a; the self edge keeps g2o's J1^T W J1
+        int u = t - 27, r = 0;
+        while (u > r) { u -= r + 1; ++r; }
+        const int c = u;
+        for (int i = (skip_self ? i_first : 0); i < k; ++i) {
+          const double* Ja = sJa + kWvJ * (l0 + i);
+          s += Ja[r] * Ja[c] + Ja[6 + r] * Ja[6 + c] + Ja[12 + r] * Ja[12 + c];
+        }
+        sLm[j * kWvLmD + 18 + r * 6 + c] = s;
+        sLm[j * kWvLmD + 18 + c * 6 + r] = s;
+      }
+    }
+    __syncwarp();
+    // ---- phase 3: (Hll + lambda I)^-1 per landmark; Hll / b_l to HBM for the back-substitution
+    if (lane < nw) {
+      double Di[9];
+      inv3_sym_lambda(sLm + lane * kWvLmD, lambda, Di);
+#pragma unroll
+      for (int q = 0; q < 9; ++q) sLm[lane * kWvLmD + 9 + q] = Di[q];
+    }
+    for (int it = lane; it < nw * 9; it += 32) {
+      const int j = it / 9, t = it - j * 9;
+      d.Dbl[12 * (size_t)(lm0 + w0 + j) + t] = sLm[j * kWvLmD + t];
+    }
+    __syncwarp();
+    // ---- phase 4: Y = B Dinv per slot; spill B (Hpl) to HBM, SoA over slots
+    const int nslots_w = nw * K;
+    for (int it = lane; it < nslots_w * 18; it += 32) {
+      const int sg = it / 18, rc = it - sg * 18, r = rc / 3, c = rc - r * 3;
+      const double* B = sB + 18 * sg + r * 3;
+      const double* Di = sLm + (sg / K) * kWvLmD + 9;
+      sY[18 * sg + rc] = B[0] * Di[c] + B[1] * Di[3 + c] + B[2] * Di[6 + c];
+    }
+    {
+      const size_t s0 = (size_t)s_base + (size_t)w0 * K;
+      for (int c = 0; c < 18; ++c)
+        for (int sg = lane; sg < nslots_w; sg += 32) d.W[(size_t)c * d.nslots + s0 + sg] = sB[18 * sg + c];
+    }
+    __syncwarp();
+    // ---- phase 5: accumulate the task's contribution to the reduced system in registers
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const int u = lane + 32 * q;
+      if (u < nunits) {
+        const int p = u / 6, r = u - p * 6;
+        const int pk = sPair[p];
+        const int m = (pk >> 5) & 31, n = pk & 31;
+        for (int j = 0; j < nw; ++j) {
+          const double* Ym = sY + 18 * (j * K + m) + r * 3;
+          const double* Bn = sB + 18 * (j * K + n);
+          const double y0 = Ym[0], y1 = Ym[1], y2 = Ym[2];
+          double v[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) v[c] = -(y0 * Bn[c * 3] + y1 * Bn[c * 3 + 1] + y2 * Bn[c * 3 + 2]);
+          if (m == n) {
+            if (m > 0) {
+              const double* Jp = sJp + kWvJ * (j * k + m - off);
+              const double a0 = Jp[r], a1 = Jp[6 + r], a2 = Jp[12 + r];
+#pragma unroll
+              for (int c = 0; c < 6; ++c) v[c] += a0 * Jp[c] + a1 * Jp[6 + c] + a2 * Jp[12 + c];
+            } else {
+              const double* A = sLm + j * kWvLmD + 18 + r * 6;
+#pragma unroll
+              for (int c = 0; c < 6; ++c) v[c] += A[c];
+            }
+          } else if (m == 0) {
+            const double* Ja = sJa + kWvJ * (j * k + n - off);
+            const double* Jp = sJp + kWvJ * (j * k + n - off);
+            const double a0 = Ja[r], a1 = Ja[6 + r], a2 = Ja[12 + r];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) v[c] += a0 * Jp[c] + a1 * Jp[6 + c] + a2 * Jp[12 + c];
+          }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[q][c] += v[c];
+        }
+      }
+    }
+    // ---- phase 6: gradients bp = -J^T W e, bc = Y b_l
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int it = lane + 32 * q;
+      if (it < K * 6) {
+        const int s = it / 6, r = it - s * 6;
+        for (int j = 0; j < nw; ++j) {
+          double g = 0.;
+          if (s > 0) {
+            const int l = j * k + s - off;
+            g = -(sJp[kWvJ * l + r] * sE[3 * l] + sJp[kWvJ * l + 6 + r] * sE[3 * l + 1] + sJp[kWvJ * l + 12 + r] * sE[3 * l + 2]);
+          } else {
+            for (int i = i_first; i < k; ++i) {
+              const int l = j * k + i;
+              g -= sJa[kWvJ * l + r] * sE[3 * l] + sJa[kWvJ * l + 6 + r] * sE[3 * l + 1] + sJa[kWvJ * l + 12 + r] * sE[3 * l + 2];
+            }
+          }
+          const double* Y = sY + 18 * (j * K + s) + r * 3;
+          const double* bl = sLm + j * kWvLmD + 6;
+          accg[q] += g;
+          accc[q] += Y[0] * bl[0] + Y[1] * bl[1] + Y[2] * bl[2];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // ---- flush: one RED.F64 per accumulated element for the whole task
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const int u = lane + 32 * q;
+    if (u < nunits) {
+      const int p = u / 6, r = u - p * 6;
+      const int pk = sPair[p];
+      double* blk = d.S + 36 * (size_t)(pk >> 11);
+      const int tr = (pk >> 10) & 1;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) atomicAdd(blk + (tr ? c * 6 + r : r * 6 + c), acc[q][c]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int it = lane + 32 * q;
+    if (it < K * 6) {
+      const int s = it / 6, r = it - s * 6;
+      const int p = sPose[s];
+      atomicAdd(d.bp + 6 * p + r, accg[q]);
+      atomicAdd(d.bc + 6 * p + r, accc[q]);
+    }
+  }
+}
+
+void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st) {
+  if (d.ntasks == 0) return;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_build_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_wave_smem_bytes());
+    configured = true;
+  }
+  const int blocks = (d.ntasks + kWvWarps - 1) / kWvWarps;
+  k_build_wave<<<blocks, kWvWarps * 32, build_wave_smem_bytes(), st>>>(d, robust, delta);
+}
+
+}  // namespace svs

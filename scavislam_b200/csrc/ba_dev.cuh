@@ -181,4 +181,77 @@ __device__ inline void constraint_build(const BaDev& d, const double* __restrict
   }
 }
 
+
+// One observation edge: residual, robust weight and the three Jacobian blocks of
+// G2oEdgeProjectPSI2UVU (anchored_points.cpp:148-189), each row scaled by sqrt(rho' * Omega_qq):
+//   Jp[3][6] wrt the observing pose, Ja[3][6] wrt the anchor pose, Js[3][3] wrt psi, Ee[3] = scaled error.
+// Returns the robust cost rho(e^T Omega e).
+__device__ __forceinline__ double linearize_edge(const BaDev& d, const double* __restrict__ Rt, int e, int ip,
+                                               const double Ra[9], const double ta[3], const double xa[3], double ipz,
+                                               int fa, int robust, double delta, double* __restrict__ Jp,
+                                               double* __restrict__ Ja, double* __restrict__ Js, double* __restrict__ Ee) {
+  const double obs[3] = {__ldg(d.e_obs + e), __ldg(d.e_obs + (size_t)d.E + e), __ldg(d.e_obs + 2 * (size_t)d.E + e)};
+  const double om[3] = {__ldg(d.e_w + e), __ldg(d.e_w + (size_t)d.E + e), __ldg(d.e_w + 2 * (size_t)d.E + e)};
+  double Rc[9], tc[3], R[9], t[3], y[3], er[3];
+  load12(Rt, ip, Rc, tc);
+  rel_pose(Rc, tc, Ra, ta, R, t);
+  mat3_vec(R, xa, y);
+  y[0] += t[0]; y[1] += t[1]; y[2] += t[2];
+  stereo_residual(d, y, obs, er);
+  const double e2 = er[0] * er[0] * om[0] + er[1] * er[1] * om[1] + er[2] * er[2] * om[2];
+  double r0 = e2, r1 = 1.;
+  if (robust) huber(e2, delta, r0, r1);
+  const double sw[3] = {sqrt(r1 * om[0]), sqrt(r1 * om[1]), sqrt(r1 * om[2])};   // sqrt(rho' Omega)
+  // d_stereoproj_d_y (transformations.h:62-71): rows (a 0 c0) (0 a c1) (a 0 c2)
+  const double iz = 1. / y[2];
+  const double a = d.f * iz;
+  const double c0 = -(d.f * y[0]) * iz * iz, c1 = -(d.f * y[1]) * iz * iz, c2 = -(d.f * (y[0] - d.b)) * iz * iz;
+  // J_pose = -Jcam [I | -hat(y)]  (anchored_points.cpp:187, transformations.h:73-80)
+  const int fp = d.fixed[ip];
+  const double zp = fp ? 0. : 1.;
+  Jp[0] = zp * sw[0] * -a;  Jp[1] = 0;                 Jp[2] = zp * sw[0] * -c0;
+  Jp[3] = zp * sw[0] * (-c0 * y[1]);  Jp[4] = zp * sw[0] * (-a * y[2] + c0 * y[0]);  Jp[5] = zp * sw[0] * (a * y[1]);
+  Jp[6] = 0;                Jp[7] = zp * sw[1] * -a;   Jp[8] = zp * sw[1] * -c1;
+  Jp[9] = zp * sw[1] * (a * y[2] - c1 * y[1]);  Jp[10] = zp * sw[1] * (c1 * y[0]);  Jp[11] = zp * sw[1] * (-a * y[0]);
+  Jp[12] = zp * sw[2] * -a; Jp[13] = 0;                Jp[14] = zp * sw[2] * -c2;
+  Jp[15] = zp * sw[2] * (-c2 * y[1]); Jp[16] = zp * sw[2] * (-a * y[2] + c2 * y[0]); Jp[17] = zp * sw[2] * (a * y[1]);
+  // J_anchor = Jcam R [I | -hat(x_a)]  (anchored_points.cpp:188)
+  const double za = fa ? 0. : 1.;
+  double M[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    M[j] = a * R[j] + c0 * R[6 + j];
+    M[3 + j] = a * R[3 + j] + c1 * R[6 + j];
+    M[6 + j] = a * R[j] + c2 * R[6 + j];
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const double s = za * sw[q];
+    Ja[q * 6 + 0] = s * M[q * 3 + 0];
+    Ja[q * 6 + 1] = s * M[q * 3 + 1];
+    Ja[q * 6 + 2] = s * M[q * 3 + 2];
+    Ja[q * 6 + 3] = s * -(M[q * 3 + 1] * xa[2] - M[q * 3 + 2] * xa[1]);
+    Ja[q * 6 + 4] = s * -(-M[q * 3 + 0] * xa[2] + M[q * 3 + 2] * xa[0]);
+    Ja[q * 6 + 5] = s * -(M[q * 3 + 0] * xa[1] - M[q * 3 + 1] * xa[0]);
+  }
+  // J_psi = -Jcam d_Tinvpsi_d_psi (anchored_points.cpp:186, transformations.h:82-95)
+  double N[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    N[i * 3 + 0] = R[i * 3 + 0] * ipz;
+    N[i * 3 + 1] = R[i * 3 + 1] * ipz;
+    N[i * 3 + 2] = -(y[i] - t[i]) * ipz;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    Js[j] = -sw[0] * (a * N[j] + c0 * N[6 + j]);
+    Js[3 + j] = -sw[1] * (a * N[3 + j] + c1 * N[6 + j]);
+    Js[6 + j] = -sw[2] * (a * N[j] + c2 * N[6 + j]);
+  }
+  Ee[0] = sw[0] * er[0];
+  Ee[1] = sw[1] * er[1];
+  Ee[2] = sw[2] * er[2];
+  return r0;
+}
+
 }  // namespace svs

@@ -35,6 +35,7 @@ struct svs_ba {
   double* d_psi0 = nullptr;
   std::vector<int> lm_to_user;  // internal landmark -> caller's index
   int Kmax = 1;
+  int Kmax_gen = 1;
   int nnzb_S = 0;
   int C_edges = 0;
   int max_col_blocks = 0;
@@ -357,6 +358,33 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     ns += l_K[l];
   }
   lm_eptr[L] = ne; lm_sptr[L] = ns;
+  // ---- work lists of the fused kernel: runs of landmarks with identical slot lists (<= 8 frames)
+  std::vector<int> task_lm, task_cnt, gen_lm;
+  int Kmax_gen = 1;
+  {
+    int chunk = L / (148 * 16);
+    chunk = chunk < 4 ? 4 : (chunk > 32 ? 32 : chunk);
+    if (getenv("SVS_BUILD_V1")) chunk = 0;   // A/B switch: everything through the one-warp-per-landmark kernel
+    auto same_slots = [&](int la, int lb) {   // internal indices
+      const int ka = lm_eptr[la + 1] - lm_eptr[la], kb = lm_eptr[lb + 1] - lm_eptr[lb];
+      if (ka != kb || lm_anchor[la] != lm_anchor[lb] || lm_self[la] != lm_self[lb]) return false;
+      for (int i = 0; i < ka; ++i)
+        if (ie_pose[lm_eptr[la] + i] != ie_pose[lm_eptr[lb] + i]) return false;
+      return true;
+    };
+    for (int li = 0; li < L; ++li) {
+      const int kk = lm_eptr[li + 1] - lm_eptr[li], KK = lm_sptr[li + 1] - lm_sptr[li];
+      if (chunk == 0 || kk == 0 || KK > 8) {
+        gen_lm.push_back(li);
+        Kmax_gen = std::max(Kmax_gen, KK);
+        continue;
+      }
+      if (!task_lm.empty() && task_lm.back() + task_cnt.back() == li && task_cnt.back() < chunk &&
+          same_slots(task_lm.back(), li))
+        task_cnt.back()++;
+      else { task_lm.push_back(li); task_cnt.push_back(1); }
+    }
+  }
 
   // ---- pose graph of the reduced system: co-visibility (all pairs inside a track) + constraints
   std::vector<std::vector<int>> adj(P);
@@ -399,6 +427,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
 #define UP(field, vec) dev_upload(h, &d.field, vec)
     UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self);
     UP(e_pose, ie_pose); UP(e_obs, ie_obs); UP(e_w, ie_w);
+    UP(task_lm, task_lm); UP(task_cnt, task_cnt); UP(gen_lm, gen_lm);
     UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
     UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab); UP(urg_dst, sy.urg_dst);
     dev_upload(h, &d.c_i, c_i, (size_t)C); dev_upload(h, &d.c_j, c_j, (size_t)C);
@@ -431,6 +460,8 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   CK(cudaMemsetAsync(d.chi_c, 0, std::max(C, 1) * sizeof(double), h->stream));
   CK(cudaMemsetAsync(d.chi_c_new, 0, std::max(C, 1) * sizeof(double), h->stream));
   h->Kmax = Kmax;
+  h->Kmax_gen = Kmax_gen;
+  d.ntasks = (int)task_lm.size(); d.ngen = (int)gen_lm.size();
   h->C_edges = C;
   h->has_problem = true;
   return svs_ba_reset_state(h);
@@ -495,13 +526,13 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
   while (it < num_iters && ok) {
     // one Levenberg trial: build (at the accepted state, current lambda) -> solve -> update -> decide
     CKO(cudaEventRecord(h->ev[1], h->stream));
-    launch_build(d, 0, d.L, h->Kmax, robust, huber_delta, h->stream);
+    launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
     CKO(cudaEventRecord(h->ev[2], h->stream));
     launch_solve(d, h->max_col_blocks, h->stream);
     CKO(cudaEventRecord(h->ev[3], h->stream));
     launch_update(d, robust, huber_delta, h->stream);
     CKO(cudaEventRecord(h->ev[4], h->stream));
-    launches += 3;
+    launches += 2 + (d.ntasks > 0 ? 1 : 0) + ((d.ngen > 0 || d.C > 0) ? 1 : 0);
     CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
     CKO(cudaStreamSynchronize(h->stream));
     CKO(cudaGetLastError());
@@ -627,7 +658,7 @@ int svs_ba_reduced_system(svs_ba* h, int robust, double huber_delta, double lamb
   int rc;
   if ((rc = set_lambda(h, lambda))) return rc;
   if ((rc = clear_system(h))) return rc;
-  launch_build(d, 0, d.L, h->Kmax, robust, huber_delta, h->stream);
+  launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
   const int P = d.P, n = 6 * P;
   std::vector<double> S(36 * (size_t)d.nblk), bp(n), bc(n), chl(d.L), chc(d.C);
   std::vector<int> colp(P + 1), rowi(d.nblk), perm(P);
@@ -675,7 +706,7 @@ int svs_ba_solve_reduced(svs_ba* h, int robust, double huber_delta, double lambd
   int rc;
   if ((rc = set_lambda(h, lambda))) return rc;
   if ((rc = clear_system(h))) return rc;
-  launch_build(d, 0, d.L, h->Kmax, robust, huber_delta, h->stream);
+  launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
   launch_solve(d, h->max_col_blocks, h->stream);
   if (d.P) CK(cudaMemcpyAsync(x, d.x, 6 * (size_t)d.P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));

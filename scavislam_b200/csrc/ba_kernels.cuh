@@ -5,7 +5,7 @@
 namespace svs {
 size_t build_smem_bytes(int warps, int Kmax);
 void launch_prep(const BaDev& d, int buf, cudaStream_t st);
-void launch_build(const BaDev& d, int lm_begin, int lm_end, int Kmax, int robust, double delta, cudaStream_t st);
+void launch_build(const BaDev& d, int Kmax, int robust, double delta, cudaStream_t st);
 void launch_solve(const BaDev& d, int max_col_blocks, cudaStream_t st);
 void launch_solve_general(const BaDev& d, cudaStream_t st);
 int update_grid_blocks(int L, int C);

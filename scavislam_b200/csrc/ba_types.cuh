@@ -43,6 +43,11 @@ struct BaDev {
   const int* lm_sptr;            // [L+1]
   const int* lm_anchor;          // [L]
   const unsigned char* lm_self;  // [L] first edge is the observation in the anchor frame
+  // fused-kernel work lists: tasks = runs of landmarks with identical slot lists and <= 8 frames
+  const int* task_lm;   // [ntasks] first landmark
+  const int* task_cnt;  // [ntasks] landmarks in the task
+  const int* gen_lm;    // [ngen] landmarks handled one warp each (long tracks, no observations)
+  int ntasks, ngen;
   // edges (internal order)
   const int* e_pose;    // [E]
   const double* e_obs;  // [3][E]

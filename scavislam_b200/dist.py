@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing of the BA path (one process per GPU, torch.distributed).
+
+Two ways the path shards:
+  * replicas: every rank optimises an independent window (BASELINE config C4); no data-path
+    collective, only the timing reduction at the end -- `window_for_rank`, `reduce_job_totals`;
+  * one large window split by landmarks (config C5): `shard_landmarks` gives each rank the
+    landmarks l with l % world == rank (their edges follow), poses are replicated, and the reduced
+    camera system is summed across ranks once per Levenberg trial -- `global_pose_pairs` is the
+    block pattern every rank must agree on.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def window_for_rank(rank: int):
+    """Rank 0 measures the C2 window itself, the others independent windows of the same shape."""
+    from . import synth
+    if rank == 0:
+        return synth.make_config("C2")
+    return synth.make_window(200, 20000, 1234 + 100 + rank, name=f"C4[{rank}]")
+
+
+def reduce_job_totals(times_s, counts, dist=None, device="cpu"):
+    """Whole-job aggregation: max over ranks of every time, sum over ranks of every count."""
+    import torch
+    t = torch.tensor(list(times_s), dtype=torch.float64, device=device)
+    n = torch.tensor(list(counts), dtype=torch.float64, device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t], [float(x) for x in n]
+
+
+def shard_landmarks(pb, rank: int, world: int):
+    """Landmark partition of one window: rank r keeps landmarks l % world == r with all their
+    observation edges; poses are replicated; pose-pose constraints stay on rank 0."""
+    keep_l = (np.arange(pb.L) % world) == rank
+    new_index = np.cumsum(keep_l) - 1
+    keep_e = keep_l[pb.e_point]
+    sh = pb.copy()
+    sh.L = int(keep_l.sum())
+    sh.psi = np.ascontiguousarray(pb.psi[keep_l])
+    sh.E = int(keep_e.sum())
+    sh.e_point = np.ascontiguousarray(new_index[pb.e_point[keep_e]].astype(np.int32))
+    for k in ("e_pose", "e_anchor", "e_obs", "e_info"):
+        setattr(sh, k, np.ascontiguousarray(getattr(pb, k)[keep_e]))
+    if rank != 0:
+        sh.C = 0
+        sh.c_i, sh.c_j = pb.c_i[:0].copy(), pb.c_j[:0].copy()
+        sh.c_T, sh.c_Lambda = pb.c_T[:0].copy(), pb.c_Lambda[:0].copy()
+    if pb.truth_psi is not None:
+        sh.truth_psi = pb.truth_psi[keep_l]
+    sh.name = f"{pb.name}[{rank}/{world}]"
+    return sh, np.nonzero(keep_l)[0]
+
+
+def global_pose_pairs(pb):
+    """Unordered pose pairs coupled by a landmark track or a constraint: the block pattern of the
+    reduced camera system of the WHOLE window (every rank needs the same one)."""
+    order = np.argsort(pb.e_point, kind="stable")
+    ep, ef = pb.e_point[order], pb.e_pose[order]
+    anchors = pb.e_anchor[order]
+    pairs = set()
+    start = 0
+    bounds = np.flatnonzero(np.diff(ep)) + 1
+    for b in list(bounds) + [len(ep)]:
+        ps = set(ef[start:b].tolist())
+        if b > start:
+            ps.add(int(anchors[start]))
+        ps = sorted(ps)
+        for i in range(len(ps)):
+            for j in range(i + 1, len(ps)):
+                pairs.add((ps[i], ps[j]))
+        start = b
+    for i, j in zip(pb.c_i.tolist(), pb.c_j.tolist()):
+        pairs.add((min(i, j), max(i, j)))
+    if not pairs:
+        return np.zeros((0, 2), np.int32)
+    return np.array(sorted(pairs), np.int32)
