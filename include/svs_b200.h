@@ -129,6 +129,25 @@ int svs_optimiseInnerAndOuterWindow(svs_ba *h, int P, double *T_qt, const unsign
                                     int num_iters, int robust, double huber_delta,
                                     svs_ba_stats *stats);
 
+/* ---- one window split by landmarks across ranks: every rank holds all poses, its
+ * share of the landmarks and their edges; the reduced camera system is summed across ranks once per
+ * Levenberg trial by the caller (ncclAllReduce / torch.distributed on the device buffers below), the
+ * solve is replicated, back-substitution stays local.  Call order per trial:
+ *   svs_ba_trial_build -> all-reduce(S, bp, bc) -> svs_ba_trial_solve -> all-reduce(totals) -> svs_ba_trial_decide */
+/* Pose pairs that must be present in the block pattern of the reduced system although this rank
+ * may hold no landmark coupling them (the whole window's pattern); call before svs_ba_set_problem. */
+int svs_ba_set_structure(svs_ba *h, int npairs, const int *pose_i, const int *pose_j);
+/* lm->setUserLambdaInit(lambda); ni = 2 (slam_graph.cpp:338-342) */
+int svs_ba_lm_begin(svs_ba *h, double lambda_init, int max_trials);
+int svs_ba_trial_build(svs_ba *h, int robust, double huber_delta);
+/* Device pointers: S (nS doubles), bp and bc (nb doubles each), totals (3 doubles: chi2 at the
+ * accepted state, chi2 at the trial state, sum dpsi (lambda dpsi + b_l) of this rank's landmarks). */
+int svs_ba_system_buffers(svs_ba *h, double **S, long long *nS, double **bp, double **bc, long long *nb,
+                          double **totals);
+int svs_ba_trial_solve(svs_ba *h, int robust, double huber_delta);
+int svs_ba_trial_decide(svs_ba *h, int *again, int *stop, int *iterations_done);
+int svs_ba_lm_stats(svs_ba *h, svs_ba_stats *stats);
+
 /* Inspection hooks used by the parity tests (device results copied to host buffers). */
 /* g2o SparseOptimizer::activeRobustChi2 at the current state. */
 int svs_ba_chi2(svs_ba *h, int robust, double huber_delta, double *chi2);

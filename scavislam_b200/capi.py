@@ -97,6 +97,8 @@ EXPORTS = [
     "svs_ba_create", "svs_ba_destroy", "svs_last_error", "svs_ba_set_problem", "svs_ba_optimize",
     "svs_ba_get_poses", "svs_ba_get_points", "svs_ba_reset_state", "svs_optimiseInnerAndOuterWindow",
     "svs_ba_chi2", "svs_ba_reduced_system", "svs_ba_solve_reduced", "svs_device_info",
+    "svs_ba_set_structure", "svs_ba_lm_begin", "svs_ba_trial_build", "svs_ba_system_buffers", "svs_ba_trial_solve",
+    "svs_ba_trial_decide", "svs_ba_lm_stats",
     "svs_fast_create", "svs_fast_destroy", "svs_fast_last_error", "svs_fast_grid_init", "svs_fast_set_image",
     "svs_fast_set_image_device", "svs_fast_detect", "svs_fast_detect_adaptively",
     "svs_dt_create", "svs_dt_destroy", "svs_dt_last_error", "svs_dt_set_intrinsics", "svs_dt_set_images",
@@ -133,6 +135,15 @@ def lib():
     L.svs_ba_reduced_system.argtypes = [vp, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp]
     L.svs_ba_solve_reduced.argtypes = [vp, C.c_int, C.c_double, C.c_double, c_dp]
     L.svs_device_info.argtypes = [C.c_char_p, C.c_int]
+    L.svs_ba_set_structure.argtypes = [vp, C.c_int, c_ip, c_ip]
+    L.svs_ba_lm_begin.argtypes = [vp, C.c_double, C.c_int]
+    L.svs_ba_trial_build.argtypes = [vp, C.c_int, C.c_double]
+    pp = C.POINTER(C.c_void_p)
+    pl = C.POINTER(C.c_longlong)
+    L.svs_ba_system_buffers.argtypes = [vp, pp, pl, pp, pp, pl, pp]
+    L.svs_ba_trial_solve.argtypes = [vp, C.c_int, C.c_double]
+    L.svs_ba_trial_decide.argtypes = [vp, c_ip, c_ip, c_ip]
+    L.svs_ba_lm_stats.argtypes = [vp, C.POINTER(SvsBaStats)]
     L.svs_fast_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.svs_fast_destroy.argtypes = [vp]
     L.svs_fast_destroy.restype = None
@@ -287,6 +298,39 @@ class BundleAdjuster:
         if rc < 0:
             self._check(rc)
         return x, rc
+
+    # ---- stepwise trial API (window split by landmarks across ranks)
+    def set_structure(self, pairs):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        pi, pj = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+        self._check(lib().svs_ba_set_structure(self._h, len(pairs), _ip(pi), _ip(pj)))
+
+    def lm_begin(self, lambda_init=50.0, max_trials=5):
+        self._check(lib().svs_ba_lm_begin(self._h, float(lambda_init), int(max_trials)))
+
+    def trial_build(self, robust=True, huber_delta=1.0):
+        self._check(lib().svs_ba_trial_build(self._h, int(robust), float(huber_delta)))
+
+    def system_buffers(self):
+        """(ptr_S, nS, ptr_bp, ptr_bc, nb, ptr_totals): raw device pointers for the caller's collective."""
+        S, bp, bc, tot = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nS, nb = C.c_longlong(), C.c_longlong()
+        self._check(lib().svs_ba_system_buffers(self._h, C.byref(S), C.byref(nS), C.byref(bp), C.byref(bc), C.byref(nb),
+                                                C.byref(tot)))
+        return S.value, nS.value, bp.value, bc.value, nb.value, tot.value
+
+    def trial_solve(self, robust=True, huber_delta=1.0):
+        self._check(lib().svs_ba_trial_solve(self._h, int(robust), float(huber_delta)))
+
+    def trial_decide(self):
+        a, s, i = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().svs_ba_trial_decide(self._h, C.byref(a), C.byref(s), C.byref(i)))
+        return a.value, s.value, i.value
+
+    def lm_stats(self):
+        st = SvsBaStats()
+        self._check(lib().svs_ba_lm_stats(self._h, C.byref(st)))
+        return st.as_dict()
 
     def optimise_inner_and_outer_window(self, pb, num_iters, robust=True, huber_delta=1.0):
         """SlamGraph::optimize in one call from host buffers; returns (iters, poses, psi, stats)."""

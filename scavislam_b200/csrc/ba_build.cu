@@ -198,7 +198,7 @@ void launch_build(const BaDev& d, int Kmax, int robust, double delta, cudaStream
   constexpr int WARPS = 8;
   launch_build_wave(d, robust, delta, st);
   const int n_lm_blocks = (d.ngen + WARPS - 1) / WARPS;
-  const int n_c_blocks = (d.C + WARPS * 32 - 1) / (WARPS * 32);
+  const int n_c_blocks = 0;   // the pose-pose constraints ride on k_build_wave's launch
   const size_t smem = build_smem_bytes(WARPS, Kmax);
   static size_t configured = 0;
   if (smem > configured) {

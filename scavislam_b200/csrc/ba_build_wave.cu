@@ -30,13 +30,20 @@ constexpr int kWvInts = 8 + 40;   // slot poses, pair table (36) padded
 size_t build_wave_smem_bytes() { return (size_t)kWvWarps * (kWvDoubles * 8 + kWvInts * 4); }
 
 __global__ void __launch_bounds__(kWvWarps * 32)
-k_build_wave(BaDev d, int robust, double delta) {
+k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int task = (int)blockIdx.x * kWvWarps + warp;
-  if (task >= d.ntasks) return;
   const LmCtl* __restrict__ ctl = d.ctl;
   const int cur = ctl->cur;
+  if ((int)blockIdx.x >= n_task_blocks) {
+    // pose-pose constraints (G2oEdgeSE3), one thread each, riding on trailing CTAs of this launch so
+    // that their long serial 6x6 arithmetic overlaps the landmark work instead of following it
+    const int c = ((int)blockIdx.x - n_task_blocks) * (kWvWarps * 32) + (int)threadIdx.x;
+    if (c < d.C) constraint_build(d, d.pose[cur], c);
+    return;
+  }
+  const int task = (int)blockIdx.x * kWvWarps + warp;
+  if (task >= d.ntasks) return;
   const double lambda = ctl->lambda;
   double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kWvDoubles;
   double* sJp = sm;
@@ -288,14 +295,15 @@ k_build_wave(BaDev d, int robust, double delta) {
 }
 
 void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st) {
-  if (d.ntasks == 0) return;
+  if (d.ntasks == 0 && d.C == 0) return;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_build_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_wave_smem_bytes());
     configured = true;
   }
-  const int blocks = (d.ntasks + kWvWarps - 1) / kWvWarps;
-  k_build_wave<<<blocks, kWvWarps * 32, build_wave_smem_bytes(), st>>>(d, robust, delta);
+  const int task_blocks = (d.ntasks + kWvWarps - 1) / kWvWarps;
+  const int c_blocks = (d.C + kWvWarps * 32 - 1) / (kWvWarps * 32);
+  k_build_wave<<<task_blocks + c_blocks, kWvWarps * 32, build_wave_smem_bytes(), st>>>(d, robust, delta, task_blocks);
 }
 
 }  // namespace svs

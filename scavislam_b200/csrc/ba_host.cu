@@ -39,6 +39,7 @@ struct svs_ba {
   int nnzb_S = 0;
   int C_edges = 0;
   int max_col_blocks = 0;
+  std::vector<int> extra_pairs;   // svs_ba_set_structure: pose pairs added to the block pattern
   cudaEvent_t ev[8] = {};
   // last optimize() settings
 };
@@ -400,6 +401,11 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
         for (int y = x + 1; y < n; ++y) { A[(size_t)ps[x] * P + ps[y]] = 1; A[(size_t)ps[y] * P + ps[x]] = 1; }
     }
     for (int c = 0; c < C; ++c) { A[(size_t)c_i[c] * P + c_j[c]] = 1; A[(size_t)c_j[c] * P + c_i[c]] = 1; }
+    for (size_t q = 0; q + 1 < h->extra_pairs.size(); q += 2) {   // svs_ba_set_structure
+      const int a = h->extra_pairs[q], b = h->extra_pairs[q + 1];
+      if (a < 0 || b < 0 || a >= P || b >= P) return fail(h, SVS_ERR_INVALID, "structure pair out of range");
+      if (a != b) { A[(size_t)a * P + b] = 1; A[(size_t)b * P + a] = 1; }
+    }
     int nnz = 0;
     for (int i = 0; i < P; ++i) {
       const unsigned char* row = A.data() + (size_t)i * P;
@@ -442,7 +448,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     AL(S, 36 * (size_t)sy.nblk); AL(bp, 6 * (size_t)P); AL(bc, 6 * (size_t)P); AL(x, 6 * (size_t)P);
     AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
     AL(ctl, 1);
-    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 24);
+    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 24); AL(totals, 4);
 #undef AL
   };
   h->measuring = true;
@@ -530,9 +536,9 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     CKO(cudaEventRecord(h->ev[2], h->stream));
     launch_solve(d, h->max_col_blocks, h->stream);
     CKO(cudaEventRecord(h->ev[3], h->stream));
-    launch_update(d, robust, huber_delta, h->stream);
+    launch_update(d, robust, huber_delta, 0, h->stream);
     CKO(cudaEventRecord(h->ev[4], h->stream));
-    launches += 2 + (d.ntasks > 0 ? 1 : 0) + ((d.ngen > 0 || d.C > 0) ? 1 : 0);
+    launches += 2 + ((d.ntasks > 0 || d.C > 0) ? 1 : 0) + (d.ngen > 0 ? 1 : 0);
     CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
     CKO(cudaStreamSynchronize(h->stream));
     CKO(cudaGetLastError());
@@ -715,6 +721,87 @@ int svs_ba_solve_reduced(svs_ba* h, int robust, double huber_delta, double lambd
   const int failed = h->h_ctl->chol_fail;
   if ((rc = clear_system(h))) return rc;
   return failed ? 1 : 0;
+}
+
+// ---- stepwise Levenberg trial for a window whose landmarks are split across ranks
+// (SURVEY.md 8e): build -> [caller all-reduces S, bp, bc] -> solve -> [caller all-reduces totals] -> decide
+
+int svs_ba_set_structure(svs_ba* h, int npairs, const int* pose_i, const int* pose_j) {
+  if (!h || npairs < 0 || (npairs && (!pose_i || !pose_j))) return SVS_ERR_INVALID;
+  h->extra_pairs.clear();
+  for (int q = 0; q < npairs; ++q) { h->extra_pairs.push_back(pose_i[q]); h->extra_pairs.push_back(pose_j[q]); }
+  return SVS_OK;
+}
+
+int svs_ba_lm_begin(svs_ba* h, double lambda_init, int max_trials) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaMemcpyAsync(h->h_ctl, h->d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int cur = h->h_ctl->cur;
+  LmCtl z{};
+  z.cur = cur; z.lambda = lambda_init; z.ni = 2; z.max_trials = max_trials;
+  *h->h_ctl = z;
+  CK(cudaMemcpyAsync(h->d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
+  return clear_system(h);
+}
+
+int svs_ba_trial_build(svs_ba* h, int robust, double huber_delta) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  launch_build(h->d, h->Kmax_gen, robust, huber_delta, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));   // the caller's collective runs on its own stream
+  return SVS_OK;
+}
+
+int svs_ba_system_buffers(svs_ba* h, double** S, long long* nS, double** bp, double** bc, long long* nb,
+                          double** totals) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  if (S) *S = h->d.S;
+  if (nS) *nS = 36ll * h->d.nblk;
+  if (bp) *bp = h->d.bp;
+  if (bc) *bc = h->d.bc;
+  if (nb) *nb = 6ll * h->d.P;
+  if (totals) *totals = h->d.totals;
+  return SVS_OK;
+}
+
+int svs_ba_trial_solve(svs_ba* h, int robust, double huber_delta) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  launch_solve(h->d, h->max_col_blocks, h->stream);
+  launch_update(h->d, robust, huber_delta, 1, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return SVS_OK;
+}
+
+int svs_ba_trial_decide(svs_ba* h, int* again, int* stop, int* iter) {
+  if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  launch_decide_deferred(h->d, h->stream);
+  CK(cudaMemcpyAsync(h->h_ctl, h->d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (again) *again = h->h_ctl->again;
+  if (stop) *stop = h->h_ctl->stop;
+  if (iter) *iter = h->h_ctl->iter;
+  return SVS_OK;
+}
+
+int svs_ba_lm_stats(svs_ba* h, svs_ba_stats* st) {
+  if (!h || !h->has_problem || !st) return SVS_ERR_INVALID;
+  memset(st, 0, sizeof *st);
+  const LmCtl& c = *h->h_ctl;
+  st->iterations = c.iter; st->trials_total = c.trials_total; st->chi2_init = c.chi_init; st->chi2_final = c.chi_cur;
+  st->lambda_final = c.lambda;
+  for (int i = 0; i < c.iter && i < SVS_BA_MAX_ITERS; ++i) {
+    st->chi2_iter[i] = c.chi_iter[i]; st->lambda_iter[i] = c.lambda_iter[i]; st->trials_iter[i] = c.trials_iter[i];
+  }
+  st->num_frames = h->d.P; st->num_points = h->d.L; st->num_point_edges = h->d.E; st->num_frame_edges = h->d.C;
+  st->nnzb_S = h->nnzb_S; st->nnzb_L = h->d.nblk; st->max_track = h->Kmax;
+  return SVS_OK;
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@ void launch_build(const BaDev& d, int Kmax, int robust, double delta, cudaStream
 void launch_solve(const BaDev& d, int max_col_blocks, cudaStream_t st);
 void launch_solve_general(const BaDev& d, cudaStream_t st);
 int update_grid_blocks(int L, int C);
-void launch_update(const BaDev& d, int robust, double delta, cudaStream_t st);
+void launch_update(const BaDev& d, int robust, double delta, int defer_decision, cudaStream_t st);
+void launch_decide_deferred(const BaDev& d, cudaStream_t st);
 void launch_chi2(const BaDev& d, int robust, double delta, cudaStream_t st);
 }  // namespace svs

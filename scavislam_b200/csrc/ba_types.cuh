@@ -79,6 +79,7 @@ struct BaDev {
   double* ywork;       // [6P]
   double* part;        // [update grid][3] per-CTA partial sums (chi2 accepted, chi2 trial, scale)
   unsigned* ticket;    // last-CTA-done counter of k_update
+  double* totals;      // [3] chi2 accepted / chi2 trial / scale of this rank's landmarks (sharded window)
   long long* dbg;      // [24] per-phase cycle counters of k_solve (thread 0, thread 64)
   LmCtl* ctl;
 };

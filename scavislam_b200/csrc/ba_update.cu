@@ -51,7 +51,7 @@ __device__ void lm_decide(LmCtl* ctl, double chi_cur, double chi_new, double sca
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-k_update(BaDev d, int robust, double delta, int n_lm_blocks) {
+k_update(BaDev d, int robust, double delta, int n_lm_blocks, int defer_decision) {
   __shared__ double sPart[WARPS][3];
   __shared__ int sLast;
   LmCtl* ctl = d.ctl;
@@ -168,17 +168,26 @@ k_update(BaDev d, int robust, double delta, int n_lm_blocks) {
   }
   if (threadIdx.x == 0) {
     *d.ticket = 0;
-    lm_decide(ctl, sFin[0][0], sFin[0][1], sFin[0][2]);
+    if (defer_decision) {   // sharded window: the totals are summed over ranks before the decision
+      d.totals[0] = sFin[0][0]; d.totals[1] = sFin[0][1]; d.totals[2] = sFin[0][2];
+    } else {
+      lm_decide(ctl, sFin[0][0], sFin[0][1], sFin[0][2]);
+    }
   }
 }
 
-void launch_update(const BaDev& d, int robust, double delta, cudaStream_t st) {
+__global__ void k_decide_deferred(BaDev d) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) lm_decide(d.ctl, d.totals[0], d.totals[1], d.totals[2]);
+}
+void launch_decide_deferred(const BaDev& d, cudaStream_t st) { k_decide_deferred<<<1, 32, 0, st>>>(d); }
+
+void launch_update(const BaDev& d, int robust, double delta, int defer_decision, cudaStream_t st) {
   constexpr int WARPS = 8;
   const int n_lm_blocks = (d.L + WARPS - 1) / WARPS;
   const int n_c_blocks = (d.C + WARPS * 32 - 1) / (WARPS * 32);
   int nb = n_lm_blocks + n_c_blocks;
   if (nb == 0) nb = 1;   // still clears the reduced system and takes the LM decision
-  k_update<WARPS><<<nb, WARPS * 32, 0, st>>>(d, robust, delta, n_lm_blocks);
+  k_update<WARPS><<<nb, WARPS * 32, 0, st>>>(d, robust, delta, n_lm_blocks, defer_decision);
 }
 int update_grid_blocks(int L, int C) {
   constexpr int WARPS = 8;

@@ -78,3 +78,82 @@ def global_pose_pairs(pb):
     if not pairs:
         return np.zeros((0, 2), np.int32)
     return np.array(sorted(pairs), np.int32)
+
+
+class _DevArray:
+    """Raw device pointer -> object torch.as_tensor understands (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class ShardedWindow:
+    """One large window (BASELINE config C5) split by landmarks over `group` = a list of
+    BundleAdjuster handles.  With torch.distributed every rank passes ONE handle and the sums go
+    through dist.all_reduce (NCCL over NVLink); without it, several handles on one GPU are summed
+    in place (used to test the sharding arithmetic on a single device).
+
+    Per Levenberg trial: every shard builds its partial reduced camera system, the partial systems
+    (S, bp, bc) are summed, every shard solves the identical system and back-substitutes its own
+    landmarks, the three scalars of the gain ratio are summed, every shard takes the same decision."""
+
+    def __init__(self, adjusters, pb, rank=0, world=None, dist=None, device=None):
+        import torch
+        self.torch = torch
+        self.dist = dist
+        self.ba = list(adjusters)
+        world = world if world is not None else (dist.get_world_size() if dist is not None else len(self.ba))
+        pairs = global_pose_pairs(pb)
+        self.index = []
+        for k, b in enumerate(self.ba):
+            r = rank if dist is not None else k
+            sh, idx = shard_landmarks(pb, r, world)
+            b.set_structure(pairs)
+            b.set_problem(sh)
+            self.index.append(idx)
+        self.L = pb.L
+        self.views = []
+        for b in self.ba:
+            pS, nS, pbp, pbc, nb, ptot = b.system_buffers()
+            dev = device if device is not None else torch.cuda.current_device()
+            mk = lambda p, n: torch.as_tensor(_DevArray(p, n), device=f"cuda:{dev}")
+            self.views.append((mk(pS, nS), mk(pbp, nb), mk(pbc, nb), mk(ptot, 3)))
+
+    def _sum(self, which):
+        ts = [v[which] for v in self.views]
+        if self.dist is not None:
+            for t in ts:
+                self.dist.all_reduce(t)
+        elif len(ts) > 1:
+            total = ts[0].clone()
+            for t in ts[1:]:
+                total += t
+            for t in ts:
+                t.copy_(total)
+        self.torch.cuda.synchronize()
+
+    def optimize(self, num_iters, robust=True, huber_delta=1.0, lambda_init=50.0, max_trials=5):
+        for b in self.ba:
+            b.lm_begin(lambda_init, max_trials)
+        it, ok = 0, True
+        while it < num_iters and ok:
+            for b in self.ba:
+                b.trial_build(robust, huber_delta)
+            for w in (0, 1, 2):
+                self._sum(w)
+            for b in self.ba:
+                b.trial_solve(robust, huber_delta)
+            self._sum(3)
+            res = [b.trial_decide() for b in self.ba]
+            again, stop, it = res[0]
+            assert all(r == res[0] for r in res), "shards disagree on the Levenberg decision"
+            if not again and stop:
+                ok = False
+        return it, self.ba[0].lm_stats()
+
+    def poses(self):
+        return self.ba[0].poses()
+
+    def points_local(self):
+        """[(global landmark indices, psi)] for the shards this process holds."""
+        return [(idx, b.points()) for idx, b in zip(self.index, self.ba)]
