@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 k_build(BaDev d, const int* __restrict__ lm_list, int n_list, int Kmax, int robust, double delta, int n_lm_blocks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const LmCtl* __restrict__ ctl = d.ctl;
+  if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
   const int cur = ctl->cur;
   if ((int)blockIdx.x >= n_lm_blocks) {   // pose-pose constraints, one thread each
     const int c = ((int)blockIdx.x - n_lm_blocks) * (WARPS * 32) + (int)threadIdx.x;

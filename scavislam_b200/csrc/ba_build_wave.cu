@@ -34,6 +34,7 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LmCtl* __restrict__ ctl = d.ctl;
+  if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
   const int cur = ctl->cur;
   if ((int)blockIdx.x >= n_task_blocks) {
     // pose-pose constraints (G2oEdgeSE3), one thread each, riding on trailing CTAs of this launch so

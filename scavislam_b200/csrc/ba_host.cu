@@ -7,6 +7,7 @@
 // when the device path is unavailable.
 #include <algorithm>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -41,6 +42,7 @@ struct svs_ba {
   int max_col_blocks = 0;
   std::vector<int> extra_pairs;   // svs_ba_set_structure: pose pairs added to the block pattern
   cudaEvent_t ev[8] = {};
+  std::vector<cudaEvent_t> tev;   // per-trial timing events
   // last optimize() settings
 };
 
@@ -255,6 +257,7 @@ void svs_ba_destroy(svs_ba* h) {
   free_problem(h);
   free_arena(h);
   for (auto& e : h->ev) cudaEventDestroy(e);
+  for (auto& e : h->tev) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -280,6 +283,14 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   cudaSetDevice(h->device);
   CK(cudaStreamSynchronize(h->stream));   // the arena and the staging buffer are about to be reused
   free_problem(h);
+  const bool host_timing = getenv("SVS_HOST_TIMING") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!host_timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "set_problem %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tp0).count());
+    tp0 = now;
+  };
 
   // ---- group edges per landmark (counting sort), flat arrays only: this runs on the caller's
   //      thread inside the end-to-end time, like g2o's buildStructure does in the reference
@@ -333,6 +344,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     key[l] = ((unsigned long long)anchor << 44) | ((unsigned long long)(1 - nself) << 43) |
              ((unsigned long long)K << 40) | (first << 20) | last;
   }
+  lap("group");
   std::vector<int> order(L);
   std::iota(order.begin(), order.end(), 0);
   std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
@@ -359,6 +371,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     ns += l_K[l];
   }
   lm_eptr[L] = ne; lm_sptr[L] = ns;
+  lap("sort+regroup");
   // ---- work lists of the fused kernel: runs of landmarks with identical slot lists (<= 8 frames)
   std::vector<int> task_lm, task_cnt, gen_lm;
   int Kmax_gen = 1;
@@ -387,6 +400,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     }
   }
 
+  lap("tasks");
   // ---- pose graph of the reduced system: co-visibility (all pairs inside a track) + constraints
   std::vector<std::vector<int>> adj(P);
   {
@@ -415,10 +429,12 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     }
     h->nnzb_S = nnz / 2 + P;
   }
+  lap("adjacency");
   Symbolic sy;
   analyse(P, adj, (h->flags & SVS_BA_NATURAL_ORDER) != 0, sy);
   if (sy.nblk >= (1 << 20)) return fail(h, SVS_ERR_UNSUPPORTED, "reduced system factor has more than 2^20 blocks");
 
+  lap("analyse");
   // ---- device image: constant arrays (uploaded in one copy) followed by work buffers
   BaDev& d = h->d;
   d.P = P; d.L = L; d.E = E; d.C = C; d.nslots = ns; d.nblk = sy.nblk; d.flags = h->flags;
@@ -457,6 +473,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   int rc;
   if ((rc = arena_reserve(h, h->arena_off, upload_bytes))) return rc;
   lay();
+  lap("stage");
   h->d_pose0 = const_cast<double*>(d_pose0c);
   h->d_psi0 = const_cast<double*>(d_psi0c);
   CK(cudaMemcpyAsync(h->arena, h->stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -504,6 +521,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
   if (d.P == 0) return -1;   // g2o: "0 vertices to optimize"
   cudaSetDevice(h->device);
   int rc;
+  int trials_seen = 0;
 #define CKO(call)                                                       \
   do {                                                                  \
     cudaError_t e_ = (call);                                            \
@@ -519,7 +537,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
   {
     const int cur = h->h_ctl->cur;
     LmCtl z{};
-    z.cur = cur; z.lambda = lambda_init; z.ni = 2; z.max_trials = max_trials;
+    z.cur = cur; z.lambda = lambda_init; z.ni = 2; z.max_trials = max_trials; z.max_iters = num_iters;
     *h->h_ctl = z;
     CKO(cudaMemcpyAsync(d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
   }
@@ -528,27 +546,37 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
   int launches = 0;
   CKO(cudaEventRecord(h->ev[0], h->stream));
   int it = 0;
-  bool ok = true;
-  while (it < num_iters && ok) {
-    // one Levenberg trial: build (at the accepted state, current lambda) -> solve -> update -> decide
-    CKO(cudaEventRecord(h->ev[1], h->stream));
-    launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
-    CKO(cudaEventRecord(h->ev[2], h->stream));
-    launch_solve(d, h->max_col_blocks, h->stream);
-    CKO(cudaEventRecord(h->ev[3], h->stream));
-    launch_update(d, robust, huber_delta, 0, h->stream);
-    CKO(cudaEventRecord(h->ev[4], h->stream));
-    launches += 2 + ((d.ntasks > 0 || d.C > 0) ? 1 : 0) + (d.ngen > 0 ? 1 : 0);
+  const int per_trial = 2 + ((d.ntasks > 0 || d.C > 0) ? 1 : 0) + (d.ngen > 0 ? 1 : 0);
+  for (;;) {
+    // Enqueue one Levenberg trial per remaining iteration without waiting for the device: every
+    // trial is the same launch sequence, and the device-side control block decides whether a trial
+    // is the next iteration or the retry of a rejected step.  Trials enqueued past the end (or after
+    // Terminate) return at once (LmCtl::max_iters).  Only rejected steps cost another round trip.
+    const int ntr = num_iters - it;
+    while ((int)h->tev.size() < 4 * ntr) { cudaEvent_t e; cudaEventCreate(&e); h->tev.push_back(e); }
+    for (int k = 0; k < ntr; ++k) {
+      CKO(cudaEventRecord(h->tev[4 * k + 0], h->stream));
+      launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
+      CKO(cudaEventRecord(h->tev[4 * k + 1], h->stream));
+      launch_solve(d, h->max_col_blocks, h->stream);
+      CKO(cudaEventRecord(h->tev[4 * k + 2], h->stream));
+      launch_update(d, robust, huber_delta, 0, h->stream);
+      CKO(cudaEventRecord(h->tev[4 * k + 3], h->stream));
+    }
     CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
     CKO(cudaStreamSynchronize(h->stream));
     CKO(cudaGetLastError());
-    for (int k = 0; k < 3; ++k) {
-      float t = 0;
-      cudaEventElapsedTime(&t, h->ev[1 + k], h->ev[2 + k]);
-      ms[k] += t;
-    }
+    const int done_trials = h->h_ctl->trials_total - trials_seen;
+    trials_seen = h->h_ctl->trials_total;
+    launches += per_trial * done_trials;
+    for (int k = 0; k < done_trials && k < ntr; ++k)
+      for (int q = 0; q < 3; ++q) {
+        float t = 0;
+        cudaEventElapsedTime(&t, h->tev[4 * k + q], h->tev[4 * k + q + 1]);
+        ms[q] += t;
+      }
     it = h->h_ctl->iter;
-    if (!h->h_ctl->again && h->h_ctl->stop) ok = false;
+    if (it >= num_iters || (h->h_ctl->stop && !h->h_ctl->again)) break;
   }
   CKO(cudaEventRecord(h->ev[6], h->stream));
   CKO(cudaStreamSynchronize(h->stream));
@@ -652,6 +680,7 @@ static int set_lambda(svs_ba* h, double lambda) {
   CK(cudaMemcpyAsync(h->h_ctl, h->d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->h_ctl->lambda = lambda;
+  h->h_ctl->max_iters = 0;   // inspection hooks run the kernels unconditionally
   CK(cudaMemcpyAsync(h->d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
   return SVS_OK;
 }

@@ -69,7 +69,7 @@ __device__ __forceinline__ bool chol6_regs(const double* __restrict__ A, double 
   return ok;
 }
 
-constexpr int kUpdPf = 4;        // update-list entries per update thread prefetched one column ahead
+constexpr int kUpdPf = 2;        // update-list entries per update thread prefetched one column ahead
 constexpr int kPanelThreads = 128;  // warps 0-3: factor the next column (look-ahead); warp 0 owns the pivot chain
 constexpr int kUpdThreads = kSolveThreads - kPanelThreads;
 
@@ -126,6 +126,7 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
   double* ysm = sm_solve + (size_t)cap * 36;
   double* yv = y_in_smem ? ysm : d.ywork;
   LmCtl* ctl = d.ctl;
+  if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
   const int t = threadIdx.x, nt = kSolveThreads, lane = t & 31, warp = t >> 5;
   const int P = d.P, nblk = d.nblk;
   const double lambda = ctl->lambda;
@@ -200,6 +201,7 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
     }
   };
 
+  // one element of a pair update (used on the pivot chain, where width beats register tiling)
   auto update_item = [&](int base, int w, int ab, int dst, int hi_res) {
     const int pidx = w / 36, el = w - pidx * 36, r = el / 6, c = el - r * 6;
     (void)pidx;
@@ -209,6 +211,29 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
     const double s = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y);
     if (dst < hi_res) ring[(size_t)(dst & mask) * 36 + el] -= s;
     else d.S[(size_t)dst * 36 + el] -= s;
+  };
+  // half of a pair update, register tiled: rows 3h..3h+2 of S_ab -= L_a L_b^T.  18 + 36 doubles loaded
+  // for 108 FMAs -- off the pivot chain, what matters is not to flood the shared-memory pipe the
+  // chain also lives on (the element-wise form loads 12 doubles per 6 FMAs).
+  auto update_half = [&](int base, int u, int ab, int dst, int hi_res) {
+    const int h = u & 1;
+    const double2* La = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab >> 16)) & mask) * 36 + h * 18);
+    const double2* Lb = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab & 0xffff)) & mask) * 36);
+    double a[18];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { const double2 v = La[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
+    double o[18];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double2 b0 = Lb[3 * c], b1 = Lb[3 * c + 1], b2 = Lb[3 * c + 2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        o[r * 6 + c] = (a[r * 6] * b0.x + a[r * 6 + 1] * b0.y) + (a[r * 6 + 2] * b1.x + a[r * 6 + 3] * b1.y) +
+                       (a[r * 6 + 4] * b2.x + a[r * 6 + 5] * b2.y);
+    }
+    double2* D = reinterpret_cast<double2*>((dst < hi_res ? ring + (size_t)(dst & mask) * 36 : d.S + (size_t)dst * 36) + h * 18);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { double2 v = D[q]; v.x -= o[2 * q]; v.y -= o[2 * q + 1]; D[q] = v; }
   };
 
   // number of "urgent" pairs of column j: those that land in column j+1 (pairs (a, 0) when the
@@ -227,16 +252,17 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
   const int ut = t - kPanelThreads;   // index among the update threads
   int pf_ab[kUpdPf], pf_dst[kUpdPf];
   auto prefetch_upd = [&](int j) {
-    const int u0 = upd_ptr[j] + urgent_of(j), nitems = (upd_ptr[j + 1] - u0) * 36;
+    const int u0 = upd_ptr[j] + urgent_of(j), nunits = (upd_ptr[j + 1] - u0) * 2;
 #pragma unroll
     for (int i = 0; i < kUpdPf; ++i) {
-      const int w = ut + i * kUpdThreads;
-      if (w < nitems) { pf_ab[i] = d.upd_ab[u0 + w / 36]; pf_dst[i] = d.upd_dst[u0 + w / 36]; }
+      const int u = ut + i * kUpdThreads;
+      if (u < nunits) { pf_ab[i] = d.upd_ab[u0 + (u >> 1)]; pf_dst[i] = d.upd_dst[u0 + (u >> 1)]; }
     }
   };
   if (P > 0 && t >= kPanelThreads) prefetch_upd(0);
   __syncthreads();
   int failed = P > 0 ? sFailBuf[0] : 0;
+  int until_refill = refill_period;
 
   TICK(0);
   for (int j = 0; j < P && !failed; ++j) {
@@ -248,20 +274,34 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
       // ---- panel warps: the part of column j's update that lands in column j+1, then factor it
       if (urgent) {
         if (warp == 0) {
-          for (int w = lane; w < 36; w += 32) update_item(base, w, 0, urg_dst[base + 1], 0x7fffffff);
-          if (lane < 6) {   // b_{j+1} -= L_{j+1,j} y_j
-            const double* La = ring + (size_t)((base + 1) & mask) * 36 + lane * 6;
-            const double* yj = yv + 6 * j;
-            double s = 0.;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) s += La[q] * yj[q];
-            yv[6 * (j + 1) + lane] -= s;
+          // S_{j+1,j+1} -= L L^T with L = L_{j+1,j}: symmetric, 21 lanes, one round; this is the only
+          // part of column j's update the next pivot chain waits for
+          if (lane < 21) {
+            int r = 0, u = lane;
+            while (u > r) { u -= r + 1; ++r; }
+            const int c = u;
+            const double2* La = reinterpret_cast<const double2*>(ring + (size_t)((base + 1) & mask) * 36 + r * 6);
+            const double2* Lb = reinterpret_cast<const double2*>(ring + (size_t)((base + 1) & mask) * 36 + c * 6);
+            const double2 a0 = La[0], a1 = La[1], a2 = La[2], b0 = Lb[0], b1 = Lb[1], b2 = Lb[2];
+            const double sv = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y);
+            double* D = ring + (size_t)(col_ptr[j + 1] & mask) * 36;
+            const double nv = D[r * 6 + c] - sv;
+            D[r * 6 + c] = nv;
+            D[c * 6 + r] = nv;
           }
           __syncwarp();
         } else {
-          for (int w = 36 + (t - 32); w < urgent * 36; w += kPanelThreads - 32) {
-            const int a = w / 36;
-            update_item(base, w, a << 16, urg_dst[base + 1 + a], 0x7fffffff);
+          if (warp == 1 && lane < 6) {   // b_{j+1} -= L_{j+1,j} y_j
+            const double* La = ring + (size_t)((base + 1) & mask) * 36 + lane * 6;
+            const double* yj = yv + 6 * j;
+            double sv = 0.;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) sv += La[q] * yj[q];
+            yv[6 * (j + 1) + lane] -= sv;
+          }
+          for (int u = 2 + (t - 32); u < urgent * 2; u += kPanelThreads - 32) {
+            const int a = u >> 1;
+            update_half(base, u, a << 16, urg_dst[base + 1 + a], 0x7fffffff);
           }
         }
       }
@@ -274,14 +314,14 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
 #pragma unroll
       for (int i = 0; i < kUpdPf; ++i) { cu_ab[i] = pf_ab[i]; cu_dst[i] = pf_dst[i]; }
       if (j + 1 < P) prefetch_upd(j + 1);
-      const int uu = u0 + urgent, nitems = (upd_ptr[j + 1] - uu) * 36;
+      const int uu = u0 + urgent, nunits = (upd_ptr[j + 1] - uu) * 2;
 #pragma unroll
       for (int i = 0; i < kUpdPf; ++i) {
-        const int w = ut + i * kUpdThreads;
-        if (w < nitems) update_item(base, w, cu_ab[i], cu_dst[i], hi);
+        const int u = ut + i * kUpdThreads;
+        if (u < nunits) update_half(base, u, cu_ab[i], cu_dst[i], hi);
       }
-      for (int w = ut + kUpdPf * kUpdThreads; w < nitems; w += kUpdThreads)
-        update_item(base, w, d.upd_ab[uu + w / 36], d.upd_dst[uu + w / 36], hi);
+      for (int u = ut + kUpdPf * kUpdThreads; u < nunits; u += kUpdThreads)
+        update_half(base, u, d.upd_ab[uu + (u >> 1)], d.upd_dst[uu + (u >> 1)], hi);
       // b_a -= L_aj y_j for the rows the panel warps did not take
       for (int w = ut + (urgent ? 6 : 0); w < nb * 6; w += kUpdThreads) {
         const int a = w / 6, r = w - a * 6;
@@ -314,7 +354,8 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
     failed = sFailBuf[(j + 1) & 1];
     // ---- every refill_period columns: reload the ring slots the finished columns freed.  Copies are
     //      never in flight while updates run, so a destination is either resident (< hi) or in HBM.
-    if ((j + 1) % refill_period == 0 && hi < nblk) {
+    if (--until_refill == 0) until_refill = refill_period;
+    if (until_refill == refill_period && hi < nblk) {
       const int hi_new = min(nblk, col_ptr[j + 1] + cap);
       for (int c = t; c < (hi_new - hi) * 18; c += nt) {
         const int id = hi + c / 18, w = c % 18;
@@ -336,69 +377,70 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
     for (int i = t; i < 6 * P; i += nt) d.x[i] = 0;
     return;
   }
-  // --- backward solve L^T x = y by warp 0; lanes (g, r): g = lane / 6 walks the column's blocks
-  //     g, g+5, ...; the next column's blocks are prefetched while this one is reduced.
-  if (warp == 0) {
-    const int r = lane % 6, g = lane / 6;
-    double pf[2][6];   // up to two prefetched blocks per lane group (column r of L_aj)
-    int prow[2];
-    double linv_c[6];  // column r of Linv_j (entries q >= r)
-    auto prefetch = [&](int j) {
-      const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int a = g + 5 * u;
-        prow[u] = -1;
-        if (lane < 30 && a < nb) {
-          const double* La = d.S + 36 * (size_t)(base + 1 + a);
-          prow[u] = row_idx[base + 1 + a];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) pf[u][q] = La[q * 6 + r];
-        }
-      }
-      if (lane < 6) {
-#pragma unroll
-        for (int q = 0; q < 6; ++q) linv_c[q] = d.Linv[36 * (size_t)j + q * 6 + lane];
-      }
+  // --- backward solve L^T x = y.  The ring is free now: the factor is streamed back through it in
+  //     chunks of columns (L blocks + the inverse diagonal factors), double buffered; warp 0 walks
+  //     the dependency chain out of shared memory while the other warps fetch the next chunk.
+  {
+    const int half = cap / 2;
+    double* bufs[2] = {ring, ring + (size_t)half * 36};
+    auto chunk_lo = [&](int jhi) {   // largest [jlo, jhi) whose blocks + diagonal inverses fit one half
+      int jlo = jhi;
+      while (jlo > 0 && (col_ptr[jhi] - col_ptr[jlo - 1]) + (jhi - (jlo - 1)) <= half) --jlo;
+      return jlo;
     };
-    if (P > 0) prefetch(P - 1);
-    for (int j = P - 1; j >= 0; --j) {
-      const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-      double acc = 0.;
+    auto load_chunk = [&](double* buf, int jlo, int jhi, int tid, int nth) {
+      const int nb16 = (col_ptr[jhi] - col_ptr[jlo]) * 18;
+      const double* src = d.S + (size_t)col_ptr[jlo] * 36;
+      for (int c = tid; c < nb16; c += nth) cp_async16(buf + 2 * (size_t)c, src + 2 * (size_t)c);
+      double* lbuf = buf + (size_t)(col_ptr[jhi] - col_ptr[jlo]) * 36;
+      const double* lsrc = d.Linv + (size_t)jlo * 36;
+      for (int c = tid; c < (jhi - jlo) * 18; c += nth) cp_async16(lbuf + 2 * (size_t)c, lsrc + 2 * (size_t)c);
+      cp_async_commit();
+    };
+    int jhi = P, which = 0;
+    int jlo = chunk_lo(jhi);
+    if (P > 0) load_chunk(bufs[0], jlo, jhi, t, nt);
+    cp_async_wait_all();
+    __syncthreads();
+    while (jhi > 0) {
+      const int njhi = jlo, njlo = njhi > 0 ? chunk_lo(njhi) : 0;
+      if (njhi > 0 && warp > 0) load_chunk(bufs[which ^ 1], njlo, njhi, t - 32, nt - 32);
+      if (warp == 0) {
+        const double* buf = bufs[which];
+        const double* lbuf = buf + (size_t)(col_ptr[jhi] - col_ptr[jlo]) * 36;
+        const int r = lane % 6, g = lane / 6;   // 5 lane groups walk a column's blocks; lanes 30,31 idle
+        for (int j = jhi - 1; j >= jlo; --j) {
+          const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
+          double acc = 0.;
+          if (lane < 30)
+            for (int a = g; a < nb; a += 5) {
+              const double* La = buf + (size_t)(base + 1 + a - col_ptr[jlo]) * 36;
+              const double* xa = yv + 6 * row_idx[base + 1 + a];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (prow[u] >= 0) {
-          const double* xa = yv + 6 * prow[u];
+              for (int q = 0; q < 6; ++q) acc += La[q * 6 + r] * xa[q];
+            }
+          double tot = acc;
+          tot += __shfl_down_sync(0xffffffffu, acc, 6);
+          const double a12 = __shfl_down_sync(0xffffffffu, acc, 12);
+          const double a18 = __shfl_down_sync(0xffffffffu, acc, 18);
+          const double a24 = __shfl_down_sync(0xffffffffu, acc, 24);
+          tot += a12 + a18 + a24;
+          double v = 0.;
+          if (lane < 6) v = yv[6 * j + lane] - tot;
+          const double* Li = lbuf + (size_t)(j - jlo) * 36;
+          double xr = 0.;   // x_r = sum_{q >= r} Linv[q][r] v_q
 #pragma unroll
-          for (int q = 0; q < 6; ++q) acc += pf[u][q] * xa[q];
+          for (int q = 0; q < 6; ++q) {
+            const double vq = __shfl_sync(0xffffffffu, v, q);
+            if (lane < 6 && q >= lane) xr += Li[q * 6 + lane] * vq;
+          }
+          if (lane < 6) yv[6 * j + lane] = xr;
+          __syncwarp();
         }
-      if (lane < 30)
-        for (int a = g + 10; a < nb; a += 5) {   // wide columns: the rest straight from L2
-          const double* La = d.S + 36 * (size_t)(base + 1 + a);
-          const double* xa = yv + 6 * row_idx[base + 1 + a];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) acc += La[q * 6 + r] * xa[q];
-        }
-      double lc[6];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) lc[q] = linv_c[q];
-      if (j > 0) prefetch(j - 1);
-      double tot = acc;
-      tot += __shfl_down_sync(0xffffffffu, acc, 6);
-      const double a12 = __shfl_down_sync(0xffffffffu, acc, 12);
-      const double a18 = __shfl_down_sync(0xffffffffu, acc, 18);
-      const double a24 = __shfl_down_sync(0xffffffffu, acc, 24);
-      tot += a12 + a18 + a24;
-      double v = 0.;
-      if (lane < 6) v = yv[6 * j + lane] - tot;
-      double xr = 0.;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const double vq = __shfl_sync(0xffffffffu, v, q);
-        if (q >= lane) xr += lc[q] * vq;
       }
-      if (lane < 6) yv[6 * j + lane] = xr;
-      __syncwarp();
+      cp_async_wait_all();
+      __syncthreads();
+      jhi = njhi; jlo = njlo; which ^= 1;
     }
   }
   __syncthreads();

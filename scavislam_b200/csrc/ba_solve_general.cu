@@ -48,6 +48,7 @@ k_solve_general(BaDev d) {
   __shared__ double sRed[kSolveThreads / 32];
   __shared__ int sFail;
   LmCtl* ctl = d.ctl;
+  if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
   const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, warp = t >> 5;
   const int P = d.P;
   const double lambda = ctl->lambda;

@@ -23,6 +23,7 @@ struct LmCtl {
   int chol_fail;   // reduced system not positive definite in this trial
   int trials_total;
   int max_trials;
+  int max_iters;   // > 0: kernels of trials enqueued past the end (or after Terminate) return at once
   double chi_init;
   double chi_iter[kMaxIters];
   double lambda_iter[kMaxIters];

@@ -55,6 +55,7 @@ k_update(BaDev d, int robust, double delta, int n_lm_blocks, int defer_decision)
   __shared__ double sPart[WARPS][3];
   __shared__ int sLast;
   LmCtl* ctl = d.ctl;
+  if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
   const int cur = ctl->cur, trial = 1 - cur;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every CTA helps clearing the reduced system for the next build
