@@ -39,7 +39,7 @@ struct svs_ba {
   int Kmax_gen = 1;
   int nnzb_S = 0;
   int C_edges = 0;
-  int max_col_blocks = 0;
+  int max_col_blocks = 0, max_col_branch = 0, nbranch = 1;
   std::vector<int> extra_pairs;   // svs_ba_set_structure: pose pairs added to the block pattern
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> tev;   // per-trial timing events
@@ -121,11 +121,14 @@ void free_arena(svs_ba* h) {
 // the pose graph, the role AMD plays inside LinearSolverCSparse), block fill, and the update
 // lists of the right-looking block Cholesky.
 struct Symbolic {
-  std::vector<int> perm, pos, col_ptr, row_idx, upd_ptr, upd_dst, upd_ab, urg_dst, tbl;
+  std::vector<int> perm, pos, col_ptr, row_idx, upd_ptr, upd_dst, upd_ab, urg_dst, tbl, branch_ptr;
+  int max_col_branch = 0, max_col_sep = 0;
   int nblk = 0;
 };
 
-void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, Symbolic& sy) {
+// `order`: empty = greedy minimum degree (or the caller's order when `natural`), else the elimination
+// order to use (nested dissection, see choose_branches).
+void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, const std::vector<int>& order, Symbolic& sy) {
   // elimination graph as a byte matrix: P is a window of poses (hundreds to a few thousand)
   std::vector<unsigned char> G((size_t)P * P, 0);
   std::vector<int> deg(P, 0);
@@ -139,7 +142,9 @@ void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, S
   std::vector<int> nb;
   for (int step = 0; step < P; ++step) {
     int v = step;
-    if (!natural) {   // greedy minimum degree, ties to the lowest index
+    if (!order.empty()) {
+      v = order[step];
+    } else if (!natural) {   // greedy minimum degree, ties to the lowest index
       int best = 1 << 30;
       for (int i = 0; i < P; ++i)
         if (!done[i] && deg[i] < best) { best = deg[i]; v = i; }
@@ -204,6 +209,33 @@ void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, S
     const int base = sy.col_ptr[j] + 1, nb = sy.col_ptr[j + 1] - base;
     for (int a = 0; a < nb; ++a) sy.urg_dst[base + a] = sy.upd_dst[sy.upd_ptr[j] + a];
   }
+}
+
+// Two-ended elimination for window-shaped pose graphs ("burn at both ends"): keyframes are
+// temporal, so in the caller's order the co-visibility graph is banded (bandwidth w).  Team 0
+// eliminates poses 0, 1, 2, ... and team 1 eliminates P-1, P-2, ... concurrently; they meet at a
+// separator of w poses in the middle that is factored last.  Neither chain starts next to a
+// separator, so no separator rows are dragged through the columns: the factor has the fill of the
+// plain band, and the pivot chain is P/2 + w columns instead of P.  (A k-way dissection with k > 2
+// was measured: interior parts drag their first separator through every column, the wider columns
+// saturate the shared-memory pipe of the one SM that runs the factorisation, and nothing is gained.)
+// Returns the number of branches (1 when the graph is not banded enough).
+int choose_branches(int P, const std::vector<std::vector<int>>& adj, std::vector<int>& order,
+                    std::vector<int>& branch_ptr) {
+  int w = 0;
+  for (int i = 0; i < P; ++i)
+    for (int j : adj[i]) w = std::max(w, std::abs(i - j));
+  order.clear();
+  branch_ptr.clear();
+  if (w == 0 || (P - w) / 2 < 3 * w) return 1;
+  const int left = (P - w) / 2;             // poses [0, left) | separator [left, left + w) | [left + w, P)
+  branch_ptr.push_back(0);
+  for (int i = 0; i < left; ++i) order.push_back(i);
+  branch_ptr.push_back((int)order.size());
+  for (int i = P - 1; i >= left + w; --i) order.push_back(i);
+  branch_ptr.push_back((int)order.size());
+  for (int i = left; i < left + w; ++i) order.push_back(i);
+  return 2;
 }
 
 int fail(svs_ba* h, int code, const std::string& msg) {
@@ -431,7 +463,31 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   }
   lap("adjacency");
   Symbolic sy;
-  analyse(P, adj, (h->flags & SVS_BA_NATURAL_ORDER) != 0, sy);
+  {
+    // two concurrent branches when the window is banded and each team's share of k_solve's
+    // shared-memory ring holds its widest columns, else a single chain (minimum degree order)
+    const bool natural = (h->flags & SVS_BA_NATURAL_ORDER) != 0;
+    int G = (natural || getenv("SVS_SOLVE_CHAIN")) ? 1 : 2;
+    for (;;) {
+      std::vector<int> order, bptr;
+      G = G > 1 ? choose_branches(P, adj, order, bptr) : 1;
+      analyse(P, adj, natural, order, sy);
+      if (G == 1) { sy.branch_ptr = {0, P}; }
+      else sy.branch_ptr = bptr;
+      const int sep0 = sy.branch_ptr[G];
+      sy.max_col_branch = sy.max_col_sep = 0;
+      for (int j = 0; j < P; ++j) {
+        const int nb = sy.col_ptr[j + 1] - sy.col_ptr[j] - 1;
+        if (G > 1 && j < sep0) sy.max_col_branch = std::max(sy.max_col_branch, nb);
+        else sy.max_col_sep = std::max(sy.max_col_sep, nb);
+      }
+      if (G == 1) break;
+      const int cap = solve_ring_capacity(P, sy.nblk);
+      if (cap / G >= 4 * (sy.max_col_branch + 1) && cap >= 4 * (sy.max_col_sep + 1)) break;
+      G /= 2;
+    }
+    h->nbranch = (int)sy.branch_ptr.size() - 1;
+  }
   if (sy.nblk >= (1 << 20)) return fail(h, SVS_ERR_UNSUPPORTED, "reduced system factor has more than 2^20 blocks");
 
   lap("analyse");
@@ -452,6 +508,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     UP(task_lm, task_lm); UP(task_cnt, task_cnt); UP(gen_lm, gen_lm);
     UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
     UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab); UP(urg_dst, sy.urg_dst);
+    UP(branch_ptr, sy.branch_ptr);
     dev_upload(h, &d.c_i, c_i, (size_t)C); dev_upload(h, &d.c_j, c_j, (size_t)C);
     dev_upload(h, &d.c_T, c_T, 7 * (size_t)C); dev_upload(h, &d.c_Lam, c_Lambda, 36 * (size_t)C);
     dev_upload(h, &d_pose0c, T_qt, 7 * (size_t)P);
@@ -478,8 +535,8 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   h->d_psi0 = const_cast<double*>(d_psi0c);
   CK(cudaMemcpyAsync(h->arena, h->stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
-  h->max_col_blocks = 0;
-  for (int j = 0; j < P; ++j) h->max_col_blocks = std::max(h->max_col_blocks, sy.col_ptr[j + 1] - sy.col_ptr[j] - 1);
+  h->max_col_blocks = sy.max_col_sep; h->max_col_branch = sy.max_col_branch;
+  d.nbranch = h->nbranch;
   CK(cudaMemsetAsync(d.chi_c, 0, std::max(C, 1) * sizeof(double), h->stream));
   CK(cudaMemsetAsync(d.chi_c_new, 0, std::max(C, 1) * sizeof(double), h->stream));
   h->Kmax = Kmax;
@@ -558,7 +615,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
       CKO(cudaEventRecord(h->tev[4 * k + 0], h->stream));
       launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
       CKO(cudaEventRecord(h->tev[4 * k + 1], h->stream));
-      launch_solve(d, h->max_col_blocks, h->stream);
+      launch_solve(d, h->max_col_branch, h->max_col_blocks, h->stream);
       CKO(cudaEventRecord(h->tev[4 * k + 2], h->stream));
       launch_update(d, robust, huber_delta, 0, h->stream);
       CKO(cudaEventRecord(h->tev[4 * k + 3], h->stream));
@@ -601,11 +658,12 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
   if (getenv("SVS_SOLVE_TIMING")) {
     long long dbg[24];
     cudaMemcpy(dbg, d.dbg, sizeof dbg, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "k_solve cycles  panel:");
-    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", dbg[i]);
-    fprintf(stderr, "\n                update:");
-    for (int i = 0; i < 8; ++i) fprintf(stderr, " %lld", dbg[12 + i]);
-    fprintf(stderr, "\n  slots: 0 prologue, 1 loop head, 2 urgent updates, 3 panel column, 4 updates, 5 column barrier, 6 refill, 7 backward\n");
+    fprintf(stderr, "k_solve cycles since setup (branches done, +barrier, separators done, back seps, back branches, end):\n");
+    for (int g = 0; g < 4; ++g) {
+      fprintf(stderr, "  team %d:", g);
+      for (int i = 0; i < 6; ++i) fprintf(stderr, " %lld", dbg[g * 6 + i]);
+      fprintf(stderr, "\n");
+    }
   }
   return h->h_ctl->iter;
 #undef CKO
@@ -742,7 +800,7 @@ int svs_ba_solve_reduced(svs_ba* h, int robust, double huber_delta, double lambd
   if ((rc = set_lambda(h, lambda))) return rc;
   if ((rc = clear_system(h))) return rc;
   launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
-  launch_solve(d, h->max_col_blocks, h->stream);
+  launch_solve(d, h->max_col_branch, h->max_col_blocks, h->stream);
   if (d.P) CK(cudaMemcpyAsync(x, d.x, 6 * (size_t)d.P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -799,7 +857,7 @@ int svs_ba_system_buffers(svs_ba* h, double** S, long long* nS, double** bp, dou
 int svs_ba_trial_solve(svs_ba* h, int robust, double huber_delta) {
   if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
   cudaSetDevice(h->device);
-  launch_solve(h->d, h->max_col_blocks, h->stream);
+  launch_solve(h->d, h->max_col_branch, h->max_col_blocks, h->stream);
   launch_update(h->d, robust, huber_delta, 1, h->stream);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));

@@ -6,7 +6,8 @@ namespace svs {
 size_t build_smem_bytes(int warps, int Kmax);
 void launch_prep(const BaDev& d, int buf, cudaStream_t st);
 void launch_build(const BaDev& d, int Kmax, int robust, double delta, cudaStream_t st);
-void launch_solve(const BaDev& d, int max_col_blocks, cudaStream_t st);
+void launch_solve(const BaDev& d, int max_col_branch, int max_col_sep, cudaStream_t st);
+int solve_ring_capacity(int P, int nblk);
 void launch_solve_general(const BaDev& d, cudaStream_t st);
 int update_grid_blocks(int L, int C);
 void launch_update(const BaDev& d, int robust, double delta, int defer_decision, cudaStream_t st);

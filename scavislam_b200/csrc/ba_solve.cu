@@ -69,9 +69,8 @@ __device__ __forceinline__ bool chol6_regs(const double* __restrict__ A, double 
   return ok;
 }
 
-constexpr int kUpdPf = 2;        // update-list entries per update thread prefetched one column ahead
-constexpr int kPanelThreads = 128;  // warps 0-3: factor the next column (look-ahead); warp 0 owns the pivot chain
-constexpr int kUpdThreads = kSolveThreads - kPanelThreads;
+constexpr int kUpdPf = 2;         // update-list entries per update thread prefetched one column ahead
+constexpr int kMaxTeams = 4;      // independent branches of the elimination tree factored concurrently
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -112,69 +111,69 @@ __device__ __forceinline__ bool chol6_lean(const double* __restrict__ A, double 
   return ok;
 }
 
-// smem layout: [ring: cap*36 doubles][y: 6P doubles if y_in_smem][meta ints: col_ptr (P+1),
-//               upd_ptr (P+1), row_idx (nblk), urg_dst (nblk), fixed-by-position (P)]
-// cap is a power of two >= 4 * (widest column + 1).
-__global__ void __launch_bounds__(kSolveThreads)
-k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
-  extern __shared__ __align__(16) double sm_solve[];
-  __shared__ int sFailBuf[2];   // indexed by column parity: written by the panel warps, read after the column barrier
-  __shared__ double sRed[kSolveThreads / 32];
-  __shared__ double sL[2][28];   // factor of the diagonal block of column j (l 21, rinv 6), double buffered
-  double* ring = sm_solve;
-  const int mask = cap - 1;
-  double* ysm = sm_solve + (size_t)cap * 36;
-  double* yv = y_in_smem ? ysm : d.ywork;
-  LmCtl* ctl = d.ctl;
-  if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
-  const int t = threadIdx.x, nt = kSolveThreads, lane = t & 31, warp = t >> 5;
-  const int P = d.P, nblk = d.nblk;
-  const double lambda = ctl->lambda;
-  const int cur = ctl->cur;
-  if (t == 0) { sFailBuf[0] = 0; sFailBuf[1] = 0; }
-  int* meta = reinterpret_cast<int*>(ysm + (y_in_smem ? ((6 * (size_t)P + 1) / 2) * 2 : 0));
-  int* col_ptr = meta;
-  int* upd_ptr = col_ptr + (P + 1);
-  int* row_idx = upd_ptr + (P + 1);
-  int* urg_dst = row_idx + nblk;
-  int* sfix = urg_dst + nblk;
-  for (int i = t; i <= P; i += nt) { col_ptr[i] = d.col_ptr[i]; upd_ptr[i] = d.upd_ptr[i]; }
-  for (int i = t; i < nblk; i += nt) { row_idx[i] = d.row_idx[i]; urg_dst[i] = d.urg_dst[i]; }
-  for (int i = t; i < P; i += nt) sfix[i] = d.fixed[d.perm[i]];
-  // initial ring fill: blocks [0, hi)
-  int hi = min(nblk, cap);
-  for (int c = t; c < hi * 18; c += nt) {
-    const int id = c / 18, w = c - id * 18;
+
+// A team = a group of warps of the CTA that factors one contiguous range of columns.  With a
+// nested-dissection ordering the ranges of different teams are branches of the elimination tree
+// that only meet in the separator columns at the end: they run concurrently (the factorisation is
+// a latency chain, so the win is the shorter chain, not the extra lanes), scatter into the separator
+// blocks with FP64 atomics, and the separators are then factored by the whole CTA as one team.
+struct Team {
+  int tid, nth, npanel;       // thread index within the team, team size, threads on the look-ahead panel
+  int bar_all, bar_panel;     // named barriers
+  int slot;                   // index of the team's fail flags / diagonal-factor buffers
+  int ring_off, cap;          // the team's share of the shared-memory ring (blocks), power of two
+  int j0, j1;                 // column range [j0, j1)
+  int sep_pos0, sep_blk0;     // first separator column / its first block (P / nblk when there is none)
+};
+
+struct SolveShared {
+  double* ring; double* yv;
+  int* col_ptr; int* upd_ptr; int* row_idx; int* urg_dst; int* sfix;
+  int (*fail)[2];
+  double (*sL)[2][28];
+};
+
+// Right-looking block Cholesky of columns [T.j0, T.j1) with look-ahead; forward solve rides along.
+__device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S, double lambda, int refill_period) {
+  const int t = T.tid, lane = threadIdx.x & 31, twarp = T.tid >> 5;
+  const int nupd = T.nth - T.npanel, ut = t - T.npanel;
+  const int mask = T.cap - 1;
+  double* ring = S.ring + (size_t)T.ring_off * 36;
+  double* yv = S.yv;
+  const int* col_ptr = S.col_ptr; const int* upd_ptr = S.upd_ptr; const int* row_idx = S.row_idx;
+  const int* urg_dst = S.urg_dst;
+  const int blk_end = col_ptr[T.j1];
+  if (T.j0 >= T.j1) return;
+
+  // ring fill: blocks [col_ptr[j0], hi)
+  int hi = min(blk_end, col_ptr[T.j0] + T.cap);
+  for (int c = t; c < (hi - col_ptr[T.j0]) * 18; c += T.nth) {
+    const int id = col_ptr[T.j0] + c / 18, w = c % 18;
     cp_async16(ring + (size_t)(id & mask) * 36 + 2 * w, d.S + (size_t)id * 36 + 2 * w);
   }
   cp_async_commit();
-  for (int i = t; i < 6 * P; i += nt) {   // right-hand side in elimination order: bs = bp - bc
-    const int j = i / 6, r = i - 6 * j;
-    const int p = d.perm[j];
-    yv[i] = d.bp[6 * p + r] - d.bc[6 * p + r];
-  }
   cp_async_wait_all();
-  __syncthreads();
+  bar_sync(T.bar_all, T.nth);
 
-  // factor + scale the panel of column jn (panel warps only): chol by warp 0, rows by both
+  // factor + scale the panel of column jn (panel threads): pivot chain on warp 0, rows on all
   auto panel_column = [&](int jn) {
     const int base = col_ptr[jn], nb = col_ptr[jn + 1] - base - 1;
-    double* sl = sL[jn & 1];
-    if (warp == 0) {
+    double* sl = S.sL[T.slot][jn & 1];
+    if (twarp == 0) {
       double l[21], rinv[6];
-      const bool ok = chol6_lean(ring + (size_t)(base & mask) * 36, lambda + (sfix[jn] ? 1. : 0.), l, rinv);
+      const bool ok = chol6_lean(ring + (size_t)(base & mask) * 36, lambda + (S.sfix[jn] ? 1. : 0.), l, rinv);
       if (lane == 0) {
-        if (!ok) sFailBuf[jn & 1] = 1;
+        if (!ok) S.fail[T.slot][jn & 1] = 1;
 #pragma unroll
         for (int i = 0; i < 21; ++i) sl[i] = l[i];
 #pragma unroll
         for (int i = 0; i < 6; ++i) sl[21 + i] = rinv[i];
       }
     }
-    bar_sync(1, kPanelThreads);
+    bar_sync(T.bar_panel, T.npanel);
     // row <- row * L^-T by forward substitution (block rows: L_ij ; rhs row: y = L^-1 b)
     const int nrows = nb * 6 + 1;
-    for (int row = t; row < nrows; row += kPanelThreads) {
+    for (int row = t; row < nrows; row += T.npanel) {
       double* src;
       double* gdst = nullptr;
       if (row < nb * 6) {
@@ -201,20 +200,8 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
     }
   };
 
-  // one element of a pair update (used on the pivot chain, where width beats register tiling)
-  auto update_item = [&](int base, int w, int ab, int dst, int hi_res) {
-    const int pidx = w / 36, el = w - pidx * 36, r = el / 6, c = el - r * 6;
-    (void)pidx;
-    const double2* La = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab >> 16)) & mask) * 36 + r * 6);
-    const double2* Lb = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab & 0xffff)) & mask) * 36 + c * 6);
-    const double2 a0 = La[0], a1 = La[1], a2 = La[2], b0 = Lb[0], b1 = Lb[1], b2 = Lb[2];
-    const double s = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y);
-    if (dst < hi_res) ring[(size_t)(dst & mask) * 36 + el] -= s;
-    else d.S[(size_t)dst * 36 + el] -= s;
-  };
-  // half of a pair update, register tiled: rows 3h..3h+2 of S_ab -= L_a L_b^T.  18 + 36 doubles loaded
-  // for 108 FMAs -- off the pivot chain, what matters is not to flood the shared-memory pipe the
-  // chain also lives on (the element-wise form loads 12 doubles per 6 FMAs).
+  // half of a pair update, register tiled: rows 3h..3h+2 of S_ab -= L_a L_b^T (18 + 36 doubles loaded
+  // for 108 FMAs: off the pivot chain, what matters is not to flood the shared-memory pipe the chain lives on)
   auto update_half = [&](int base, int u, int ab, int dst, int hi_res) {
     const int h = u & 1;
     const double2* La = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab >> 16)) & mask) * 36 + h * 18);
@@ -231,51 +218,52 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
         o[r * 6 + c] = (a[r * 6] * b0.x + a[r * 6 + 1] * b0.y) + (a[r * 6 + 2] * b1.x + a[r * 6 + 3] * b1.y) +
                        (a[r * 6 + 4] * b2.x + a[r * 6 + 5] * b2.y);
     }
-    double2* D = reinterpret_cast<double2*>((dst < hi_res ? ring + (size_t)(dst & mask) * 36 : d.S + (size_t)dst * 36) + h * 18);
+    if (dst < hi_res) {
+      double2* D = reinterpret_cast<double2*>(ring + (size_t)(dst & mask) * 36 + h * 18);
 #pragma unroll
-    for (int q = 0; q < 9; ++q) { double2 v = D[q]; v.x -= o[2 * q]; v.y -= o[2 * q + 1]; D[q] = v; }
+      for (int q = 0; q < 9; ++q) { double2 v = D[q]; v.x -= o[2 * q]; v.y -= o[2 * q + 1]; D[q] = v; }
+    } else if (dst >= T.sep_blk0) {   // separator block shared with the other teams
+      double* D = d.S + (size_t)dst * 36 + h * 18;
+#pragma unroll
+      for (int q = 0; q < 18; ++q) atomicAdd(D + q, -o[q]);
+    } else {
+      double2* D = reinterpret_cast<double2*>(d.S + (size_t)dst * 36 + h * 18);
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { double2 v = D[q]; v.x -= o[2 * q]; v.y -= o[2 * q + 1]; D[q] = v; }
+    }
   };
 
-  // number of "urgent" pairs of column j: those that land in column j+1 (pairs (a, 0) when the
-  // first sub-diagonal row of column j is j+1; the update list is ordered b-major)
+  // pairs of column j that land in column j+1 (pairs (a, 0) when the first sub-diagonal row is j+1)
   auto urgent_of = [&](int j) {
     const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-    return (nb > 0 && row_idx[base + 1] == j + 1) ? nb : 0;
+    return (j + 1 < T.j1 && nb > 0 && row_idx[base + 1] == j + 1) ? nb : 0;
   };
 
-  long long tm[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) tm[i] = 0;
-  long long t_prev = clock64();
-#define TICK(slot) { const long long now_ = clock64(); tm[slot] += now_ - t_prev; t_prev = now_; }
-  if (P > 0 && t < kPanelThreads) panel_column(0);
-  const int ut = t - kPanelThreads;   // index among the update threads
+  if (t < T.npanel) panel_column(T.j0);
   int pf_ab[kUpdPf], pf_dst[kUpdPf];
   auto prefetch_upd = [&](int j) {
     const int u0 = upd_ptr[j] + urgent_of(j), nunits = (upd_ptr[j + 1] - u0) * 2;
 #pragma unroll
     for (int i = 0; i < kUpdPf; ++i) {
-      const int u = ut + i * kUpdThreads;
+      const int u = ut + i * nupd;
       if (u < nunits) { pf_ab[i] = d.upd_ab[u0 + (u >> 1)]; pf_dst[i] = d.upd_dst[u0 + (u >> 1)]; }
     }
   };
-  if (P > 0 && t >= kPanelThreads) prefetch_upd(0);
-  __syncthreads();
-  int failed = P > 0 ? sFailBuf[0] : 0;
+  if (t >= T.npanel) prefetch_upd(T.j0);
+  bar_sync(T.bar_all, T.nth);
+  int failed = S.fail[T.slot][T.j0 & 1];
   int until_refill = refill_period;
 
-  TICK(0);
-  for (int j = 0; j < P && !failed; ++j) {
+  for (int j = T.j0; j < T.j1 && !failed; ++j) {
     const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
     const int urgent = urgent_of(j);
     const int u0 = upd_ptr[j];
-    TICK(1);
-    if (t < kPanelThreads) {
-      // ---- panel warps: the part of column j's update that lands in column j+1, then factor it
+    if (t < T.npanel) {
+      // ---- panel threads: the part of column j's update that lands in column j+1, then factor it
       if (urgent) {
-        if (warp == 0) {
-          // S_{j+1,j+1} -= L L^T with L = L_{j+1,j}: symmetric, 21 lanes, one round; this is the only
-          // part of column j's update the next pivot chain waits for
+        if (twarp == 0) {
+          // S_{j+1,j+1} -= L L^T with L = L_{j+1,j}: symmetric, 21 lanes, one round -- the only part of
+          // column j's update the next pivot chain waits for
           if (lane < 21) {
             int r = 0, u = lane;
             while (u > r) { u -= r + 1; ++r; }
@@ -291,7 +279,7 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
           }
           __syncwarp();
         } else {
-          if (warp == 1 && lane < 6) {   // b_{j+1} -= L_{j+1,j} y_j
+          if (twarp == 1 && lane < 6) {   // b_{j+1} -= L_{j+1,j} y_j
             const double* La = ring + (size_t)((base + 1) & mask) * 36 + lane * 6;
             const double* yj = yv + 6 * j;
             double sv = 0.;
@@ -299,42 +287,42 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
             for (int q = 0; q < 6; ++q) sv += La[q] * yj[q];
             yv[6 * (j + 1) + lane] -= sv;
           }
-          for (int u = 2 + (t - 32); u < urgent * 2; u += kPanelThreads - 32) {
+          for (int u = 2 + (t - 32); u < urgent * 2; u += T.npanel - 32) {
             const int a = u >> 1;
             update_half(base, u, a << 16, urg_dst[base + 1 + a], 0x7fffffff);
           }
         }
       }
-      TICK(2);
-      if (j + 1 < P) panel_column(j + 1);   // its barrier also orders warp 1's panel updates before the row scaling
-      TICK(3);
+      if (j + 1 < T.j1) panel_column(j + 1);   // its barrier also orders the other panel warps' updates before the row scaling
     } else {
-      // ---- update warps: the rest of column j's trailing update
+      // ---- update threads: the rest of column j's trailing update
       int cu_ab[kUpdPf], cu_dst[kUpdPf];
 #pragma unroll
       for (int i = 0; i < kUpdPf; ++i) { cu_ab[i] = pf_ab[i]; cu_dst[i] = pf_dst[i]; }
-      if (j + 1 < P) prefetch_upd(j + 1);
+      if (j + 1 < T.j1) prefetch_upd(j + 1);
       const int uu = u0 + urgent, nunits = (upd_ptr[j + 1] - uu) * 2;
 #pragma unroll
       for (int i = 0; i < kUpdPf; ++i) {
-        const int u = ut + i * kUpdThreads;
+        const int u = ut + i * nupd;
         if (u < nunits) update_half(base, u, cu_ab[i], cu_dst[i], hi);
       }
-      for (int u = ut + kUpdPf * kUpdThreads; u < nunits; u += kUpdThreads)
+      for (int u = ut + kUpdPf * nupd; u < nunits; u += nupd)
         update_half(base, u, d.upd_ab[uu + (u >> 1)], d.upd_dst[uu + (u >> 1)], hi);
-      // b_a -= L_aj y_j for the rows the panel warps did not take
-      for (int w = ut + (urgent ? 6 : 0); w < nb * 6; w += kUpdThreads) {
+      // b_a -= L_aj y_j for the rows the panel threads did not take
+      for (int w = ut + (urgent ? 6 : 0); w < nb * 6; w += nupd) {
         const int a = w / 6, r = w - a * 6;
         const double* La = ring + (size_t)((base + 1 + a) & mask) * 36 + r * 6;
         const double* yj = yv + 6 * j;
         double s = 0.;
 #pragma unroll
         for (int q = 0; q < 6; ++q) s += La[q] * yj[q];
-        yv[6 * row_idx[base + 1 + a] + r] -= s;
+        const int row = row_idx[base + 1 + a];
+        if (row >= T.sep_pos0) atomicAdd(yv + 6 * row + r, -s);   // separator row shared with the other teams
+        else yv[6 * row + r] -= s;
       }
       // inverse of column j's diagonal factor for the backward solve (off the critical path)
-      if (warp == kSolveThreads / 32 - 1 && lane < 6) {
-        const double* sl = sL[j & 1];
+      if (twarp == (T.nth >> 5) - 1 && lane < 6) {
+        const double* sl = S.sL[T.slot][j & 1];
         const int c = lane;
         double col[6];
 #pragma unroll
@@ -347,29 +335,162 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) d.Linv[36 * (size_t)j + r * 6 + c] = col[r];
       }
-      TICK(4);
     }
-    __syncthreads();
-    TICK(5);
-    failed = sFailBuf[(j + 1) & 1];
+    bar_sync(T.bar_all, T.nth);
+    failed = S.fail[T.slot][(j + 1) & 1];
     // ---- every refill_period columns: reload the ring slots the finished columns freed.  Copies are
     //      never in flight while updates run, so a destination is either resident (< hi) or in HBM.
     if (--until_refill == 0) until_refill = refill_period;
-    if (until_refill == refill_period && hi < nblk) {
-      const int hi_new = min(nblk, col_ptr[j + 1] + cap);
-      for (int c = t; c < (hi_new - hi) * 18; c += nt) {
+    if (until_refill == refill_period && hi < blk_end && j + 1 < T.j1) {
+      const int hi_new = min(blk_end, col_ptr[j + 1] + T.cap);
+      for (int c = t; c < (hi_new - hi) * 18; c += T.nth) {
         const int id = hi + c / 18, w = c % 18;
         cp_async16(ring + (size_t)(id & mask) * 36 + 2 * w, d.S + (size_t)id * 36 + 2 * w);
       }
       cp_async_commit();
       cp_async_wait_all();
-      __syncthreads();
+      bar_sync(T.bar_all, T.nth);
       hi = hi_new;
-      TICK(6);
     }
+  }
+  if (failed && t == 0) S.fail[T.slot][0] = S.fail[T.slot][1] = 1;
+}
+
+// Backward solve L^T x = y for columns [T.j0, T.j1), descending: the factor is streamed back through
+// the team's ring in chunks (L blocks + inverse diagonal factors), double buffered; the team's warp 0
+// walks the dependency chain out of shared memory while its other warps fetch the next chunk.
+__device__ void backsolve_range(const BaDev& d, const Team& T, const SolveShared& S) {
+  if (T.j0 >= T.j1) return;
+  const int t = T.tid, lane = threadIdx.x & 31, twarp = T.tid >> 5;
+  const int* col_ptr = S.col_ptr; const int* row_idx = S.row_idx;
+  double* yv = S.yv;
+  const int half = T.cap / 2;
+  double* bufs[2] = {S.ring + (size_t)T.ring_off * 36, S.ring + (size_t)(T.ring_off + half) * 36};
+  auto chunk_lo = [&](int jhi) {   // largest [jlo, jhi) whose blocks + diagonal inverses fit one half
+    int jlo = jhi - 1;
+    while (jlo > T.j0 && (col_ptr[jhi] - col_ptr[jlo - 1]) + (jhi - (jlo - 1)) <= half) --jlo;
+    return jlo;
+  };
+  auto load_chunk = [&](double* buf, int jlo, int jhi, int tid, int nth) {
+    const int nb16 = (col_ptr[jhi] - col_ptr[jlo]) * 18;
+    const double* src = d.S + (size_t)col_ptr[jlo] * 36;
+    for (int c = tid; c < nb16; c += nth) cp_async16(buf + 2 * (size_t)c, src + 2 * (size_t)c);
+    double* lbuf = buf + (size_t)(col_ptr[jhi] - col_ptr[jlo]) * 36;
+    const double* lsrc = d.Linv + (size_t)jlo * 36;
+    for (int c = tid; c < (jhi - jlo) * 18; c += nth) cp_async16(lbuf + 2 * (size_t)c, lsrc + 2 * (size_t)c);
+    cp_async_commit();
+  };
+  int jhi = T.j1, which = 0;
+  int jlo = chunk_lo(jhi);
+  load_chunk(bufs[0], jlo, jhi, t, T.nth);
+  cp_async_wait_all();
+  bar_sync(T.bar_all, T.nth);
+  while (jhi > T.j0) {
+    const int njhi = jlo, njlo = njhi > T.j0 ? chunk_lo(njhi) : T.j0;
+    if (njhi > T.j0 && twarp > 0) load_chunk(bufs[which ^ 1], njlo, njhi, t - 32, T.nth - 32);
+    if (twarp == 0) {
+      const double* buf = bufs[which];
+      const double* lbuf = buf + (size_t)(col_ptr[jhi] - col_ptr[jlo]) * 36;
+      const int r = lane % 6, g = lane / 6;   // 5 lane groups walk a column's blocks; lanes 30,31 idle
+      for (int j = jhi - 1; j >= jlo; --j) {
+        const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
+        double acc = 0.;
+        if (lane < 30)
+          for (int a = g; a < nb; a += 5) {
+            const double* La = buf + (size_t)(base + 1 + a - col_ptr[jlo]) * 36;
+            const double* xa = yv + 6 * row_idx[base + 1 + a];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc += La[q * 6 + r] * xa[q];
+          }
+        double tot = acc;
+        tot += __shfl_down_sync(0xffffffffu, acc, 6);
+        const double a12 = __shfl_down_sync(0xffffffffu, acc, 12);
+        const double a18 = __shfl_down_sync(0xffffffffu, acc, 18);
+        const double a24 = __shfl_down_sync(0xffffffffu, acc, 24);
+        tot += a12 + a18 + a24;
+        double v = 0.;
+        if (lane < 6) v = yv[6 * j + lane] - tot;
+        const double* Li = lbuf + (size_t)(j - jlo) * 36;
+        double xr = 0.;   // x_r = sum_{q >= r} Linv[q][r] v_q
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double vq = __shfl_sync(0xffffffffu, v, q);
+          if (lane < 6 && q >= lane) xr += Li[q * 6 + lane] * vq;
+        }
+        if (lane < 6) yv[6 * j + lane] = xr;
+        __syncwarp();
+      }
+    }
+    cp_async_wait_all();
+    bar_sync(T.bar_all, T.nth);
+    jhi = njhi; jlo = njlo; which ^= 1;
+  }
+}
+
+// smem layout: [ring: cap*36 doubles][y: 6P doubles][meta ints: col_ptr (P+1), upd_ptr (P+1),
+//               row_idx (nblk), urg_dst (nblk), fixed-by-position (P)]
+// cap is a power of two; every team's share is >= 4 * (widest column of its range + 1).
+__global__ void __launch_bounds__(kSolveThreads)
+k_solve(BaDev d, int cap, int refill_branch, int refill_sep) {
+  extern __shared__ __align__(16) double sm_solve[];
+  __shared__ int sFail[kMaxTeams + 1][2];
+  __shared__ double sRed[kSolveThreads / 32];
+  __shared__ double sLbuf[kMaxTeams + 1][2][28];
+  LmCtl* ctl = d.ctl;
+  if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
+  const int t = threadIdx.x, nt = kSolveThreads, lane = t & 31, warp = t >> 5;
+  const int P = d.P, nblk = d.nblk;
+  const double lambda = ctl->lambda;
+  const int cur = ctl->cur;
+  SolveShared S;
+  S.ring = sm_solve;
+  S.yv = sm_solve + (size_t)cap * 36;
+  int* meta = reinterpret_cast<int*>(S.yv + ((6 * (size_t)P + 1) / 2) * 2);
+  S.col_ptr = meta; S.upd_ptr = S.col_ptr + (P + 1); S.row_idx = S.upd_ptr + (P + 1);
+  S.urg_dst = S.row_idx + nblk; S.sfix = S.urg_dst + nblk;
+  S.fail = sFail; S.sL = sLbuf;
+  if (t < 2 * (kMaxTeams + 1)) sFail[t >> 1][t & 1] = 0;
+  for (int i = t; i <= P; i += nt) { S.col_ptr[i] = d.col_ptr[i]; S.upd_ptr[i] = d.upd_ptr[i]; }
+  for (int i = t; i < nblk; i += nt) { S.row_idx[i] = d.row_idx[i]; S.urg_dst[i] = d.urg_dst[i]; }
+  for (int i = t; i < P; i += nt) S.sfix[i] = d.fixed[d.perm[i]];
+  for (int i = t; i < 6 * P; i += nt) {   // right-hand side in elimination order: bs = bp - bc
+    const int j = i / 6, r = i - 6 * j;
+    const int p = d.perm[j];
+    S.yv[i] = d.bp[6 * p + r] - d.bc[6 * p + r];
+  }
+  __syncthreads();
+  long long tk[8];
+  tk[0] = clock64();
+
+  const int G = d.nbranch;                 // 1: a single chain (no nested dissection)
+  const int sep0 = d.branch_ptr[G];        // first separator column (= P when G == 1)
+  Team whole;
+  whole.tid = t; whole.nth = nt; whole.npanel = 128; whole.bar_all = 0; whole.bar_panel = 9; whole.slot = kMaxTeams;
+  whole.ring_off = 0; whole.cap = cap; whole.sep_pos0 = P; whole.sep_blk0 = nblk;
+  Team mine = whole;
+  if (G > 1) {
+    const int tn = nt / G, g = t / tn;
+    mine.tid = t - g * tn; mine.nth = tn; mine.npanel = tn / 2; mine.bar_all = 1 + 2 * g; mine.bar_panel = 2 + 2 * g;
+    mine.slot = g; mine.cap = cap / G; mine.ring_off = g * (cap / G);
+    mine.j0 = d.branch_ptr[g]; mine.j1 = d.branch_ptr[g + 1];
+    mine.sep_pos0 = sep0; mine.sep_blk0 = S.col_ptr[sep0];
+    factor_range(d, mine, S, lambda, refill_branch);
+    tk[1] = clock64();
+    __threadfence_block();
+    __syncthreads();
+    tk[2] = clock64();
+    whole.j0 = sep0; whole.j1 = P;
+    factor_range(d, whole, S, lambda, refill_sep);
+  } else {
+    tk[1] = tk[2] = tk[0];
+    whole.j0 = 0; whole.j1 = P;
+    factor_range(d, whole, S, lambda, refill_sep);
   }
   cp_async_wait_all();
   __syncthreads();
+  tk[3] = clock64();
+  int failed = 0;
+  for (int g = 0; g <= kMaxTeams; ++g) failed |= sFail[g][0] | sFail[g][1];
   if (failed) {
     if (t == 0) { ctl->chol_fail = 1; ctl->scale_pose = 0; }
     for (int i = t; i < 7 * P; i += nt) d.pose[1 - cur][i] = d.pose[cur][i];
@@ -377,77 +498,23 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
     for (int i = t; i < 6 * P; i += nt) d.x[i] = 0;
     return;
   }
-  // --- backward solve L^T x = y.  The ring is free now: the factor is streamed back through it in
-  //     chunks of columns (L blocks + the inverse diagonal factors), double buffered; warp 0 walks
-  //     the dependency chain out of shared memory while the other warps fetch the next chunk.
-  {
-    const int half = cap / 2;
-    double* bufs[2] = {ring, ring + (size_t)half * 36};
-    auto chunk_lo = [&](int jhi) {   // largest [jlo, jhi) whose blocks + diagonal inverses fit one half
-      int jlo = jhi;
-      while (jlo > 0 && (col_ptr[jhi] - col_ptr[jlo - 1]) + (jhi - (jlo - 1)) <= half) --jlo;
-      return jlo;
-    };
-    auto load_chunk = [&](double* buf, int jlo, int jhi, int tid, int nth) {
-      const int nb16 = (col_ptr[jhi] - col_ptr[jlo]) * 18;
-      const double* src = d.S + (size_t)col_ptr[jlo] * 36;
-      for (int c = tid; c < nb16; c += nth) cp_async16(buf + 2 * (size_t)c, src + 2 * (size_t)c);
-      double* lbuf = buf + (size_t)(col_ptr[jhi] - col_ptr[jlo]) * 36;
-      const double* lsrc = d.Linv + (size_t)jlo * 36;
-      for (int c = tid; c < (jhi - jlo) * 18; c += nth) cp_async16(lbuf + 2 * (size_t)c, lsrc + 2 * (size_t)c);
-      cp_async_commit();
-    };
-    int jhi = P, which = 0;
-    int jlo = chunk_lo(jhi);
-    if (P > 0) load_chunk(bufs[0], jlo, jhi, t, nt);
-    cp_async_wait_all();
+  // backward: separators first, then the branches concurrently
+  if (G > 1) {
+    backsolve_range(d, whole, S);
     __syncthreads();
-    while (jhi > 0) {
-      const int njhi = jlo, njlo = njhi > 0 ? chunk_lo(njhi) : 0;
-      if (njhi > 0 && warp > 0) load_chunk(bufs[which ^ 1], njlo, njhi, t - 32, nt - 32);
-      if (warp == 0) {
-        const double* buf = bufs[which];
-        const double* lbuf = buf + (size_t)(col_ptr[jhi] - col_ptr[jlo]) * 36;
-        const int r = lane % 6, g = lane / 6;   // 5 lane groups walk a column's blocks; lanes 30,31 idle
-        for (int j = jhi - 1; j >= jlo; --j) {
-          const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-          double acc = 0.;
-          if (lane < 30)
-            for (int a = g; a < nb; a += 5) {
-              const double* La = buf + (size_t)(base + 1 + a - col_ptr[jlo]) * 36;
-              const double* xa = yv + 6 * row_idx[base + 1 + a];
-#pragma unroll
-              for (int q = 0; q < 6; ++q) acc += La[q * 6 + r] * xa[q];
-            }
-          double tot = acc;
-          tot += __shfl_down_sync(0xffffffffu, acc, 6);
-          const double a12 = __shfl_down_sync(0xffffffffu, acc, 12);
-          const double a18 = __shfl_down_sync(0xffffffffu, acc, 18);
-          const double a24 = __shfl_down_sync(0xffffffffu, acc, 24);
-          tot += a12 + a18 + a24;
-          double v = 0.;
-          if (lane < 6) v = yv[6 * j + lane] - tot;
-          const double* Li = lbuf + (size_t)(j - jlo) * 36;
-          double xr = 0.;   // x_r = sum_{q >= r} Linv[q][r] v_q
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const double vq = __shfl_sync(0xffffffffu, v, q);
-            if (lane < 6 && q >= lane) xr += Li[q * 6 + lane] * vq;
-          }
-          if (lane < 6) yv[6 * j + lane] = xr;
-          __syncwarp();
-        }
-      }
-      cp_async_wait_all();
-      __syncthreads();
-      jhi = njhi; jlo = njlo; which ^= 1;
-    }
+    tk[4] = clock64();
+    backsolve_range(d, mine, S);
+    tk[5] = clock64();
+  } else {
+    backsolve_range(d, whole, S);
+    tk[4] = tk[5] = clock64();
   }
   __syncthreads();
-  TICK(7);
-  if (d.dbg && (t == 0 || t == kPanelThreads)) {
-    for (int i = 0; i < 12; ++i) d.dbg[(t ? 12 : 0) + i] = tm[i];
+  tk[6] = clock64();
+  if (d.dbg && (t & 127) == 0) {   // one thread per team: phase boundaries in cycles since the setup
+    for (int i = 1; i < 7; ++i) d.dbg[(t >> 7) * 6 + i - 1] = tk[i] - tk[0];
   }
+  double* yv = S.yv;
   // --- pose update (G2oVertexSE3::oplusImpl) into the trial buffer; scale = sum x (lambda x + b)
   double sc = 0;
   for (int p = t; p < P; p += nt) {
@@ -490,37 +557,41 @@ k_solve(BaDev d, int cap, int y_in_smem, int refill_period) {
   }
 }
 
-// Picks the ring capacity for a device and launches; falls back to the global-memory kernel
-// when one factor column alone would not fit the ring.
-void launch_solve(const BaDev& d, int max_col_blocks, cudaStream_t st) {
+// Shared-memory budget of k_solve: ring capacity (blocks, power of two) for a problem, 0 if the
+// right-hand side and the index metadata alone do not fit.
+int solve_ring_capacity(int P, int nblk) {
   static int smem_optin = -1;
   if (smem_optin < 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
+    cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);   // 2.4 KB static
   }
-  const size_t budget = (size_t)smem_optin - 1024 - 256;
-  const int y_in_smem = (size_t)6 * d.P * 8 <= budget / 4;
-  const size_t ybytes = y_in_smem ? (((size_t)6 * d.P * 8 + 15) / 16) * 16 : 0;
-  const size_t mbytes = ((size_t)(2 * (d.P + 1) + 2 * d.nblk + d.P) * 4 + 15) / 16 * 16;
-  int cap = 0;
-  if (ybytes + mbytes < budget) {
-    const int avail = (int)((budget - ybytes - mbytes) / 288);
-    for (cap = 1; cap * 2 <= avail; cap *= 2) {}
-    if (cap > avail) cap = 0;
-  }
-  // the look-ahead kernel keeps two columns live and never checks residency on them
-  if (d.P == 0 || cap < 4 * (max_col_blocks + 1)) {
+  const size_t budget = (size_t)smem_optin - 4096 - 256;
+  const size_t ybytes = (((size_t)6 * P * 8 + 15) / 16) * 16;
+  const size_t mbytes = ((size_t)(2 * (P + 1) + 2 * nblk + P) * 4 + 15) / 16 * 16;
+  if (ybytes + mbytes >= budget || ybytes > budget / 4) return 0;
+  const int avail = (int)((budget - ybytes - mbytes) / 288);
+  int cap = 1;
+  while (cap * 2 <= avail) cap *= 2;
+  return cap <= avail ? cap : 0;
+}
+
+// Launches the look-ahead kernel when every team's ring share holds 4 of its widest columns
+// (it keeps two columns live and never checks residency on them); otherwise the global-memory kernel.
+void launch_solve(const BaDev& d, int max_col_branch, int max_col_sep, cudaStream_t st) {
+  int cap = d.P > 0 ? solve_ring_capacity(d.P, d.nblk) : 0;
+  const int G = d.nbranch;
+  if (cap == 0 || cap / G < 4 * (max_col_branch + 1) || cap < 4 * (max_col_sep + 1)) {
     launch_solve_general(d, st);
     return;
   }
-  while (cap / 2 >= d.nblk && cap / 2 >= 4 * (max_col_blocks + 1)) cap /= 2;   // small problems: small ring
-  // columns j+1 and j+2 must stay resident between refills: cap >= (period + 3) * widest column
-  int period = cap / (max_col_blocks + 1) - 3;
-  period = period < 1 ? 1 : (period > 32 ? 32 : period);
+  while (G == 1 && cap / 2 >= d.nblk && cap / 2 >= 4 * (max_col_sep + 1)) cap /= 2;   // small problems: small ring
+  auto period = [](int c, int widest) { int p = c / (widest + 1) - 3; return p < 1 ? 1 : (p > 32 ? 32 : p); };
+  const size_t ybytes = (((size_t)6 * d.P * 8 + 15) / 16) * 16;
+  const size_t mbytes = ((size_t)(2 * (d.P + 1) + 2 * d.nblk + d.P) * 4 + 15) / 16 * 16;
   const size_t smem = (size_t)cap * 288 + ybytes + mbytes;
-  k_solve<<<1, kSolveThreads, smem, st>>>(d, cap, y_in_smem, period);
+  k_solve<<<1, kSolveThreads, smem, st>>>(d, cap, period(cap / G, max_col_branch), period(cap, max_col_sep));
 }
 
 }  // namespace svs

@@ -77,6 +77,8 @@ struct BaDev {
   const int* upd_ab;   // (a << 16 | b): indices into the column's sub-diagonal list (b-major order)
   const int* urg_dst;  // [nblk] destination of pair (a, 0) of column j at col_ptr[j] + 1 + a
   double* Linv;        // [P][36] inverse of the diagonal factor blocks
+  int nbranch;              // independent branches of the elimination tree (1 = a single chain)
+  const int* branch_ptr;    // [nbranch + 1] column ranges of the branches; [nbranch] = first separator column
   double* ywork;       // [6P]
   double* part;        // [update grid][3] per-CTA partial sums (chi2 accepted, chi2 trial, scale)
   unsigned* ticket;    // last-CTA-done counter of k_update
