@@ -41,6 +41,11 @@ struct svs_ba {
   int C_edges = 0;
   int max_col_blocks = 0, max_col_branch = 0, nbranch = 1;
   std::vector<int> extra_pairs;   // svs_ba_set_structure: pose pairs added to the block pattern
+  // host scratch of set_problem, kept across calls (fresh multi-MB vectors page-fault every time)
+  std::vector<int> w_eptr, w_eord, w_fill, w_anchor, w_K, w_order, w_lm_eptr, w_lm_sptr, w_lm_anchor, w_ie_pose, w_bucket;
+  std::vector<unsigned char> w_self, w_lm_self, w_adj;
+  std::vector<unsigned long long> w_key;
+  std::vector<double> w_obs, w_w, w_psi;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> tev;   // per-trial timing events
   // last optimize() settings
@@ -80,7 +85,19 @@ int dev_upload(svs_ba* h, const T** p, const T* src, size_t n) {
   T* q = nullptr;
   dev_alloc(h, &q, n);
   if (!h->measuring) {
-    if (n) memcpy(h->stage + off, src, n * sizeof(T));
+    if (n) {
+      const size_t bytes = n * sizeof(T);
+      if (bytes >= (1u << 20)) {   // multi-MB arrays (observations, weights): split the copy over a few threads
+        const int parts = 4;
+#pragma omp parallel for num_threads(4)
+        for (int q = 0; q < parts; ++q) {
+          const size_t b0 = bytes * q / parts, b1 = bytes * (q + 1) / parts;
+          memcpy(h->stage + off + b0, reinterpret_cast<const char*>(src) + b0, b1 - b0);
+        }
+      } else {
+        memcpy(h->stage + off, src, bytes);
+      }
+    }
     *p = q;
   }
   return SVS_OK;
@@ -325,17 +342,21 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   };
 
   // ---- group edges per landmark (counting sort), flat arrays only: this runs on the caller's
-  //      thread inside the end-to-end time, like g2o's buildStructure does in the reference
-  std::vector<int> eptr(L + 1, 0);
+  //      thread inside the end-to-end time, like g2o's buildStructure does in the reference.
+  //      Scratch lives in the handle; the per-landmark and per-edge loops use a few host threads.
+  auto& eptr = h->w_eptr; auto& eord = h->w_eord; auto& fillp = h->w_fill;
+  eptr.assign(L + 1, 0);
   for (int e = 0; e < E; ++e) eptr[e_point[e] + 1]++;
   for (int l = 0; l < L; ++l) eptr[l + 1] += eptr[l];
-  std::vector<int> eord(E), fillp(eptr.begin(), eptr.end() - 1);
+  eord.resize(E);
+  fillp.assign(eptr.begin(), eptr.end() - 1);
   for (int e = 0; e < E; ++e) eord[fillp[e_point[e]]++] = e;
   // per landmark: anchor, self-observation flag, observer edges sorted by pose index (in place in eord)
-  std::vector<int> l_anchor(L, -1), l_K(L, 0);
-  std::vector<unsigned char> l_self(L, 0);
-  std::vector<unsigned long long> key(L);
+  auto& l_anchor = h->w_anchor; auto& l_K = h->w_K; auto& l_self = h->w_self; auto& key = h->w_key;
+  l_anchor.assign(L, -1); l_K.assign(L, 0); l_self.assign(L, 0); key.resize(L);
   int Kmax = 1;
+  int bad = 0;
+#pragma omp parallel for schedule(static) reduction(max : Kmax) reduction(max : bad) num_threads(4) if (L > 4096)
   for (int l = 0; l < L; ++l) {
     const int b = eptr[l], en = eptr[l + 1];
     key[l] = ~0ull;   // landmarks without observations go last
@@ -344,8 +365,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     int nself = 0;
     for (int k = b; k < en; ++k) {
       const int e = eord[k];
-      if (e_anchor[e] != anchor)
-        return fail(h, SVS_ERR_UNSUPPORTED, "edges of one point name different anchor frames");
+      if (e_anchor[e] != anchor) bad = std::max(bad, 1);
       if (e_pose[e] == anchor) ++nself;
     }
     // insertion sort by (is-not-self, pose): the self edge first, then ascending pose index
@@ -363,47 +383,64 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
       eord[q + 1] = e;
     }
     for (int k = b + 1; k < en; ++k)
-      if (e_pose[eord[k]] == e_pose[eord[k - 1]])
-        return fail(h, SVS_ERR_UNSUPPORTED, "a point is observed twice by the same frame");
+      if (e_pose[eord[k]] == e_pose[eord[k - 1]]) bad = std::max(bad, 2);
     const int K = 1 + (en - b) - nself;
-    if (K > kMaxTrack) return fail(h, SVS_ERR_UNSUPPORTED, "landmark track longer than 31 frames + anchor");
+    if (K > kMaxTrack) bad = std::max(bad, 3);
     l_anchor[l] = anchor; l_self[l] = (unsigned char)nself; l_K[l] = K;
     Kmax = std::max(Kmax, K);
-    // locality key: anchor, then track shape (first and last observer), so that neighbouring warps
-    // of the fused kernel scatter into the same blocks of the reduced system
+    // locality key: track shape (self flag, length, first and last observer) inside an anchor, so that
+    // neighbouring warps of the fused kernel scatter into the same blocks of the reduced system
     const unsigned long long first = (unsigned long long)(e_pose[eord[b + (nself ? 1 : 0) < en ? b + (nself ? 1 : 0) : b]] & 0xfffff);
     const unsigned long long last = (unsigned long long)(e_pose[eord[en - 1]] & 0xfffff);
-    key[l] = ((unsigned long long)anchor << 44) | ((unsigned long long)(1 - nself) << 43) |
-             ((unsigned long long)K << 40) | (first << 20) | last;
+    key[l] = ((unsigned long long)(1 - nself) << 43) | ((unsigned long long)K << 40) | (first << 20) | last;
   }
+  if (bad == 1) return fail(h, SVS_ERR_UNSUPPORTED, "edges of one point name different anchor frames");
+  if (bad == 2) return fail(h, SVS_ERR_UNSUPPORTED, "a point is observed twice by the same frame");
+  if (bad == 3) return fail(h, SVS_ERR_UNSUPPORTED, "landmark track longer than 31 frames + anchor");
   lap("group");
-  std::vector<int> order(L);
-  std::iota(order.begin(), order.end(), 0);
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
+  // internal landmark order: bucket by anchor (counting sort), then by track shape inside a bucket
+  auto& order = h->w_order; auto& bucket = h->w_bucket;
+  order.resize(L);
+  bucket.assign(P + 2, 0);
+  for (int l = 0; l < L; ++l) bucket[(l_anchor[l] < 0 ? P : l_anchor[l]) + 1]++;
+  for (int a = 0; a <= P; ++a) bucket[a + 1] += bucket[a];
+  {
+    auto& cur = fillp;
+    cur.assign(bucket.begin(), bucket.end() - 1);
+    for (int l = 0; l < L; ++l) order[cur[l_anchor[l] < 0 ? P : l_anchor[l]]++] = l;
+  }
+#pragma omp parallel for schedule(dynamic, 16) num_threads(4) if (L > 4096)
+  for (int a = 0; a <= P; ++a)
+    std::sort(order.begin() + bucket[a], order.begin() + bucket[a + 1],
+              [&](int x, int y) { return key[x] != key[y] ? key[x] < key[y] : x < y; });
   h->lm_to_user = order;
-  std::vector<int> lm_eptr(L + 1, 0), lm_sptr(L + 1, 0), lm_anchor(L, 0), ie_pose(E);
-  std::vector<unsigned char> lm_self(L, 0);
-  std::vector<double> ie_obs(3 * (size_t)E), ie_w(3 * (size_t)E), ipsi(3 * (size_t)L);
-  int ne = 0, ns = 0;
+  auto& lm_eptr = h->w_lm_eptr; auto& lm_sptr = h->w_lm_sptr; auto& lm_anchor = h->w_lm_anchor; auto& ie_pose = h->w_ie_pose;
+  auto& lm_self = h->w_lm_self; auto& ie_obs = h->w_obs; auto& ie_w = h->w_w; auto& ipsi = h->w_psi;
+  lm_eptr.assign(L + 1, 0); lm_sptr.assign(L + 1, 0); lm_anchor.assign(L, 0); ie_pose.resize(E);
+  lm_self.assign(L, 0); ie_obs.resize(3 * (size_t)E); ie_w.resize(3 * (size_t)E); ipsi.resize(3 * (size_t)L);
   for (int li = 0; li < L; ++li) {
     const int l = order[li];
-    lm_eptr[li] = ne; lm_sptr[li] = ns;
+    lm_eptr[li + 1] = lm_eptr[li] + (eptr[l + 1] - eptr[l]);
+    lm_sptr[li + 1] = lm_sptr[li] + l_K[l];
+  }
+  const int ne = lm_eptr[L], ns = lm_sptr[L];
+  (void)ne;
+#pragma omp parallel for schedule(static) num_threads(4) if (L > 4096)
+  for (int li = 0; li < L; ++li) {
+    const int l = order[li];
     for (int q = 0; q < 3; ++q) ipsi[3 * (size_t)li + q] = psi[3 * (size_t)l + q];
     if (l_anchor[l] < 0) continue;
     lm_anchor[li] = l_anchor[l]; lm_self[li] = l_self[l];
-    for (int k = eptr[l]; k < eptr[l + 1]; ++k) {
+    int at = lm_eptr[li];
+    for (int k = eptr[l]; k < eptr[l + 1]; ++k, ++at) {
       const int e = eord[k];
-      ie_pose[ne] = e_pose[e];
+      ie_pose[at] = e_pose[e];
       for (int q = 0; q < 3; ++q) {
-        ie_obs[(size_t)q * E + ne] = e_obs[3 * (size_t)e + q];
-        ie_w[(size_t)q * E + ne] = e_info[3 * (size_t)e + q];
+        ie_obs[(size_t)q * E + at] = e_obs[3 * (size_t)e + q];
+        ie_w[(size_t)q * E + at] = e_info[3 * (size_t)e + q];
       }
-      ++ne;
     }
-    ns += l_K[l];
   }
-  lm_eptr[L] = ne; lm_sptr[L] = ns;
-  lap("sort+regroup");
   // ---- work lists of the fused kernel: runs of landmarks with identical slot lists (<= 8 frames)
   std::vector<int> task_lm, task_cnt, gen_lm;
   int Kmax_gen = 1;
@@ -436,7 +473,10 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   // ---- pose graph of the reduced system: co-visibility (all pairs inside a track) + constraints
   std::vector<std::vector<int>> adj(P);
   {
-    std::vector<unsigned char> A((size_t)P * P, 0);
+    auto& A = h->w_adj;
+    A.assign((size_t)P * P, 0);
+    // (concurrent writers only ever store 1 into a byte: benign)
+#pragma omp parallel for schedule(static) num_threads(4) if (L > 4096)
     for (int l = 0; l < L; ++l) {
       if (l_anchor[l] < 0) continue;
       int ps[kMaxTrack + 1];

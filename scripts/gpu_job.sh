@@ -1,3 +1,10 @@
-timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_c.json 2>/dev/null; python -c "
-import json; d=json.loads(open('gpurun_out/bench_c.json').read()); print({k:d[k] for k in ('value','ms_per_step','e2e','kernel_ms_per_step','gpu_launches')}); print(d['roofline']); print(d['frontend'])"
+timeout 200 python -m pytest tests/test_ba_gpu.py tests/test_dist_gpu.py tests/test_cpp_shim.py -x -q -m gpu 2>&1 | tail -3
+SVS_HOST_TIMING=1 timeout 100 python - 2>&1 <<'PY' | tail -12
+import sys, time; sys.path.insert(0,'.')
+from scavislam_b200 import capi, synth
+pb = synth.make_config("C2"); ba = capi.BundleAdjuster()
+for i in range(4):
+    t=time.perf_counter(); it,p,s,st = ba.optimise_inner_and_outer_window(pb, 10); t2=time.perf_counter()
+    print("one-call", (t2-t)*1e3, "ms; device", st["ms_total"])
+PY
+nproc
