@@ -165,3 +165,72 @@ def test_c2_full_size_parity(ba, oracle):
     assert _rel(ba.points(), pso) < POSE_RTOL
     # size-independent property: chi2 decreases monotonically over accepted iterations
     assert all(a >= b for a, b in zip([st["chi2_init"]] + st["chi2_iter"][:-1], st["chi2_iter"]))
+
+
+# ---------------------------------------------------------------- structure variety (generic code paths)
+
+def _add_constraints(pb, pairs, seed=0):
+    """Extra pose-pose constraints (e.g. loop closures) with the measurement taken from the truth."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(seed)
+    ci, cj, cT, cL = list(pb.c_i), list(pb.c_j), list(pb.c_T), list(pb.c_Lambda)
+    for (i, j) in pairs:
+        T = po.se3_mul(po.se3_exp(rng.normal(0, 1e-3, 6)), po.se3_mul(pb.truth_pose_qt[j], po.se3_inv(pb.truth_pose_qt[i])))
+        lam = np.diag([4e4] * 3 + [1e5] * 3).reshape(36)
+        ci.append(i); cj.append(j); cT.append(T); cL.append(lam)
+    pb.c_i = np.asarray(ci, np.int32); pb.c_j = np.asarray(cj, np.int32)
+    pb.c_T = np.asarray(cT, np.float64).reshape(-1, 7); pb.c_Lambda = np.asarray(cL, np.float64).reshape(-1, 36)
+    pb.C = len(ci)
+    return pb
+
+
+def _check_against_oracle(ba, oracle, pb, iters=4):
+    ba.set_problem(pb)
+    it, st = ba.optimize(iters)
+    po_, ps_, sto = oracle.optimize(pb, iters)
+    assert it == sto["iterations"] and st["trials_iter"] == sto["trials_iter"]
+    np.testing.assert_allclose(st["chi2_iter"], sto["chi2_iter"], rtol=1e-7)
+    assert _rel(ba.poses(), po_) < POSE_RTOL and _rel(ba.points(), ps_) < POSE_RTOL
+    return st
+
+
+def test_long_tracks_use_the_generic_build_kernel(ba, oracle):
+    """Tracks of up to 14 frames (> 8): one-warp-per-landmark path of the fused kernel."""
+    pb = synth.make_window(30, 1500, seed=31, T=14)
+    st = _check_against_oracle(ba, oracle, pb)
+    assert st["max_track"] > 8
+
+
+def test_loop_closures_break_the_band(ba, oracle):
+    """Constraints between far-apart keyframes: no two-ended split, minimum-degree order with fill."""
+    pb = _add_constraints(synth.make_window(60, 3000, seed=32), [(0, 59), (59, 0), (5, 40), (12, 55), (20, 58)])
+    st = _check_against_oracle(ba, oracle, pb)
+    assert st["nnzb_L"] > st["nnzb_S"]          # fill-in happened
+
+
+def test_dense_reduced_system_uses_the_general_solver(ba, oracle):
+    """All-to-all pose constraints: every factor column is wider than the shared-memory ring share."""
+    P = 140
+    pb = synth.make_window(P, 1400, seed=33)
+    pairs = [(i, j) for i in range(P) for j in range(i + 1, P) if (i * 7 + j * 3) % 5 == 0 or j - i > 100]
+    pb = _add_constraints(pb, pairs)
+    st = _check_against_oracle(ba, oracle, pb, iters=3)
+    assert st["nnzb_L"] > 0.8 * P * (P + 1) / 2
+
+
+def test_two_ended_split_is_used_and_equals_the_chain(ba, oracle, svs):
+    import os
+    pb = synth.make_window(90, 4000, seed=34)
+    ba.set_problem(pb)
+    it, st = ba.optimize(3)
+    poses = ba.poses()
+    os.environ["SVS_SOLVE_CHAIN"] = "1"
+    try:
+        b2 = svs.BundleAdjuster()
+        b2.set_problem(pb)
+        it2, st2 = b2.optimize(3)
+        assert _rel(b2.poses(), poses) < 1e-9
+        np.testing.assert_allclose(st2["chi2_iter"], st["chi2_iter"], rtol=1e-10)
+        b2.close()
+    finally:
+        del os.environ["SVS_SOLVE_CHAIN"]
