@@ -447,6 +447,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   {
     int chunk = L / (148 * 16);
     chunk = chunk < 4 ? 4 : (chunk > 32 ? 32 : chunk);
+    if (const char* cs = getenv("SVS_BUILD_CHUNK")) chunk = atoi(cs);   // tuning knob
     if (getenv("SVS_BUILD_V1")) chunk = 0;   // A/B switch: everything through the one-warp-per-landmark kernel
     auto same_slots = [&](int la, int lb) {   // internal indices
       const int ka = lm_eptr[la + 1] - lm_eptr[la], kb = lm_eptr[lb + 1] - lm_eptr[lb];
