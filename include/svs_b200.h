@@ -300,6 +300,28 @@ int svs_match(svs_matcher *h, const double T_cur_from_actkey[7], const double T_
               const svs_match_point *pts, int n, int search_radius, int thr_mean, int thr_std,
               svs_match_result *out);
 
+/* ------------------------------------------------------------------ frame preprocessing ("next" row) */
+
+typedef struct svs_prep svs_prep;
+/* FrameGrabber::preprocessing (frame_grabber.cpp:287-336): uint8 pyramid (cv::buildPyramid), float
+ * image / 255, float pyramid (cv::gpu::pyrDown), x/y derivatives ([-1 0 1], replicated border,
+ * frame_grabber.cpp:104-115) for `nlevels` levels; everything stays on the device. */
+int svs_prep_create(int device, int w, int height, int nlevels, svs_prep **out);
+void svs_prep_destroy(svs_prep *h);
+const char *svs_prep_last_error(const svs_prep *h);
+int svs_prep_process(svs_prep *h, const unsigned char *img, int pitch);
+/* device pointers of one level (any output pointer may be NULL) */
+int svs_prep_level(svs_prep *h, int level, int *w, int *height, const unsigned char **u8, int *pitch_u8,
+                   const float **f32, const float **dx, const float **dy, int *stride_f32);
+int svs_prep_get_u8(svs_prep *h, int level, unsigned char *out);          /* tightly packed w*h */
+int svs_prep_get_f32(svs_prep *h, int level, int which, float *out);      /* which: 0 image, 1 dx, 2 dy */
+/* device-to-device hand-over into the consumers */
+int svs_dt_set_images_device(svs_dt *h, int level, const float *prev, const float *cur, const float *dx,
+                             const float *dy, int stride_floats);
+int svs_dt_swap_prev_cur(svs_dt *h);
+int svs_matcher_set_pyramid_device(svs_matcher *h, int which, const double T_me_from_w[7],
+                                   const unsigned char *const *d_pyr, const int *pitch);
+
 /* Library/device info: writes "name;sm;SMs;..." into buf. */
 int svs_device_info(char *buf, int buflen);
 

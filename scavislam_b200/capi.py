@@ -106,6 +106,9 @@ EXPORTS = [
     "svs_dt_chi2", "svs_dt_jacobian_reduction", "svs_dt_track",
     "svs_matcher_create", "svs_matcher_destroy", "svs_matcher_last_error", "svs_matcher_set_keyframe",
     "svs_matcher_set_current", "svs_matcher_set_features", "svs_match",
+    "svs_prep_create", "svs_prep_destroy", "svs_prep_last_error", "svs_prep_process", "svs_prep_level",
+    "svs_prep_get_u8", "svs_prep_get_f32", "svs_dt_set_images_device", "svs_dt_swap_prev_cur",
+    "svs_matcher_set_pyramid_device",
 ]
 
 
@@ -170,6 +173,19 @@ def lib():
     L.svs_dt_chi2.argtypes = [vp, C.c_int, c_dp, c_dp]
     L.svs_dt_jacobian_reduction.argtypes = [vp, C.c_int, c_dp, c_dp, c_dp, c_dp]
     L.svs_dt_track.argtypes = [vp, c_dp, C.POINTER(SvsDtStats)]
+    L.svs_prep_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.svs_prep_destroy.argtypes = [vp]
+    L.svs_prep_destroy.restype = None
+    L.svs_prep_last_error.argtypes = [vp]
+    L.svs_prep_last_error.restype = C.c_char_p
+    L.svs_prep_process.argtypes = [vp, c_up, C.c_int]
+    pvp = C.POINTER(C.c_void_p)
+    L.svs_prep_level.argtypes = [vp, C.c_int, c_ip, c_ip, pvp, c_ip, pvp, pvp, pvp, c_ip]
+    L.svs_prep_get_u8.argtypes = [vp, C.c_int, c_up]
+    L.svs_prep_get_f32.argtypes = [vp, C.c_int, C.c_int, c_fp]
+    L.svs_dt_set_images_device.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.svs_dt_swap_prev_cur.argtypes = [vp]
+    L.svs_matcher_set_pyramid_device.argtypes = [vp, C.c_int, c_dp, C.POINTER(C.c_void_p), c_ip]
     ucpp = C.POINTER(C.POINTER(C.c_ubyte))
     L.svs_matcher_create.argtypes = [C.c_int, C.c_int, C.POINTER(SvsMatchLevel), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.svs_matcher_destroy.argtypes = [vp]
@@ -459,6 +475,12 @@ class DenseTracker:
         w = self.w0 >> level
         self._ck(lib().svs_dt_set_images(self._h, level, *[self._fp(a) for a in arrs], w))
 
+    def set_images_device(self, level, prev=None, cur=None, dx=None, dy=None, stride=0):
+        self._ck(lib().svs_dt_set_images_device(self._h, level, prev, cur, dx, dy, stride))
+
+    def swap_prev_cur(self):
+        self._ck(lib().svs_dt_swap_prev_cur(self._h))
+
     def set_disparity(self, disp):
         d = np.ascontiguousarray(disp, np.float32)
         self._ck(lib().svs_dt_set_disparity(self._h, self._fp(d), d.shape[1], d.shape[1], d.shape[0]))
@@ -544,6 +566,13 @@ class GuidedMatcher:
                                                None if d is None else d.ctypes.data_as(C.POINTER(C.c_float)),
                                                0 if d is None else d.shape[1]))
 
+    def set_pyramid_device(self, which, ptrs, pitches, T_me_from_w=None):
+        """which = -1: current frame, >= 0: keyframe slot (needs T_me_from_w); device pointers per level."""
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        pitch = np.asarray(pitches, np.int32)
+        T = None if T_me_from_w is None else np.ascontiguousarray(T_me_from_w, np.float64)
+        self._ck(lib().svs_matcher_set_pyramid_device(self._h, which, None if T is None else _dp(T), arr, _ip(pitch)))
+
     def set_features(self, level, xy, content):
         xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
         content = np.ascontiguousarray(content, np.int32)
@@ -560,4 +589,56 @@ class GuidedMatcher:
                              out.ctypes.data_as(C.POINTER(SvsMatchResult)))
         if rc < 0:
             self._ck(rc)
+        return out
+
+
+class FramePreprocessor:
+    """FrameGrabber::preprocessing (reference frame_grabber.cpp:287-336) on the device: uint8 and
+    float pyramids and the x/y derivatives of one frame; outputs stay on the GPU."""
+
+    def __init__(self, w, h, nlevels=3, device=-1):
+        self._h = C.c_void_p()
+        rc = lib().svs_prep_create(device, w, h, nlevels, C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_prep_create failed (no CUDA device? there is no CPU fallback)")
+        self.nlevels = nlevels
+
+    def close(self):
+        if self._h:
+            lib().svs_prep_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SvsError(rc, lib().svs_prep_last_error(self._h).decode())
+
+    def process(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        self._ck(lib().svs_prep_process(self._h, img.ctypes.data_as(c_up), img.strides[0]))
+
+    def level(self, l):
+        """dict(w, h, u8, pitch_u8, f32, dx, dy, stride_f32) with raw device pointers."""
+        w, h, p8, s32 = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        u8, f32, dx, dy = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(lib().svs_prep_level(self._h, l, C.byref(w), C.byref(h), C.byref(u8), C.byref(p8), C.byref(f32),
+                                      C.byref(dx), C.byref(dy), C.byref(s32)))
+        return dict(w=w.value, h=h.value, u8=u8.value, pitch_u8=p8.value, f32=f32.value, dx=dx.value, dy=dy.value,
+                    stride_f32=s32.value)
+
+    def get_u8(self, l):
+        lv = self.level(l)
+        out = np.zeros((lv["h"], lv["w"]), np.uint8)
+        self._ck(lib().svs_prep_get_u8(self._h, l, out.ctypes.data_as(c_up)))
+        return out
+
+    def get_f32(self, l, which=0):
+        lv = self.level(l)
+        out = np.zeros((lv["h"], lv["w"]), np.float32)
+        self._ck(lib().svs_prep_get_f32(self._h, l, which, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out

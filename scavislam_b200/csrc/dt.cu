@@ -413,6 +413,30 @@ int svs_dt_set_images(svs_dt* h, int level, const float* prev, const float* cur,
   return SVS_OK;
 }
 
+// same planes already on the device (e.g. svs_prep_level pointers): device-to-device copies
+int svs_dt_set_images_device(svs_dt* h, int level, const float* prev, const float* cur, const float* dx, const float* dy,
+                             int stride_floats) {
+  if (!h || level < 0 || level >= h->nlevels || stride_floats < h->lv[level].w) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const DtLevel& L = h->lv[level];
+  const float* src[4] = {prev, cur, dx, dy};
+  for (int k = 0; k < 4; ++k)
+    if (src[k])
+      DCK(cudaMemcpy2DAsync(h->img[level][k], sizeof(float) * L.stride, src[k], sizeof(float) * stride_floats,
+                            sizeof(float) * L.w, L.h, cudaMemcpyDeviceToDevice, h->stream));
+  return SVS_OK;
+}
+
+// the current images become the previous ones (frame hand-over of FrameData::nextFrame)
+int svs_dt_swap_prev_cur(svs_dt* h) {
+  if (!h) return SVS_ERR_INVALID;
+  for (int l = 0; l < h->nlevels; ++l) {
+    std::swap(h->img[l][0], h->img[l][1]);
+    h->lv[l].prev = h->img[l][0]; h->lv[l].cur = h->img[l][1];
+  }
+  return SVS_OK;
+}
+
 int svs_dt_set_disparity(svs_dt* h, const float* disp, int stride_floats, int w, int hgt) {
   if (!h || !disp || w <= 0 || hgt <= 0 || w > h->w0 || hgt > h->h0 || stride_floats < w) return SVS_ERR_INVALID;
   cudaSetDevice(h->device);

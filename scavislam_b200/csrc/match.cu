@@ -371,6 +371,24 @@ int svs_matcher_set_current(svs_matcher * h, const unsigned char* const* pyr, co
   return SVS_OK;
 }
 
+// Same as set_keyframe / set_current, but the pyramid already lives on this device (svs_prep_level):
+// a device-to-device copy into the handle's own buffers, so a keyframe outlives the preprocessor's frame.
+int svs_matcher_set_pyramid_device(svs_matcher * h, int which, const double T_me_from_w[7], const unsigned char* const* d_pyr,
+                                   const int* pitch) {
+  if (!h || which < -1 || which >= h->max_kf || !d_pyr || !pitch || (which >= 0 && !T_me_from_w)) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  for (int l = 0; l < h->nlevels; ++l) {
+    unsigned char* dst = which < 0 ? h->d_cur[l] : h->d_kfimg[(size_t)which * h->nlevels + l];
+    MCK(cudaMemcpy2DAsync(dst, h->pitch[l], d_pyr[l], pitch[l], h->lv[l].w, h->lv[l].h, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (which >= 0) {
+    memcpy(h->h_kf[which].T, T_me_from_w, sizeof(double) * 7);
+    MCK(cudaMemcpyAsync(h->d_kf + which, &h->h_kf[which], sizeof(KfDev), cudaMemcpyHostToDevice, h->stream));
+  }
+  MCK(cudaStreamSynchronize(h->stream));
+  return SVS_OK;
+}
+
 int svs_matcher_set_features(svs_matcher * h, int level, const int* xy, const int* content, int n) {
   if (!h || level < 0 || level >= h->nlevels || n < 0 || n > h->max_kp || (n && (!xy || !content))) return SVS_ERR_INVALID;
   for (int i = 0; i < n; ++i)
