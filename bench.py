@@ -77,7 +77,8 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=2)
+        if self.is_alive():
+            self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
@@ -158,7 +159,8 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local)
-    sampler.start()
+    if not os.environ.get("SVS_BENCH_NO_SAMPLER"):      # developer knob
+        sampler.start()
     barrier()
     wall0 = time.perf_counter()
     ms = 0.0
@@ -259,8 +261,8 @@ def run_ours(args):
 def frontend_bench(device, n_frames=12):
     """Second half of the BASELINE metric: front-end frames/sec at 640x480 (config C3) --
     grid FAST (2 levels, adaptive) + dense tracking (3 levels) + dense point cloud + guided
-    matching against the previous frame, through the C ABI.  `fps_e2e` takes every input from host
-    memory each frame; `fps_resident` re-runs the kernels on the data already on the device."""
+    matching against the previous frame, through the C ABI.  `fps_e2e` takes the raw left image and the disparity maps from
+    host memory each frame and includes the pyramid/gradient preprocessing (svs_prep_*); `fps_resident` re-runs the kernels on the data already on the device."""
     import numpy as np
     import torch
     from oracle import pyoracle as po
@@ -270,9 +272,9 @@ def frontend_bench(device, n_frames=12):
     I7 = np.array([0, 0, 0, 1, 0, 0, 0.0])
     lv2 = [(640 >> l, 480 >> l, cams[l][0], cams[l][1], cams[l][2]) for l in range(2)]
     frames = []
-    for f in seq:                      # input preparation (pyramids, gradients): a "next" row, not timed
+    for f in seq:                      # host pyramids/gradients (OpenCV) feed the CPU baseline only
         fp = fi.float_pyramid(f["img"])
-        frames.append(dict(u8=fi.uint8_pyramid(f["img"], 2), f32=fp, grad=[fi.gradients(x) for x in fp], disp=f["disp"]))
+        frames.append(dict(img=f["img"], u8=fi.uint8_pyramid(f["img"], 2), f32=fp, grad=[fi.gradients(x) for x in fp], disp=f["disp"]))
     grids = [capi.FastGrid(640, 480, 222, 74, 25, 3, 3, device=device), capi.FastGrid(320, 240, 55, 18, 25, 3, 3, device=device)]
     dt = capi.DenseTracker(640, 480, 3, device=device)
     for l in range(3):
@@ -289,39 +291,66 @@ def frontend_bench(device, n_frames=12):
         p["anchor_obs_pyr"] = kxy
         return p
 
+    pps = [capi.FramePreprocessor(640, 480, 3, device=device) for _ in range(2)]
+    state = {"k": 0}
+
     def one_frame(prev, cur, prev_xy, upload=True):
+        """upload=True: the per-frame host inputs are the raw left image and the disparity maps; pyramids
+        and gradients are made on the device (svs_prep_*) and handed over by pointer."""
+        if upload:
+            state["k"] ^= 1
+            pp, pq = pps[state["k"]], pps[state["k"] ^ 1]       # pp: current frame, pq: previous frame
+            pp.process(cur["img"])
+            lv = [pp.level(l) for l in range(3)]
         feats = []
         for l in range(2):
             if upload:
-                grids[l].set_image(cur["u8"][l])
+                grids[l].set_image_device(lv[l]["u8"], lv[l]["pitch_u8"], lv[l]["w"], lv[l]["h"])
             xy, off = grids[l].detect_adaptively(6)
             feats.append((xy, np.concatenate([np.arange(off[c + 1] - off[c]) for c in range(9)]).astype(np.int32)))
         if upload:
             dt.set_disparity(prev["disp"])
+            dt.swap_prev_cur()                                   # FrameData::nextFrame
             for l in range(3):
-                dt.set_images(l, prev["f32"][l], cur["f32"][l], cur["grad"][l][0], cur["grad"][l][1])
+                dt.set_images_device(l, None, lv[l]["f32"], lv[l]["dx"], lv[l]["dy"], lv[l]["stride_f32"])
         dt.compute_point_cloud(I7, cams)
         T, st = dt.track(I7)
         if upload:
-            mt.set_keyframe(0, I7, prev["u8"])
-            mt.set_current(cur["u8"], cur["disp"])
+            lq = [pq.level(l) for l in range(2)]
+            mt.set_pyramid_device(0, [x["u8"] for x in lq], [x["pitch_u8"] for x in lq], I7)
+            mt.set_pyramid_device(-1, [x["u8"] for x in lv[:2]], [x["pitch_u8"] for x in lv[:2]])
+            mt.set_current_disparity(cur["disp"])
             for l in range(2):
                 mt.set_features(l, *feats[l])
         res = mt.match(T, I7, make_points(prev, prev_xy), 4, 22, 10)
         return feats[0][0], T, int(res["matched"].sum()), st
 
+    order = [0, 1, 2, 3, 2, 1]                 # ping-pong so that every frame follows its neighbour
+    pps[0].process(frames[0]["img"])            # prime: frame 0 is "previous"
+    for l in range(3):
+        lv0 = pps[0].level(l)
+        dt.set_images_device(l, lv0["f32"], lv0["f32"], lv0["dx"], lv0["dy"], lv0["stride_f32"])
     prev_xy = one_frame(frames[0], frames[1], np.zeros((0, 2), np.int32))[0]
+    for i in range(2, 6):                       # warm-up once around
+        prev_xy = one_frame(frames[order[i - 1]], frames[order[i]], prev_xy)[0]
+    prev_xy = one_frame(frames[1], frames[0], prev_xy)[0]
     torch.cuda.synchronize()
+    e2e, matched, frame_ms = None, 0, []
+    for rep in range(3):                        # best of 3 passes (a single host hiccup would halve a 20 ms pass)
+        t0 = time.perf_counter()
+        m_rep = 0
+        for i in range(n_frames):
+            a, b = frames[order[i % 6]], frames[order[(i + 1) % 6]]
+            tf = time.perf_counter()
+            prev_xy, T, m, st = one_frame(a, b, prev_xy)
+            frame_ms.append((time.perf_counter() - tf) * 1e3)
+            m_rep += m
+        t_rep = time.perf_counter() - t0
+        if e2e is None or t_rep < e2e:
+            e2e, matched = t_rep, m_rep
     t0 = time.perf_counter()
-    matched = 0
     for i in range(n_frames):
-        a, b = frames[i % 3], frames[i % 3 + 1]
-        prev_xy, T, m, st = one_frame(a, b, prev_xy)
-        matched += m
-    e2e = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    for i in range(n_frames):
-        one_frame(frames[2], frames[3], prev_xy, upload=False)
+        one_frame(a, b, prev_xy, upload=False)
     res_s = time.perf_counter() - t0
     # CPU oracle on the same frames (1 thread), bounded sample
     c0 = time.perf_counter()
@@ -335,14 +364,16 @@ def frontend_bench(device, n_frames=12):
                    py=cams[l][2], cloud=po.dt_point_cloud(I7, cams[l], a["disp"], l, 640 >> l, 480 >> l)) for l in range(3)]
         po.dt_track(lv, I7)
     cpu_s = time.perf_counter() - c0
-    out = {"workload": "C3: 640x480 synthetic stereo stream; FAST grid (2 levels, 6 trials) + dense tracking (3 levels) "
-                       "+ point cloud + guided matching (radius 4)",
+    out = {"workload": "C3: 640x480 synthetic stereo stream; preprocessing (pyramids, gradients) + FAST grid (2 levels, "
+                       "6 trials) + dense tracking (3 levels) + point cloud + guided matching (radius 4)",
            "fps_e2e": n_frames / e2e, "fps_resident": n_frames / res_s, "frames": n_frames,
+           "frame_ms_median": float(np.median(frame_ms)), "frame_ms_max": float(np.max(frame_ms)),
+           "timing": "wall clock, best of 3 passes of `frames` frames",
            "matched_per_frame": matched / n_frames, "dense_tracking_passes": st["passes"],
            "dense_tracking_ms": st["ms_total"],
            "cpu_baseline_fps": ncpu / cpu_s, "cpu_baseline": "oracle FAST + dense tracking (GPU semantics), 1 thread, "
                                                                f"{ncpu} frames (matcher excluded: <5 ms)"}
-    for g in grids:
+    for g in grids + pps:
         g.close()
     dt.close()
     mt.close()

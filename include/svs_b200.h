@@ -289,7 +289,7 @@ const char *svs_matcher_last_error(const svs_matcher *h);
 /* keyframe_map[id].pyr + vertex_map[id].T_me_from_w for one anchor keyframe (uint8 pyramid, host) */
 int svs_matcher_set_keyframe(svs_matcher *h, int slot, const double T_me_from_w[7], const unsigned char *const *pyr,
                            const int *pitch);
-/* cur_frame.pyr + cur_frame.disp (level-0 float disparity, may be NULL to keep) */
+/* cur_frame.pyr + cur_frame.disp (level-0 float disparity); either may be NULL to keep what is loaded */
 int svs_matcher_set_current(svs_matcher *h, const unsigned char *const *pyr, const int *pitch, const float *disp,
                           int disp_pitch_floats);
 /* feature_tree.at(level): the FAST corners (x, y) and their quadtree content (index within the cell) */

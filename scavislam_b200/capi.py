@@ -566,6 +566,10 @@ class GuidedMatcher:
                                                None if d is None else d.ctypes.data_as(C.POINTER(C.c_float)),
                                                0 if d is None else d.shape[1]))
 
+    def set_current_disparity(self, disp):
+        d = np.ascontiguousarray(disp, np.float32)
+        self._ck(lib().svs_matcher_set_current(self._h, None, None, d.ctypes.data_as(C.POINTER(C.c_float)), d.shape[1]))
+
     def set_pyramid_device(self, which, ptrs, pitches, T_me_from_w=None):
         """which = -1: current frame, >= 0: keyframe slot (needs T_me_from_w); device pointers per level."""
         arr = (C.c_void_p * len(ptrs))(*ptrs)

@@ -360,9 +360,9 @@ int svs_matcher_set_keyframe(svs_matcher * h, int slot, const double T_me_from_w
 
 int svs_matcher_set_current(svs_matcher * h, const unsigned char* const* pyr, const int* pitch, const float* disp,
                           int disp_pitch_floats) {
-  if (!h || !pyr || !pitch) return SVS_ERR_INVALID;
+  if (!h || (pyr && !pitch) || (!pyr && !disp)) return SVS_ERR_INVALID;
   cudaSetDevice(h->device);
-  for (int l = 0; l < h->nlevels; ++l)
+  for (int l = 0; pyr && l < h->nlevels; ++l)
     MCK(cudaMemcpy2DAsync(h->d_cur[l], h->pitch[l], pyr[l], pitch[l], h->lv[l].w, h->lv[l].h, cudaMemcpyHostToDevice, h->stream));
   if (disp)
     MCK(cudaMemcpy2DAsync(h->d_disp, sizeof(float) * h->disp_pitch, disp, sizeof(float) * disp_pitch_floats,

@@ -76,7 +76,7 @@ def test_device_handover_feeds_tracker_fast_and_matcher(svs, oracle):
     m = svs.GuidedMatcher(lv2)
     m.set_pyramid_device(0, [pa.level(l)["u8"] for l in range(2)], [pa.level(l)["pitch_u8"] for l in range(2)], I7)
     m.set_pyramid_device(-1, [pb.level(l)["u8"] for l in range(2)], [pb.level(l)["pitch_u8"] for l in range(2)])
-    m.set_current([pb.get_u8(0), pb.get_u8(1)], seq[1]["disp"])   # disparity still comes from the host
+    m.set_current_disparity(seq[1]["disp"])   # disparity still comes from the host
     content = np.concatenate([np.arange(off[c + 1] - off[c]) for c in range(9)]).astype(np.int32)
     m.set_features(0, xy, content)
     m.set_features(1, np.zeros((0, 2), np.int32), np.zeros(0, np.int32))
