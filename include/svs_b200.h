@@ -28,6 +28,7 @@ extern "C" {
 #define SVS_ERR_UNSUPPORTED (-3)  /* structurally valid input this build cannot take */
 #define SVS_ERR_STATE (-4)        /* call order (e.g. optimize before set_problem) */
 #define SVS_ERR_NOGPU (-5)        /* no CUDA device: there is NO CPU fallback */
+#define SVS_ERR_NUMERIC (-6)      /* NaN residual (the reference throws std::runtime_error("Res is NaN!")) */
 
 /* ------------------------------------------------------------------ BA */
 
@@ -321,6 +322,45 @@ int svs_dt_set_images_device(svs_dt *h, int level, const float *prev, const floa
 int svs_dt_swap_prev_cur(svs_dt *h);
 int svs_matcher_set_pyramid_device(svs_matcher *h, int which, const double T_me_from_w[7],
                                    const unsigned char *const *d_pyr, const int *pitch);
+
+/* ------------------------------------------------------------------ motion-only pose refinement
+ * ("next" row).  BA_SE3_XYZ_STEREO::calcFastMotionOnly (pose_optimizer.h:135-298) with
+ * SE3XYZ_STEREO (transformations.h:414-460): 6-DoF Levenberg-Marquardt over fixed 3-D points with the
+ * pseudo-Huber reweighting; callers stereo_frontend.cpp:1058, backend.cpp:754-779. */
+
+typedef struct svs_pose svs_pose;
+
+/* PoseOptimizerParams (pose_optimizer.h:38-58); SVS_POSE_PARAMS_DEFAULT mirrors its constructor */
+typedef struct {
+  int robust_kernel;
+  double kernel_param;
+  int num_iter;
+  double initial_mu;   /* -1: tau * max diag(J^T J) */
+  double tau;
+} svs_pose_params;
+#define SVS_POSE_PARAMS_DEFAULT {1, 1.0, 50, -1.0, 0.00001}
+
+/* OptimizerStatistics (pose_optimizer.h:60-98) + counters */
+typedef struct {
+  double initial_chi2, chi2, max_err;
+  int num_obs;
+  int iterations;   /* accepted steps */
+  int trials;       /* 6x6 solves */
+  float ms;         /* device time of the LM kernel */
+} svs_pose_stats;
+
+int svs_pose_create(int device, int max_obs, svs_pose **out);
+void svs_pose_destroy(svs_pose *h);
+const char *svs_pose_last_error(const svs_pose *h);
+/* obs_list as (point_id, obs = (u, v, u_right)) arrays, point_list as xyz[3 * npoints]; T_frame in/out.
+ * Returns SVS_OK or a negative SVS_ERR_* (SVS_ERR_NUMERIC where the reference throws). */
+int svs_calcFastMotionOnly(svs_pose *h, int n, const int *obs_point_id, const double *obs_uvu, int npoints,
+                           const double *point_xyz, const svs_cam *cam, const svs_pose_params *params,
+                           double T_frame[7], svs_pose_stats *stats);
+/* Same, on the TrackData of the last svs_match(m, ...) where it lies on the device (matched entries'
+ * obs / xyz_actkey): no host trip between matching and pose refinement. */
+int svs_calcFastMotionOnly_matched(svs_pose *h, svs_matcher *m, const svs_cam *cam, const svs_pose_params *params,
+                                   double T_frame[7], svs_pose_stats *stats);
 
 /* Library/device info: writes "name;sm;SMs;..." into buf. */
 int svs_device_info(char *buf, int buflen);

@@ -16,7 +16,9 @@
 #ifndef SVS_B200_HPP
 #define SVS_B200_HPP
 
+#include <cmath>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -228,6 +230,59 @@ class GuidedMatcher {
 
  private:
   svs_matcher* h_ = nullptr;
+  bool ok_ = false;
+};
+
+// ScaViSLAM::PoseOptimizerParams (pose_optimizer.h:38-58)
+struct PoseOptimizerParams : svs_pose_params {
+  PoseOptimizerParams(bool robust_kernel_ = true, double kernel_param_ = 1, int num_iter_ = 50, double initial_mu_ = -1) {
+    robust_kernel = robust_kernel_; kernel_param = kernel_param_; num_iter = num_iter_; initial_mu = initial_mu_;
+    tau = 0.00001;
+  }
+};
+
+// ScaViSLAM::OptimizerStatistics (pose_optimizer.h:60-98)
+struct OptimizerStatistics : svs_pose_stats {
+  double rmse() const { return num_obs > 0 ? std::sqrt(chi2 / num_obs) : 0.; }
+};
+
+// ScaViSLAM::BA_SE3_XYZ_STEREO = PoseOptimizer<SE3,6,IdObs<3>,3> (pose_optimizer.h:495)
+class BA_SE3_XYZ_STEREO {
+ public:
+  explicit BA_SE3_XYZ_STEREO(int max_obs = 16384) { ok_ = svs_pose_create(-1, max_obs, &h_) == SVS_OK; }
+  ~BA_SE3_XYZ_STEREO() { if (h_) svs_pose_destroy(h_); }
+  BA_SE3_XYZ_STEREO(const BA_SE3_XYZ_STEREO&) = delete;
+  BA_SE3_XYZ_STEREO& operator=(const BA_SE3_XYZ_STEREO&) = delete;
+  bool valid() const { return ok_; }
+  // calcFastMotionOnly(obs_list, prediction(cam), ba_params, &frame, &point_list); throws where the reference does
+  OptimizerStatistics calcFastMotionOnly(const std::vector<int>& obs_point_id, const std::vector<double>& obs_uvu,
+                                         const svs_cam& cam, const PoseOptimizerParams& ba_params, SE3d* frame,
+                                         const std::vector<double>& point_list_xyz) {
+    OptimizerStatistics st{};
+    double T[7] = {frame->q[0], frame->q[1], frame->q[2], frame->q[3], frame->t[0], frame->t[1], frame->t[2]};
+    const int rc = ok_ ? svs_calcFastMotionOnly(h_, (int)obs_point_id.size(), obs_point_id.data(), obs_uvu.data(),
+                                                (int)(point_list_xyz.size() / 3), point_list_xyz.data(), &cam, &ba_params,
+                                                T, &st)
+                       : SVS_ERR_NOGPU;
+    if (rc != SVS_OK) throw std::runtime_error(ok_ ? svs_pose_last_error(h_) : "no CUDA device");
+    for (int k = 0; k < 4; ++k) frame->q[k] = T[k];
+    for (int k = 0; k < 3; ++k) frame->t[k] = T[4 + k];
+    return st;
+  }
+  // the same on the TrackData the matcher left on the device
+  OptimizerStatistics calcFastMotionOnly(GuidedMatcher& matcher, const svs_cam& cam, const PoseOptimizerParams& ba_params,
+                                         SE3d* frame) {
+    OptimizerStatistics st{};
+    double T[7] = {frame->q[0], frame->q[1], frame->q[2], frame->q[3], frame->t[0], frame->t[1], frame->t[2]};
+    const int rc = ok_ ? svs_calcFastMotionOnly_matched(h_, matcher.handle(), &cam, &ba_params, T, &st) : SVS_ERR_NOGPU;
+    if (rc != SVS_OK) throw std::runtime_error(ok_ ? svs_pose_last_error(h_) : "no CUDA device");
+    for (int k = 0; k < 4; ++k) frame->q[k] = T[k];
+    for (int k = 0; k < 3; ++k) frame->t[k] = T[4 + k];
+    return st;
+  }
+
+ private:
+  svs_pose* h_ = nullptr;
   bool ok_ = false;
 };
 

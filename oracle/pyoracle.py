@@ -414,3 +414,43 @@ def match(levels, cur_pyr, disp, trees, keyframes, T_cur_from_actkey, T_actkey_f
     lib().omatch_match(C.byref(fr), kfs, len(keyframes), _dp(Ta), _dp(Tb), pts.ctypes.data, len(pts),
                        int(search_radius), int(thr_mean), int(thr_std), out.ctypes.data)
     return out
+
+
+# ---------------------------------------------------------------- motion-only LM (pose_oracle.c)
+class OPOStats(C.Structure):
+    _fields_ = [("initial_chi2", C.c_double), ("chi2", C.c_double), ("max_err", C.c_double), ("num_obs", C.c_int),
+                ("iterations", C.c_int), ("trials", C.c_int), ("nan_error", C.c_int)]
+
+
+def pose_map(cam, T, xyz):
+    o = f64(3)
+    L = lib(); L.opo_map.argtypes = [c_dp] * 4; L.opo_map.restype = None
+    L.opo_map(_dp(np.ascontiguousarray(cam, np.float64)), _dp(np.ascontiguousarray(T, np.float64)),
+              _dp(np.ascontiguousarray(xyz, np.float64)), _dp(o))
+    return o
+
+
+def pose_frame_jac(cam, T, xyz):
+    o = f64(3, 6)
+    L = lib(); L.opo_frame_jac.argtypes = [c_dp] * 4; L.opo_frame_jac.restype = None
+    L.opo_frame_jac(_dp(np.ascontiguousarray(cam, np.float64)), _dp(np.ascontiguousarray(T, np.float64)),
+                    _dp(np.ascontiguousarray(xyz, np.float64)), _dp(o))
+    return o
+
+
+def calc_fast_motion_only(obs_point_id, obs_uvu, point_xyz, cam, T_frame, robust_kernel=True, kernel_param=1.0,
+                          num_iter=50, initial_mu=-1.0, tau=0.00001):
+    L = lib()
+    L.opo_calc_fast_motion_only.argtypes = [C.c_int, C.POINTER(C.c_int), c_dp, c_dp, c_dp, C.c_int, C.c_double, C.c_int,
+                                            C.c_double, C.c_double, c_dp, C.POINTER(OPOStats)]
+    L.opo_calc_fast_motion_only.restype = None
+    pid = np.ascontiguousarray(obs_point_id, np.int32)
+    obs = np.ascontiguousarray(obs_uvu, np.float64)
+    xyz = np.ascontiguousarray(point_xyz, np.float64)
+    T = np.array(T_frame, np.float64).copy()
+    st = OPOStats()
+    L.opo_calc_fast_motion_only(len(pid), pid.ctypes.data_as(C.POINTER(C.c_int)), _dp(obs), _dp(xyz),
+                                _dp(np.ascontiguousarray(cam, np.float64)), int(robust_kernel), float(kernel_param),
+                                int(num_iter), float(initial_mu), float(tau), _dp(T), C.byref(st))
+    return T, dict(initial_chi2=st.initial_chi2, chi2=st.chi2, max_err=st.max_err, num_obs=st.num_obs,
+                   iterations=st.iterations, trials=st.trials, nan_error=st.nan_error)

@@ -71,6 +71,16 @@ class SvsDtStats(C.Structure):
                 ("launches", C.c_int), ("ms_total", C.c_float)]
 
 
+class SvsPoseParams(C.Structure):
+    _fields_ = [("robust_kernel", C.c_int), ("kernel_param", C.c_double), ("num_iter", C.c_int),
+                ("initial_mu", C.c_double), ("tau", C.c_double)]
+
+
+class SvsPoseStats(C.Structure):
+    _fields_ = [("initial_chi2", C.c_double), ("chi2", C.c_double), ("max_err", C.c_double), ("num_obs", C.c_int),
+                ("iterations", C.c_int), ("trials", C.c_int), ("ms", C.c_float)]
+
+
 class SvsMatchLevel(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("f", C.c_double), ("px", C.c_double), ("py", C.c_double)]
 
@@ -109,6 +119,8 @@ EXPORTS = [
     "svs_prep_create", "svs_prep_destroy", "svs_prep_last_error", "svs_prep_process", "svs_prep_level",
     "svs_prep_get_u8", "svs_prep_get_f32", "svs_dt_set_images_device", "svs_dt_swap_prev_cur",
     "svs_matcher_set_pyramid_device",
+    "svs_pose_create", "svs_pose_destroy", "svs_pose_last_error", "svs_calcFastMotionOnly",
+    "svs_calcFastMotionOnly_matched",
 ]
 
 
@@ -186,6 +198,15 @@ def lib():
     L.svs_dt_set_images_device.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.svs_dt_swap_prev_cur.argtypes = [vp]
     L.svs_matcher_set_pyramid_device.argtypes = [vp, C.c_int, c_dp, C.POINTER(C.c_void_p), c_ip]
+    L.svs_pose_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.svs_pose_destroy.argtypes = [vp]
+    L.svs_pose_destroy.restype = None
+    L.svs_pose_last_error.argtypes = [vp]
+    L.svs_pose_last_error.restype = C.c_char_p
+    L.svs_calcFastMotionOnly.argtypes = [vp, C.c_int, c_ip, c_dp, C.c_int, c_dp, C.POINTER(SvsCam),
+                                         C.POINTER(SvsPoseParams), c_dp, C.POINTER(SvsPoseStats)]
+    L.svs_calcFastMotionOnly_matched.argtypes = [vp, vp, C.POINTER(SvsCam), C.POINTER(SvsPoseParams), c_dp,
+                                                 C.POINTER(SvsPoseStats)]
     ucpp = C.POINTER(C.POINTER(C.c_ubyte))
     L.svs_matcher_create.argtypes = [C.c_int, C.c_int, C.POINTER(SvsMatchLevel), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.svs_matcher_destroy.argtypes = [vp]
@@ -646,3 +667,60 @@ class FramePreprocessor:
         out = np.zeros((lv["h"], lv["w"]), np.float32)
         self._ck(lib().svs_prep_get_f32(self._h, l, which, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
+
+
+class PoseOptimizer:
+    """BA_SE3_XYZ_STEREO (reference pose_optimizer.h:495): motion-only LM, whole loop in one kernel."""
+
+    def __init__(self, max_obs=16384, device=-1):
+        self._h = C.c_void_p()
+        rc = lib().svs_pose_create(device, max_obs, C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_pose_create failed (no CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().svs_pose_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SvsError(rc, lib().svs_pose_last_error(self._h).decode())
+
+    @staticmethod
+    def _params(robust_kernel, kernel_param, num_iter, initial_mu):
+        return SvsPoseParams(int(robust_kernel), float(kernel_param), int(num_iter), float(initial_mu), 0.00001)
+
+    @staticmethod
+    def _stats(st):
+        return dict(initial_chi2=st.initial_chi2, chi2=st.chi2, max_err=st.max_err, num_obs=st.num_obs,
+                    iterations=st.iterations, trials=st.trials, ms=st.ms)
+
+    def calc_fast_motion_only(self, obs_point_id, obs_uvu, point_xyz, cam, T_frame, robust_kernel=True,
+                              kernel_param=1.0, num_iter=50, initial_mu=-1.0):
+        """Returns (T_frame_new, stats); cam = (f, px, py, baseline)."""
+        pid = np.ascontiguousarray(obs_point_id, np.int32)
+        obs = np.ascontiguousarray(obs_uvu, np.float64).reshape(-1, 3)
+        xyz = np.ascontiguousarray(point_xyz, np.float64).reshape(-1, 3)
+        T = np.array(T_frame, np.float64).copy()
+        c = SvsCam(*[float(x) for x in cam])
+        p = self._params(robust_kernel, kernel_param, num_iter, initial_mu)
+        st = SvsPoseStats()
+        self._ck(lib().svs_calcFastMotionOnly(self._h, len(pid), _ip(pid), _dp(obs), len(xyz), _dp(xyz), C.byref(c),
+                                              C.byref(p), _dp(T), C.byref(st)))
+        return T, self._stats(st)
+
+    def calc_fast_motion_only_matched(self, matcher, cam, T_frame, robust_kernel=True, kernel_param=1.0, num_iter=50,
+                                      initial_mu=-1.0):
+        T = np.array(T_frame, np.float64).copy()
+        c = SvsCam(*[float(x) for x in cam])
+        p = self._params(robust_kernel, kernel_param, num_iter, initial_mu)
+        st = SvsPoseStats()
+        self._ck(lib().svs_calcFastMotionOnly_matched(self._h, matcher._h, C.byref(c), C.byref(p), _dp(T), C.byref(st)))
+        return T, self._stats(st)

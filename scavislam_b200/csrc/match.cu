@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/svs_b200.h"
+#include "internal.cuh"
 #include "se3_dev.cuh"
 
 namespace {
@@ -269,6 +270,7 @@ struct svs_matcher {
   int nkp[kMaxLv] = {}, bw[kMaxLv] = {}, bh[kMaxLv] = {};
   svs_match_point* d_pts = nullptr;
   svs_match_result* d_res = nullptr;
+  int last_n = 0;   // candidate points of the last svs_match (results stay in d_res)
 };
 
 #define MCK(call)                                                       \
@@ -279,6 +281,12 @@ struct svs_matcher {
       return SVS_ERR_CUDA;                                              \
     }                                                                   \
   } while (0)
+
+namespace svs {
+void matcher_device_results(svs_matcher* m, const svs_match_result** d_res, int* n, int* device) {
+  *d_res = m->d_res; *n = m->last_n; *device = m->device;
+}
+}  // namespace svs
 
 extern "C" {
 
@@ -418,6 +426,7 @@ int svs_match(svs_matcher * h, const double T_cur_from_actkey[7], const double T
               const svs_match_point* pts, int n, int search_radius, int thr_mean, int thr_std, svs_match_result* out) {
   if (!h || !T_cur_from_actkey || !T_actkey_from_w || n < 0 || n > h->max_pts || (n && (!pts || !out)) || search_radius < 0)
     return SVS_ERR_INVALID;
+  h->last_n = 0;
   if (n == 0) return 0;
   cudaSetDevice(h->device);
   MatchArgs a;
@@ -441,6 +450,7 @@ int svs_match(svs_matcher * h, const double T_cur_from_actkey[7], const double T
   MCK(cudaGetLastError());
   MCK(cudaMemcpyAsync(out, h->d_res, sizeof(svs_match_result) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   MCK(cudaStreamSynchronize(h->stream));
+  h->last_n = n;
   int nm = 0;
   for (int i = 0; i < n; ++i) nm += out[i].matched;
   return nm;

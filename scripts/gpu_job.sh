@@ -1,4 +1,3 @@
 #!/bin/bash
 cd /root/repo
-python bench.py --steps 5 --warmup 3 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('sampler', d['frontend']['fps_e2e'], d['frontend']['fps_resident'], d['e2e']['value'])"
-SVS_BENCH_NO_SAMPLER=1 python bench.py --steps 5 --warmup 3 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('nosampler', d['frontend']['fps_e2e'], d['frontend']['fps_resident'], d['e2e']['value'])"
+timeout 300 python -m pytest tests/test_pose_gpu.py -x -q 2>&1 | tail -30
