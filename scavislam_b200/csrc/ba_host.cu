@@ -562,7 +562,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     AL(S, 36 * (size_t)sy.nblk); AL(bp, 6 * (size_t)P); AL(bc, 6 * (size_t)P); AL(x, 6 * (size_t)P);
     AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
     AL(ctl, 1);
-    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 24); AL(totals, 4);
+    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 48); AL(totals, 4);
 #undef AL
   };
   h->measuring = true;
@@ -697,8 +697,10 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     st->launches = launches;
   }
   if (getenv("SVS_SOLVE_TIMING")) {
-    long long dbg[24];
+    long long dbg[48];
     cudaMemcpy(dbg, d.dbg, sizeof dbg, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "profile (SVS_SOLVE_PROFILE builds): panel diag-upd %lld chol %lld bar_panel %lld scale %lld bar_all %lld | "
+            "update work %lld bar_all %lld\n", dbg[24], dbg[25], dbg[26], dbg[27], dbg[28], dbg[37], dbg[38]);
     fprintf(stderr, "k_solve cycles since setup (branches done, +barrier, separators done, back seps, back branches, end):\n");
     for (int g = 0; g < 4; ++g) {
       fprintf(stderr, "  team %d:", g);

@@ -69,7 +69,7 @@ __device__ __forceinline__ bool chol6_regs(const double* __restrict__ A, double 
   return ok;
 }
 
-constexpr int kUpdPf = 2;         // update-list entries per update thread prefetched one column ahead
+constexpr int kUpdStage = 128;    // update-list entries of a column staged in shared memory one column ahead
 constexpr int kMaxTeams = 4;      // independent branches of the elimination tree factored concurrently
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -111,7 +111,6 @@ __device__ __forceinline__ bool chol6_lean(const double* __restrict__ A, double 
   return ok;
 }
 
-
 // A team = a group of warps of the CTA that factors one contiguous range of columns.  With a
 // nested-dissection ordering the ranges of different teams are branches of the elimination tree
 // that only meet in the separator columns at the end: they run concurrently (the factorisation is
@@ -131,12 +130,22 @@ struct SolveShared {
   int* col_ptr; int* upd_ptr; int* row_idx; int* urg_dst; int* sfix;
   int (*fail)[2];
   double (*sL)[2][28];
+  int2 (*upd)[2][kUpdStage];   // [min(slot, 2)]
 };
 
 // Right-looking block Cholesky of columns [T.j0, T.j1) with look-ahead; forward solve rides along.
 __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S, double lambda, int refill_period) {
   const int t = T.tid, lane = threadIdx.x & 31, twarp = T.tid >> 5;
-  const int nupd = T.nth - T.npanel, ut = t - T.npanel;
+  // Panel threads are the team's first T.npanel threads (its warps 0..3); update units are dealt from the
+  // team's LAST warp downwards, because warp w issues from scheduler w % 4: the pivot-chain warp (panel
+  // warp 0) then shares its scheduler and FP64 pipe with the least loaded update warp (measured: -15 % per
+  // column).  For the same reason the second team's pivot chain runs on its panel warp 1, not 0.
+  const bool crit = t < T.npanel;
+  const int npw = T.npanel >> 5;
+  const int pw = crit ? (twarp + (T.slot == 1 ? npw - 1 : 0)) % npw : twarp;
+  const int pt = pw * 32 + lane;
+  const int kPanel = T.npanel;
+  const int nupd = T.nth - T.npanel, ut = T.nth - 1 - t;
   const int mask = T.cap - 1;
   double* ring = S.ring + (size_t)T.ring_off * 36;
   double* yv = S.yv;
@@ -155,25 +164,55 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
   cp_async_wait_all();
   bar_sync(T.bar_all, T.nth);
 
+#ifdef SVS_SOLVE_PROFILE
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pc0 = 0, pc1 = clock64();
+  long long* pprof = pacc;
+  long long* pclk = &pc1;
+#endif
   // factor + scale the panel of column jn (panel threads): pivot chain on warp 0, rows on all
-  auto panel_column = [&](int jn) {
+  auto panel_column = [&](int jn, const double* Lsub) {
     const int base = col_ptr[jn], nb = col_ptr[jn + 1] - base - 1;
     double* sl = S.sL[T.slot][jn & 1];
-    if (twarp == 0) {
-      double l[21], rinv[6];
-      const bool ok = chol6_lean(ring + (size_t)(base & mask) * 36, lambda + (S.sfix[jn] ? 1. : 0.), l, rinv);
-      if (lane == 0) {
-        if (!ok) S.fail[T.slot][jn & 1] = 1;
-#pragma unroll
-        for (int i = 0; i < 21; ++i) sl[i] = l[i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) sl[21 + i] = rinv[i];
+    if (pw == 0) {
+      double* D = ring + (size_t)(base & mask) * 36;
+      if (Lsub) {
+        // S_jj -= L L^T with L = L_{jn,jn-1} just scaled by the previous column: symmetric, 21 lanes, one
+        // round -- the only part of that column's update the pivot chain waits for
+        if (lane < 21) {
+          const int r = (lane >= 1) + (lane >= 3) + (lane >= 6) + (lane >= 10) + (lane >= 15);
+          const int c = lane - r * (r + 1) / 2;
+          const double2* La = reinterpret_cast<const double2*>(Lsub + r * 6);
+          const double2* Lb = reinterpret_cast<const double2*>(Lsub + c * 6);
+          const double2 a0 = La[0], a1 = La[1], a2 = La[2], b0 = Lb[0], b1 = Lb[1], b2 = Lb[2];
+          D[r * 6 + c] -= (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y);
+        }
+        __syncwarp();
       }
+      // every lane factors the block redundantly in registers: no shuffles or shared-memory round trips on
+      // the pivot chain (scripts/ubench/chol.cu: both queue behind the update warps' traffic)
+      double l[21], rinv[6];
+      const bool ok = chol6_lean(D, lambda + (S.sfix[jn] ? 1. : 0.), l, rinv);
+      if (lane == 0 && !ok) S.fail[T.slot][jn & 1] = 1;
+      {   // sl[i] <- l[i] (i < 21), rinv[i - 21]: one store per lane instead of 27 by lane 0
+        double v = 0.;
+#pragma unroll
+        for (int i = 0; i < 21; ++i) v = (lane == i) ? l[i] : v;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v = (lane == 21 + i) ? rinv[i] : v;
+        if (lane < 27) sl[lane] = v;
+      }
+#ifdef SVS_SOLVE_PROFILE
+      if (pprof) { const long long c_ = clock64(); pprof[1] += c_ - *pclk; *pclk = c_; }
+#endif
     }
-    bar_sync(T.bar_panel, T.npanel);
+    bar_sync(T.bar_panel, kPanel);
+#ifdef SVS_SOLVE_PROFILE
+    if (pprof && sl[21] != 0.) { const long long c_ = clock64(); pprof[2] += c_ - *pclk; *pclk = c_; }
+#endif
     // row <- row * L^-T by forward substitution (block rows: L_ij ; rhs row: y = L^-1 b)
     const int nrows = nb * 6 + 1;
-    for (int row = t; row < nrows; row += T.npanel) {
+    for (int row = pt; row < nrows; row += kPanel) {
       double* src;
       double* gdst = nullptr;
       if (row < nb * 6) {
@@ -183,53 +222,73 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       } else {
         src = yv + 6 * jn;
       }
-      double o[6];
+      double o[6], v[6], L_[28];
+      {
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        const double2 s0 = s2[0], s1 = s2[1], s3 = s2[2];
+        v[0] = s0.x; v[1] = s0.y; v[2] = s1.x; v[3] = s1.y; v[4] = s3.x; v[5] = s3.y;
+        const double2* l2 = reinterpret_cast<const double2*>(sl);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double s = src[c];
-#pragma unroll
-        for (int q = 0; q < c; ++q) s -= o[q] * sl[c * (c + 1) / 2 + q];
-        o[c] = s * sl[21 + c];
+        for (int q = 0; q < 14; ++q) { const double2 t2 = l2[q]; L_[2 * q] = t2.x; L_[2 * q + 1] = t2.y; }
       }
 #pragma unroll
-      for (int q = 0; q < 6; ++q) src[q] = o[q];
-      if (gdst) {
+      for (int c = 0; c < 6; ++c) {
+        double s = v[c];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) gdst[q] = o[q];   // final factor column, read by the backward solve
+        for (int q = 0; q < c; ++q) s -= o[q] * L_[c * (c + 1) / 2 + q];
+        o[c] = s * L_[21 + c];
+      }
+      {
+        double2* d2 = reinterpret_cast<double2*>(src);
+        d2[0] = make_double2(o[0], o[1]); d2[1] = make_double2(o[2], o[3]); d2[2] = make_double2(o[4], o[5]);
+        if (gdst) {   // final factor column, read by the backward solve
+          double2* g2 = reinterpret_cast<double2*>(gdst);
+          g2[0] = make_double2(o[0], o[1]); g2[1] = make_double2(o[2], o[3]); g2[2] = make_double2(o[4], o[5]);
+        }
       }
     }
   };
 
-  // half of a pair update, register tiled: rows 3h..3h+2 of S_ab -= L_a L_b^T (18 + 36 doubles loaded
-  // for 108 FMAs: off the pivot chain, what matters is not to flood the shared-memory pipe the chain lives on)
-  auto update_half = [&](int base, int u, int ab, int dst, int hi_res) {
-    const int h = u & 1;
+  // a quarter of a pair update: rows 3h..3h+2, columns 3g..3g+2 of S_ab -= L_a L_b^T.  What bounds a column
+  // step is the instruction count of its longest warp (a lone warp retires an instruction every 7-12
+  // cycles here), so the unit is sized to give every update thread at most one: 18 16-byte loads, 54 FMAs
+  // into accumulators preloaded with the destination, 12 loads/stores of the destination.
+  auto update_quarter = [&](int base, int u, int ab, int dst, int hi_res) {
+    const int h = (u >> 1) & 1, g = u & 1;
     const double2* La = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab >> 16)) & mask) * 36 + h * 18);
-    const double2* Lb = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab & 0xffff)) & mask) * 36);
-    double a[18];
+    const double2* Lb = reinterpret_cast<const double2*>(ring + (size_t)((base + 1 + (ab & 0xffff)) & mask) * 36 + g * 18);
+    double a[18], b[18], o[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) { const double2 v = La[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
-    double o[18];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      const double2 b0 = Lb[3 * c], b1 = Lb[3 * c + 1], b2 = Lb[3 * c + 2];
+    for (int q = 0; q < 9; ++q) { const double2 v = Lb[q]; b[2 * q] = v.x; b[2 * q + 1] = v.y; }
+    const bool in_ring = dst < hi_res, shared_sep = !in_ring && dst >= T.sep_blk0;
+    double* D = (in_ring ? ring + (size_t)(dst & mask) * 36 : d.S + (size_t)dst * 36) + h * 18 + g * 3;
+    if (shared_sep) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) o[i] = 0.;
+    } else {
 #pragma unroll
       for (int r = 0; r < 3; ++r)
-        o[r * 6 + c] = (a[r * 6] * b0.x + a[r * 6 + 1] * b0.y) + (a[r * 6 + 2] * b1.x + a[r * 6 + 3] * b1.y) +
-                       (a[r * 6 + 4] * b2.x + a[r * 6 + 5] * b2.y);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[r * 3 + c] = D[r * 6 + c];
     }
-    if (dst < hi_res) {
-      double2* D = reinterpret_cast<double2*>(ring + (size_t)(dst & mask) * 36 + h * 18);
 #pragma unroll
-      for (int q = 0; q < 9; ++q) { double2 v = D[q]; v.x -= o[2 * q]; v.y -= o[2 * q + 1]; D[q] = v; }
-    } else if (dst >= T.sep_blk0) {   // separator block shared with the other teams
-      double* D = d.S + (size_t)dst * 36 + h * 18;
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int q = 0; q < 18; ++q) atomicAdd(D + q, -o[q]);
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[r * 3 + c] = fma(-a[r * 6 + k], b[c * 6 + k], o[r * 3 + c]);
+    if (shared_sep) {   // separator block shared with the other teams
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(D + r * 6 + c, o[r * 3 + c]);
     } else {
-      double2* D = reinterpret_cast<double2*>(d.S + (size_t)dst * 36 + h * 18);
 #pragma unroll
-      for (int q = 0; q < 9; ++q) { double2 v = D[q]; v.x -= o[2 * q]; v.y -= o[2 * q + 1]; D[q] = v; }
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) D[r * 6 + c] = o[r * 3 + c];
     }
   };
 
@@ -239,47 +298,43 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
     return (j + 1 < T.j1 && nb > 0 && row_idx[base + 1] == j + 1) ? nb : 0;
   };
 
-  if (t < T.npanel) panel_column(T.j0);
-  int pf_ab[kUpdPf], pf_dst[kUpdPf];
-  auto prefetch_upd = [&](int j) {
-    const int u0 = upd_ptr[j] + urgent_of(j), nunits = (upd_ptr[j + 1] - u0) * 2;
-#pragma unroll
-    for (int i = 0; i < kUpdPf; ++i) {
-      const int u = ut + i * nupd;
-      if (u < nunits) { pf_ab[i] = d.upd_ab[u0 + (u >> 1)]; pf_dst[i] = d.upd_dst[u0 + (u >> 1)]; }
-    }
+  if (crit) panel_column(T.j0, nullptr);
+  // column j's list of non-urgent pairs is staged in shared memory during column j-1
+  int2 (*stage)[kUpdStage] = S.upd[T.slot < 2 ? T.slot : 2];
+  auto stage_load = [&](int j, int2& e) {
+    const int v0 = upd_ptr[j] + urgent_of(j), np = upd_ptr[j + 1] - v0;
+    const bool mine = ut < np && ut < kUpdStage;
+    if (mine) e = make_int2(d.upd_ab[v0 + ut], d.upd_dst[v0 + ut]);
+    return mine;
   };
-  if (t >= T.npanel) prefetch_upd(T.j0);
+  if (!crit) {
+    int2 e;
+    if (stage_load(T.j0, e)) stage[T.j0 & 1][ut] = e;
+  }
   bar_sync(T.bar_all, T.nth);
   int failed = S.fail[T.slot][T.j0 & 1];
   int until_refill = refill_period;
 
+#ifdef SVS_SOLVE_PROFILE
+#define PSTAMP(i) do { const long long c_ = clock64(); pacc[i] += c_ - pc1; pc1 = c_; } while (0)
+#else
+#define PSTAMP(i) do {} while (0)
+#endif
   for (int j = T.j0; j < T.j1 && !failed; ++j) {
     const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
     const int urgent = urgent_of(j);
     const int u0 = upd_ptr[j];
-    if (t < T.npanel) {
+#ifdef SVS_SOLVE_PROFILE
+    pc0 = pc1 = clock64();
+#endif
+    if (crit) {
       // ---- panel threads: the part of column j's update that lands in column j+1, then factor it
       if (urgent) {
-        if (twarp == 0) {
-          // S_{j+1,j+1} -= L L^T with L = L_{j+1,j}: symmetric, 21 lanes, one round -- the only part of
-          // column j's update the next pivot chain waits for
-          if (lane < 21) {
-            int r = 0, u = lane;
-            while (u > r) { u -= r + 1; ++r; }
-            const int c = u;
-            const double2* La = reinterpret_cast<const double2*>(ring + (size_t)((base + 1) & mask) * 36 + r * 6);
-            const double2* Lb = reinterpret_cast<const double2*>(ring + (size_t)((base + 1) & mask) * 36 + c * 6);
-            const double2 a0 = La[0], a1 = La[1], a2 = La[2], b0 = Lb[0], b1 = Lb[1], b2 = Lb[2];
-            const double sv = (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y) + (a2.x * b2.x + a2.y * b2.y);
-            double* D = ring + (size_t)(col_ptr[j + 1] & mask) * 36;
-            const double nv = D[r * 6 + c] - sv;
-            D[r * 6 + c] = nv;
-            D[c * 6 + r] = nv;
-          }
-          __syncwarp();
+        if (pw == 0) {
+          // (the diagonal part of this update is done by panel_column below)
+          PSTAMP(0);
         } else {
-          if (twarp == 1 && lane < 6) {   // b_{j+1} -= L_{j+1,j} y_j
+          if (pw == 1 && lane < 6) {   // b_{j+1} -= L_{j+1,j} y_j
             const double* La = ring + (size_t)((base + 1) & mask) * 36 + lane * 6;
             const double* yj = yv + 6 * j;
             double sv = 0.;
@@ -287,27 +342,27 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
             for (int q = 0; q < 6; ++q) sv += La[q] * yj[q];
             yv[6 * (j + 1) + lane] -= sv;
           }
-          for (int u = 2 + (t - 32); u < urgent * 2; u += T.npanel - 32) {
-            const int a = u >> 1;
-            update_half(base, u, a << 16, urg_dst[base + 1 + a], 0x7fffffff);
+          for (int u = 4 + (pt - 32); u < urgent * 4; u += kPanel - 32) {
+            const int a = u >> 2;
+            update_quarter(base, u, a << 16, urg_dst[base + 1 + a], 0x7fffffff);
           }
         }
       }
-      if (j + 1 < T.j1) panel_column(j + 1);   // its barrier also orders the other panel warps' updates before the row scaling
+      if (j + 1 < T.j1)   // its barrier also orders the other panel warps' updates before the row scaling
+        panel_column(j + 1, urgent ? ring + (size_t)((base + 1) & mask) * 36 : nullptr);
+      PSTAMP(3);
     } else {
       // ---- update threads: the rest of column j's trailing update
-      int cu_ab[kUpdPf], cu_dst[kUpdPf];
-#pragma unroll
-      for (int i = 0; i < kUpdPf; ++i) { cu_ab[i] = pf_ab[i]; cu_dst[i] = pf_dst[i]; }
-      if (j + 1 < T.j1) prefetch_upd(j + 1);
-      const int uu = u0 + urgent, nunits = (upd_ptr[j + 1] - uu) * 2;
-#pragma unroll
-      for (int i = 0; i < kUpdPf; ++i) {
-        const int u = ut + i * nupd;
-        if (u < nunits) update_half(base, u, cu_ab[i], cu_dst[i], hi);
+      int2 nxt;
+      const bool have_nxt = j + 1 < T.j1 && stage_load(j + 1, nxt);
+      const int uu = u0 + urgent, npairs = upd_ptr[j + 1] - uu;
+      const int2* cur = stage[j & 1];
+      for (int u = ut; u < npairs * 4; u += nupd) {
+        const int pr = u >> 2;
+        const int2 e = pr < kUpdStage ? cur[pr] : make_int2(d.upd_ab[uu + pr], d.upd_dst[uu + pr]);
+        update_quarter(base, u, e.x, e.y, hi);
       }
-      for (int u = ut + kUpdPf * nupd; u < nunits; u += nupd)
-        update_half(base, u, d.upd_ab[uu + (u >> 1)], d.upd_dst[uu + (u >> 1)], hi);
+      if (have_nxt) stage[(j + 1) & 1][ut] = nxt;
       // b_a -= L_aj y_j for the rows the panel threads did not take
       for (int w = ut + (urgent ? 6 : 0); w < nb * 6; w += nupd) {
         const int a = w / 6, r = w - a * 6;
@@ -321,7 +376,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
         else yv[6 * row + r] -= s;
       }
       // inverse of column j's diagonal factor for the backward solve (off the critical path)
-      if (twarp == (T.nth >> 5) - 1 && lane < 6) {
+      if (twarp == npw + 1 && lane < 6) {
         const double* sl = S.sL[T.slot][j & 1];
         const int c = lane;
         double col[6];
@@ -335,9 +390,13 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
 #pragma unroll
         for (int r = 0; r < 6; ++r) d.Linv[36 * (size_t)j + r * 6 + c] = col[r];
       }
+      PSTAMP(5);
     }
     bar_sync(T.bar_all, T.nth);
     failed = S.fail[T.slot][(j + 1) & 1];
+#ifdef SVS_SOLVE_PROFILE
+    if (failed >= 0) { if (crit) PSTAMP(4); else PSTAMP(6); }
+#endif
     // ---- every refill_period columns: reload the ring slots the finished columns freed.  Copies are
     //      never in flight while updates run, so a destination is either resident (< hi) or in HBM.
     if (--until_refill == 0) until_refill = refill_period;
@@ -354,6 +413,11 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
     }
   }
   if (failed && t == 0) S.fail[T.slot][0] = S.fail[T.slot][1] = 1;
+#ifdef SVS_SOLVE_PROFILE
+  (void)pc0;
+  if (d.dbg && T.slot == 0 && (t == 0 || t == T.npanel))
+    for (int i = 0; i < 8; ++i) d.dbg[24 + (t ? 8 : 0) + i] = pacc[i];
+#endif
 }
 
 // Backward solve L^T x = y for columns [T.j0, T.j1), descending: the factor is streamed back through
@@ -435,7 +499,8 @@ k_solve(BaDev d, int cap, int refill_branch, int refill_sep) {
   extern __shared__ __align__(16) double sm_solve[];
   __shared__ int sFail[kMaxTeams + 1][2];
   __shared__ double sRed[kSolveThreads / 32];
-  __shared__ double sLbuf[kMaxTeams + 1][2][28];
+  __shared__ __align__(16) double sLbuf[kMaxTeams + 1][2][28];
+  __shared__ int2 sUpd[3][2][kUpdStage];
   LmCtl* ctl = d.ctl;
   if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
   const int t = threadIdx.x, nt = kSolveThreads, lane = t & 31, warp = t >> 5;
@@ -448,7 +513,7 @@ k_solve(BaDev d, int cap, int refill_branch, int refill_sep) {
   int* meta = reinterpret_cast<int*>(S.yv + ((6 * (size_t)P + 1) / 2) * 2);
   S.col_ptr = meta; S.upd_ptr = S.col_ptr + (P + 1); S.row_idx = S.upd_ptr + (P + 1);
   S.urg_dst = S.row_idx + nblk; S.sfix = S.urg_dst + nblk;
-  S.fail = sFail; S.sL = sLbuf;
+  S.fail = sFail; S.sL = sLbuf; S.upd = sUpd;
   if (t < 2 * (kMaxTeams + 1)) sFail[t >> 1][t & 1] = 0;
   for (int i = t; i <= P; i += nt) { S.col_ptr[i] = d.col_ptr[i]; S.upd_ptr[i] = d.upd_ptr[i]; }
   for (int i = t; i < nblk; i += nt) { S.row_idx[i] = d.row_idx[i]; S.urg_dst[i] = d.urg_dst[i]; }
@@ -565,9 +630,9 @@ int solve_ring_capacity(int P, int nblk) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);   // 2.4 KB static
+    cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 10240);   // 9.6 KB static
   }
-  const size_t budget = (size_t)smem_optin - 4096 - 256;
+  const size_t budget = (size_t)smem_optin - 10240 - 256;
   const size_t ybytes = (((size_t)6 * P * 8 + 15) / 16) * 16;
   const size_t mbytes = ((size_t)(2 * (P + 1) + 2 * nblk + P) * 4 + 15) / 16 * 16;
   if (ybytes + mbytes >= budget || ybytes > budget / 4) return 0;
