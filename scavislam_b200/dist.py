@@ -14,11 +14,14 @@ import numpy as np
 
 
 def window_for_rank(rank: int):
-    """Rank 0 measures the C2 window itself, the others independent windows of the same shape."""
+    """Rank 0 measures the C2 window itself; the other ranks get the same 200-keyframe / 20k-landmark
+    window (identical structure, so that the per-rank work of the weak-scaling run is equal) with an
+    independent realisation of the measurement and initialisation noise."""
     from . import synth
     if rank == 0:
         return synth.make_config("C2")
-    return synth.make_window(200, 20000, 1234 + 100 + rank, name=f"C4[{rank}]")
+    P, L, idx = synth.CONFIGS["C2"]
+    return synth.make_window(P, L, 1234 + idx, name=f"C4[{rank}]", noise_seed=9000 + rank)
 
 
 def reduce_job_totals(times_s, counts, dist=None, device="cpu"):

@@ -149,7 +149,9 @@ def quat_to_R(q):
 
 def make_window(P: int, L: int, seed: int, T: int = 8, name: str = "",
                 pose_noise=(0.02, 0.005), depth_noise=0.05, obs_sigma=0.5,
-                outlier_frac=0.02) -> BAProblem:
+                outlier_frac=0.02, noise_seed=None) -> BAProblem:
+    """`seed` fixes the window (trajectory, landmarks, visibility); measurement / pose / depth noise come
+    from the same stream, or from `noise_seed` when given (same window, another noise realisation)."""
     rng = np.random.default_rng(seed)
     f, px, py, b = CAM_F, CAM_PX, CAM_PY, CAM_B
 
@@ -198,6 +200,8 @@ def make_window(P: int, L: int, seed: int, T: int = 8, name: str = "",
     e_point, e_pose, e_obs = e_point[order], e_pose[order], e_obs[order]
     E = e_point.shape[0]
     e_anchor = anchor[e_point]
+    if noise_seed is not None:
+        rng = np.random.default_rng(noise_seed)
     e_obs = e_obs + rng.normal(0, obs_sigma, (E, 3))
     outl = rng.uniform(size=E) < outlier_frac
     e_obs[outl] += rng.uniform(-20, 20, (int(outl.sum()), 3))
