@@ -49,6 +49,16 @@ __device__ void lm_decide(LmCtl* ctl, double chi_cur, double chi_new, double sca
   ctl->qmax = qmax;
 }
 
+constexpr int kLmLanes = 8;   // lanes per landmark in k_update
+
+// sum over the kLmLanes lanes of a landmark's group; groups of one warp may sit in different branches,
+// so the shuffle names only the group's own lanes
+__device__ __forceinline__ double group_sum(double v, unsigned gmask) {
+#pragma unroll
+  for (int o = kLmLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_update(BaDev d, int robust, double delta, int n_lm_blocks, int defer_decision) {
@@ -76,7 +86,12 @@ k_update(BaDev d, int robust, double delta, int n_lm_blocks, int defer_decision)
     part_cur = warp_sum(a);
     part_new = warp_sum(b);
   } else {
-    const int li = (int)blockIdx.x * WARPS + warp;
+    // four landmarks per warp, eight lanes each (a track is ~6 observations: one warp per landmark
+    // ran 4/5 of its lanes idle); longer tracks just take more rounds of the strided loops
+    const int sub = lane & (kLmLanes - 1);
+    const unsigned gmask = ((1u << kLmLanes) - 1u) << (lane & ~(kLmLanes - 1));
+    const int li = ((int)blockIdx.x * WARPS + warp) * (32 / kLmLanes) + lane / kLmLanes;
+    double g_cur = 0, g_new = 0, g_scale = 0;   // this landmark's share (valid on sub-lane 0)
     if (li < d.L) {
       const double lambda = ctl->lambda;
       const int e0 = d.lm_eptr[li], k = d.lm_eptr[li + 1] - e0;
@@ -84,15 +99,15 @@ k_update(BaDev d, int robust, double delta, int n_lm_blocks, int defer_decision)
       const double* psi = d.psi[cur] + 3 * (size_t)li;
       double* psin = d.psi[trial] + 3 * (size_t)li;
       if (k == 0 || ctl->chol_fail) {
-        if (lane < 3) psin[lane] = psi[lane];
-        part_cur = (k == 0) ? 0. : d.chi_l[li];
+        if (sub < 3) psin[sub] = psi[sub];
+        g_cur = (k == 0) ? 0. : d.chi_l[li];
       } else {
-        part_cur = d.chi_l[li];
+        g_cur = d.chi_l[li];
         const int off = d.lm_self[li] ? 0 : 1;
         const int ia = d.lm_anchor[li];
         // c = b_l - sum_slots B_s^T x_s
         double c3[3] = {0, 0, 0};
-        for (int s = lane; s < K; s += 32) {
+        for (int s = sub; s < K; s += kLmLanes) {
           const int p = (s == 0) ? ia : d.e_pose[e0 + s - off];
           const double* xs = d.x + 6 * p;
 #pragma unroll
@@ -103,7 +118,7 @@ k_update(BaDev d, int robust, double delta, int n_lm_blocks, int defer_decision)
           }
         }
 #pragma unroll
-        for (int q = 0; q < 3; ++q) c3[q] = warp_sum(c3[q]);
+        for (int q = 0; q < 3; ++q) c3[q] = group_sum(c3[q], gmask);
         const double* Dbl = d.Dbl + 12 * (size_t)li;
         const double bl[3] = {Dbl[6], Dbl[7], Dbl[8]};
         double Di[9];
@@ -115,9 +130,9 @@ k_update(BaDev d, int robust, double delta, int n_lm_blocks, int defer_decision)
           dpsi[q] = Di[q * 3] * cc[0] + Di[q * 3 + 1] * cc[1] + Di[q * 3 + 2] * cc[2];
           pn[q] = psi[q] + dpsi[q];
         }
-        if (lane < 3) psin[lane] = pn[lane];
-        part_scale = dpsi[0] * (lambda * dpsi[0] + bl[0]) + dpsi[1] * (lambda * dpsi[1] + bl[1]) +
-                     dpsi[2] * (lambda * dpsi[2] + bl[2]);
+        if (sub < 3) psin[sub] = pn[sub];
+        g_scale = dpsi[0] * (lambda * dpsi[0] + bl[0]) + dpsi[1] * (lambda * dpsi[1] + bl[1]) +
+                  dpsi[2] * (lambda * dpsi[2] + bl[2]);
         // robust chi2 of this landmark's observations at the trial state
         const double* __restrict__ Rt = d.Rt[trial];
         double Ra[9], ta[3];
@@ -125,15 +140,19 @@ k_update(BaDev d, int robust, double delta, int n_lm_blocks, int defer_decision)
         const double ipz = 1. / pn[2];
         const double xa[3] = {pn[0] * ipz, pn[1] * ipz, ipz};
         double chi = 0;
-        for (int i = lane; i < k; i += 32) {
+        for (int i = sub; i < k; i += kLmLanes) {
           const int e = e0 + i;
           const double obs[3] = {__ldg(d.e_obs + e), __ldg(d.e_obs + (size_t)d.E + e), __ldg(d.e_obs + 2 * (size_t)d.E + e)};
           const double om[3] = {__ldg(d.e_w + e), __ldg(d.e_w + (size_t)d.E + e), __ldg(d.e_w + 2 * (size_t)d.E + e)};
           chi += edge_cost(d, Rt, d.e_pose[e], Ra, ta, xa, obs, om, robust, delta);
         }
-        part_new = warp_sum(chi);
+        g_new = group_sum(chi, gmask);
       }
     }
+    // the warp's share: its landmarks in a fixed order
+    part_cur = warp_sum(sub == 0 ? g_cur : 0.);
+    part_new = warp_sum(sub == 0 ? g_new : 0.);
+    part_scale = warp_sum(sub == 0 ? g_scale : 0.);
   }
   // CTA partials in a fixed order -> part[blockIdx][3]; the last CTA to finish reduces them
   if (lane == 0) { sPart[warp][0] = part_cur; sPart[warp][1] = part_new; sPart[warp][2] = part_scale; }
@@ -184,7 +203,8 @@ void launch_decide_deferred(const BaDev& d, cudaStream_t st) { k_decide_deferred
 
 void launch_update(const BaDev& d, int robust, double delta, int defer_decision, cudaStream_t st) {
   constexpr int WARPS = 8;
-  const int n_lm_blocks = (d.L + WARPS - 1) / WARPS;
+  constexpr int kPerBlock = WARPS * (32 / kLmLanes);
+  const int n_lm_blocks = (d.L + kPerBlock - 1) / kPerBlock;
   const int n_c_blocks = (d.C + WARPS * 32 - 1) / (WARPS * 32);
   int nb = n_lm_blocks + n_c_blocks;
   if (nb == 0) nb = 1;   // still clears the reduced system and takes the LM decision
@@ -192,7 +212,8 @@ void launch_update(const BaDev& d, int robust, double delta, int defer_decision,
 }
 int update_grid_blocks(int L, int C) {
   constexpr int WARPS = 8;
-  const int nb = (L + WARPS - 1) / WARPS + (C + WARPS * 32 - 1) / (WARPS * 32);
+  constexpr int kPerBlock = WARPS * (32 / kLmLanes);
+  const int nb = (L + kPerBlock - 1) / kPerBlock + (C + WARPS * 32 - 1) / (WARPS * 32);
   return nb > 0 ? nb : 1;
 }
 
