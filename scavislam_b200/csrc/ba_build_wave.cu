@@ -137,47 +137,42 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
       for (int i = 0; i < k; ++i) s += sChi[lane * k + i];
       d.chi_l[lm0 + w0 + lane] = s;
     }
-    // ---- phase 2: per-landmark sums over its edges: anchor Hpl block (18), Hll (6), b_l (3), A_aa (21)
-    for (int it = lane; it < nw * 48; it += 32) {
-      const int j = it / 48, t = it - j * 48;
-      const int l0 = j * k;
+    // ---- phase 2: per-landmark sums over its edges: anchor Hpl block (18), Hll (6), b_l (3), A_aa (21);
+    //      one loop per kind so that the lanes of a round share a code path
+    for (int it = lane; it < nw * 18; it += 32) {
+      const int j = it / 18, t = it - j * 18, r = t / 3, c = t - r * 3;
+      const double* Ja = sJa + kWvJ * (j * k + i_first);
+      const double* Js = sJs + 9 * (j * k + i_first);
       double s = 0.;
-      if (t < 18) {
-        const int r = t / 3, c = t - r * 3;
-        for (int i = i_first; i < k; ++i) {
-          const double* Ja = sJa + kWvJ * (l0 + i);
-          const double* Js = sJs + 9 * (l0 + i);
-          s += Ja[r] * Js[c] + Ja[6 + r] * Js[3 + c] + Ja[12 + r] * Js[6 + c];
-        }
-        sB[18 * (j * K) + t] = s;
-      } else if (t < 24) {
-        const int u = t - 18;
-        const int r = u < 3 ? 0 : (u < 5 ? 1 : 2), c = u < 3 ? u : (u < 5 ? u - 2 : 2);
-        for (int i = 0; i < k; ++i) {
-          const double* Js = sJs + 9 * (l0 + i);
-          s += Js[r] * Js[c] + Js[3 + r] * Js[3 + c] + Js[6 + r] * Js[6 + c];
-        }
-        sLm[j * kWvLmD + u] = s;
-      } else if (t < 27) {
-        const int c = t - 24;
-        for (int i = 0; i < k; ++i) {
-          const double* Js = sJs + 9 * (l0 + i);
-          const double* Ee = sE + 3 * (l0 + i);
-          s -= Js[c] * Ee[0] + Js[3 + c] * Ee[1] + Js[6 + c] * Ee[2];
-        }
-        sLm[j * kWvLmD + 6 + c] = s;
-      } else {
-        // anchor diagonal: all edges' J~a^T J~a; the self edge keeps g2o's J1^T W J1
-        int u = t - 27, r = 0;
-        while (u > r) { u -= r + 1; ++r; }
-        const int c = u;
-        for (int i = (skip_self ? i_first : 0); i < k; ++i) {
-          const double* Ja = sJa + kWvJ * (l0 + i);
-          s += Ja[r] * Ja[c] + Ja[6 + r] * Ja[6 + c] + Ja[12 + r] * Ja[12 + c];
-        }
-        sLm[j * kWvLmD + 18 + r * 6 + c] = s;
-        sLm[j * kWvLmD + 18 + c * 6 + r] = s;
-      }
+      for (int i = i_first; i < k; ++i, Ja += kWvJ, Js += 9) s += Ja[r] * Js[c] + Ja[6 + r] * Js[3 + c] + Ja[12 + r] * Js[6 + c];
+      sB[18 * (j * K) + t] = s;
+    }
+    for (int it = lane; it < nw * 6; it += 32) {
+      const int j = it / 6, u = it - j * 6;
+      const int r = u < 3 ? 0 : (u < 5 ? 1 : 2), c = u < 3 ? u : (u < 5 ? u - 2 : 2);
+      const double* Js = sJs + 9 * (j * k);
+      double s = 0.;
+      for (int i = 0; i < k; ++i, Js += 9) s += Js[r] * Js[c] + Js[3 + r] * Js[3 + c] + Js[6 + r] * Js[6 + c];
+      sLm[j * kWvLmD + u] = s;
+    }
+    for (int it = lane; it < nw * 3; it += 32) {
+      const int j = it / 3, c = it - j * 3;
+      const double* Js = sJs + 9 * (j * k);
+      const double* Ee = sE + 3 * (j * k);
+      double s = 0.;
+      for (int i = 0; i < k; ++i, Js += 9, Ee += 3) s -= Js[c] * Ee[0] + Js[3 + c] * Ee[1] + Js[6 + c] * Ee[2];
+      sLm[j * kWvLmD + 6 + c] = s;
+    }
+    for (int it = lane; it < nw * 21; it += 32) {
+      // anchor diagonal: all edges' J~a^T J~a; the self edge keeps g2o's J1^T W J1
+      const int j = it / 21, u = it - j * 21;
+      const int r = (u >= 1) + (u >= 3) + (u >= 6) + (u >= 10) + (u >= 15), c = u - r * (r + 1) / 2;
+      const int i0 = skip_self ? i_first : 0;
+      const double* Ja = sJa + kWvJ * (j * k + i0);
+      double s = 0.;
+      for (int i = i0; i < k; ++i, Ja += kWvJ) s += Ja[r] * Ja[c] + Ja[6 + r] * Ja[6 + c] + Ja[12 + r] * Ja[12 + c];
+      sLm[j * kWvLmD + 18 + r * 6 + c] = s;
+      sLm[j * kWvLmD + 18 + c * 6 + r] = s;
     }
     __syncwarp();
     // ---- phase 3: (Hll + lambda I)^-1 per landmark; Hll / b_l to HBM for the back-substitution
@@ -206,7 +201,9 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
         for (int sg = lane; sg < nslots_w; sg += 32) d.W[(size_t)c * d.nslots + s0 + sg] = sB[18 * sg + c];
     }
     __syncwarp();
-    // ---- phase 5: accumulate the task's contribution to the reduced system in registers
+    // ---- phase 5: accumulate the task's contribution to the reduced system in registers.
+    //      The Schur product common to every unit runs branch-free (9 16-byte loads of B_n, FMAs straight
+    //      into the accumulators); the direct J^T W J terms of the few special pairs follow in their own loops.
 #pragma unroll
     for (int q = 0; q < 7; ++q) {
       const int u = lane + 32 * q;
@@ -214,33 +211,48 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
         const int p = u / 6, r = u - p * 6;
         const int pk = sPair[p];
         const int m = (pk >> 5) & 31, n = pk & 31;
-        for (int j = 0; j < nw; ++j) {
-          const double* Ym = sY + 18 * (j * K + m) + r * 3;
-          const double* Bn = sB + 18 * (j * K + n);
-          const double y0 = Ym[0], y1 = Ym[1], y2 = Ym[2];
-          double v[6];
+        {
+          const double* Ym = sY + 18 * m + r * 3;
+          const double2* Bn = reinterpret_cast<const double2*>(sB + 18 * n);
+#pragma unroll 1
+          for (int j = 0; j < nw; ++j, Ym += 18 * K, Bn += 9 * K) {
+            const double y0 = -Ym[0], y1 = -Ym[1], y2 = -Ym[2];
+            double bb[18];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) v[c] = -(y0 * Bn[c * 3] + y1 * Bn[c * 3 + 1] + y2 * Bn[c * 3 + 2]);
-          if (m == n) {
-            if (m > 0) {
-              const double* Jp = sJp + kWvJ * (j * k + m - off);
+            for (int i = 0; i < 9; ++i) { const double2 t2 = Bn[i]; bb[2 * i] = t2.x; bb[2 * i + 1] = t2.y; }
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+              acc[q][c] = fma(y2, bb[c * 3 + 2], fma(y1, bb[c * 3 + 1], fma(y0, bb[c * 3], acc[q][c])));
+          }
+        }
+        if (m == n) {
+          if (m > 0) {   // own J~p^T J~p of the observer
+            const double* Jp = sJp + kWvJ * (m - off);
+#pragma unroll 1
+            for (int j = 0; j < nw; ++j, Jp += kWvJ * k) {
               const double a0 = Jp[r], a1 = Jp[6 + r], a2 = Jp[12 + r];
 #pragma unroll
-              for (int c = 0; c < 6; ++c) v[c] += a0 * Jp[c] + a1 * Jp[6 + c] + a2 * Jp[12 + c];
-            } else {
-              const double* A = sLm + j * kWvLmD + 18 + r * 6;
-#pragma unroll
-              for (int c = 0; c < 6; ++c) v[c] += A[c];
+              for (int c = 0; c < 6; ++c)
+                acc[q][c] = fma(a2, Jp[12 + c], fma(a1, Jp[6 + c], fma(a0, Jp[c], acc[q][c])));
             }
-          } else if (m == 0) {
-            const double* Ja = sJa + kWvJ * (j * k + n - off);
-            const double* Jp = sJp + kWvJ * (j * k + n - off);
+          } else {       // anchor diagonal, summed over the edges in phase 2
+            const double* A = sLm + 18 + r * 6;
+#pragma unroll 1
+            for (int j = 0; j < nw; ++j, A += kWvLmD) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) acc[q][c] += A[c];
+            }
+          }
+        } else if (m == 0) {   // anchor x observer: J~a^T J~p
+          const double* Ja = sJa + kWvJ * (n - off);
+          const double* Jp = sJp + kWvJ * (n - off);
+#pragma unroll 1
+          for (int j = 0; j < nw; ++j, Ja += kWvJ * k, Jp += kWvJ * k) {
             const double a0 = Ja[r], a1 = Ja[6 + r], a2 = Ja[12 + r];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) v[c] += a0 * Jp[c] + a1 * Jp[6 + c] + a2 * Jp[12 + c];
+            for (int c = 0; c < 6; ++c)
+              acc[q][c] = fma(a2, Jp[12 + c], fma(a1, Jp[6 + c], fma(a0, Jp[c], acc[q][c])));
           }
-#pragma unroll
-          for (int c = 0; c < 6; ++c) acc[q][c] += v[c];
         }
       }
     }
