@@ -116,7 +116,7 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
       const int e = e_base + (w0 + j) * k + i;
       const double* __restrict__ psi = d.psi[cur] + 3 * (size_t)li;
       const double p0 = __ldg(psi), p1 = __ldg(psi + 1), p2 = __ldg(psi + 2);
-      const double ipz = 1. / p2;
+      const double ipz = fast_inv(p2);
       const double xa[3] = {p0 * ipz, p1 * ipz, ipz};
       const int ip = (has_self && i == 0) ? ia : sPose[i + off];
       double* Jp = sJp + kWvJ * lane;
@@ -189,11 +189,14 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
     __syncwarp();
     // ---- phase 4: Y = B Dinv per slot; spill B (Hpl) to HBM, SoA over slots
     const int nslots_w = nw * K;
-    for (int it = lane; it < nslots_w * 18; it += 32) {
-      const int sg = it / 18, rc = it - sg * 18, r = rc / 3, c = rc - r * 3;
+    for (int it = lane; it < nslots_w * 6; it += 32) {   // one row of a slot's block per lane
+      const int sg = it / 6, r = it - sg * 6;
       const double* B = sB + 18 * sg + r * 3;
       const double* Di = sLm + (sg / K) * kWvLmD + 9;
-      sY[18 * sg + rc] = B[0] * Di[c] + B[1] * Di[3 + c] + B[2] * Di[6 + c];
+      const double b0 = B[0], b1 = B[1], b2 = B[2];
+      double* Y = sY + 18 * sg + r * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Y[c] = b0 * Di[c] + b1 * Di[3 + c] + b2 * Di[6 + c];
     }
     {
       const size_t s0 = (size_t)s_base + (size_t)w0 * K;

@@ -28,10 +28,30 @@ __device__ __forceinline__ void rel_pose(const double Rc[9], const double tc[3],
 }
 
 // e = z - pi_stereo(y)   (G2oCameraParameters::stereocam_uvu_map, anchored_points.cpp:43-50)
+// 1/a and sqrt(a) from the hardware approximations + two Newton steps (full double precision up to
+// rounding; the library versions cost 20+ instructions each on the edge path)
+__device__ __forceinline__ double fast_inv(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_sqrt(double a) {   // a >= 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  y = fma(y, fma(-h * y, y, 0.5), y);
+  y = fma(y, fma(-h * y, y, 0.5), y);
+  return a > 0. ? a * y : 0.;
+}
+
 __device__ __forceinline__ void stereo_residual(const BaDev& d, const double y[3], const double obs[3], double e[3]) {
-  e[0] = obs[0] - ((y[0] / y[2]) * d.f + d.px);
-  e[1] = obs[1] - ((y[1] / y[2]) * d.f + d.py);
-  e[2] = obs[2] - (((y[0] - d.b) / y[2]) * d.f + d.px);
+  const double iz = fast_inv(y[2]);
+  e[0] = obs[0] - ((y[0] * iz) * d.f + d.px);
+  e[1] = obs[1] - ((y[1] * iz) * d.f + d.py);
+  e[2] = obs[2] - (((y[0] - d.b) * iz) * d.f + d.px);
 }
 
 // robust cost of one observation at (pose, anchor, psi)
@@ -201,9 +221,9 @@ __device__ __forceinline__ double linearize_edge(const BaDev& d, const double* _
   const double e2 = er[0] * er[0] * om[0] + er[1] * er[1] * om[1] + er[2] * er[2] * om[2];
   double r0 = e2, r1 = 1.;
   if (robust) huber(e2, delta, r0, r1);
-  const double sw[3] = {sqrt(r1 * om[0]), sqrt(r1 * om[1]), sqrt(r1 * om[2])};   // sqrt(rho' Omega)
+  const double sw[3] = {fast_sqrt(r1 * om[0]), fast_sqrt(r1 * om[1]), fast_sqrt(r1 * om[2])};   // sqrt(rho' Omega)
   // d_stereoproj_d_y (transformations.h:62-71): rows (a 0 c0) (0 a c1) (a 0 c2)
-  const double iz = 1. / y[2];
+  const double iz = fast_inv(y[2]);
   const double a = d.f * iz;
   const double c0 = -(d.f * y[0]) * iz * iz, c1 = -(d.f * y[1]) * iz * iz, c2 = -(d.f * (y[0] - d.b)) * iz * iz;
   // J_pose = -Jcam [I | -hat(y)]  (anchored_points.cpp:187, transformations.h:73-80)
