@@ -26,6 +26,7 @@ struct svs_ba {
   cudaStream_t stream = nullptr;
   std::string err;
   bool has_problem = false;
+  int cur_known = -1;   // host mirror of LmCtl::cur (index of the accepted state buffers), -1 = ask the device
   BaDev d{};
   // one device arena + one pinned staging arena, grown on demand and reused across set_problem calls
   char* arena = nullptr; size_t arena_cap = 0, arena_off = 0;
@@ -596,6 +597,7 @@ int svs_ba_reset_state(svs_ba* h) {
   CK(cudaMemcpyAsync(d.psi[0], h->d_psi0, 3 * (size_t)d.L * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   LmCtl z{};
   *h->h_ctl = z;
+  h->cur_known = 0;
   CK(cudaMemcpyAsync(d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
   launch_prep(d, 0, h->stream);
   CK(cudaGetLastError());
@@ -630,10 +632,14 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
   } while (0)
   // LM state is not carried across calls (slam_graph.cpp:338-342); the accepted
   // state stays where the previous call (or set_problem) left it.
-  CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
-  CKO(cudaStreamSynchronize(h->stream));
+  if (h->cur_known < 0) {   // someone else may have flipped the state buffers: ask the device
+    CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+    CKO(cudaStreamSynchronize(h->stream));
+    h->cur_known = h->h_ctl->cur;
+  }
   {
-    const int cur = h->h_ctl->cur;
+    const int cur = h->cur_known;   // known on the host: no round trip while the upload is still in flight
+    h->cur_known = -1;
     LmCtl z{};
     z.cur = cur; z.lambda = lambda_init; z.ni = 2; z.max_trials = max_trials; z.max_iters = num_iters;
     *h->h_ctl = z;
@@ -678,6 +684,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
   }
   CKO(cudaEventRecord(h->ev[6], h->stream));
   CKO(cudaStreamSynchronize(h->stream));
+  h->cur_known = h->h_ctl->cur;   // read back after the last trial of this call
   if (st) {
     const LmCtl& c = *h->h_ctl;
     st->iterations = c.iter;
@@ -913,6 +920,7 @@ int svs_ba_trial_decide(svs_ba* h, int* again, int* stop, int* iter) {
   launch_decide_deferred(h->d, h->stream);
   CK(cudaMemcpyAsync(h->h_ctl, h->d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  h->cur_known = h->h_ctl->cur;
   CK(cudaGetLastError());
   if (again) *again = h->h_ctl->again;
   if (stop) *stop = h->h_ctl->stop;

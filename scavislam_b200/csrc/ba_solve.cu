@@ -218,7 +218,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       if (row < nb * 6) {
         const int a = row / 6, r = row - a * 6;
         src = ring + (size_t)((base + 1 + a) & mask) * 36 + r * 6;
-        gdst = d.S + (size_t)(base + 1 + a) * 36 + r * 6;
+        gdst = d.S + (size_t)(base + 1 + a) * 36 + r;
       } else {
         src = yv + 6 * jn;
       }
@@ -241,9 +241,10 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       {
         double2* d2 = reinterpret_cast<double2*>(src);
         d2[0] = make_double2(o[0], o[1]); d2[1] = make_double2(o[2], o[3]); d2[2] = make_double2(o[4], o[5]);
-        if (gdst) {   // final factor column, read by the backward solve
-          double2* g2 = reinterpret_cast<double2*>(gdst);
-          g2[0] = make_double2(o[0], o[1]); g2[1] = make_double2(o[2], o[3]); g2[2] = make_double2(o[4], o[5]);
+        if (gdst) {   // final factor column for the backward solve, stored TRANSPOSED (L_ij^T row-major):
+                      // the backward chain then reads rows of L^T with 16-byte loads
+#pragma unroll
+          for (int q = 0; q < 6; ++q) gdst[q * 6] = o[q];
         }
       }
     }
@@ -461,10 +462,10 @@ __device__ void backsolve_range(const BaDev& d, const Team& T, const SolveShared
         double acc = 0.;
         if (lane < 30)
           for (int a = g; a < nb; a += 5) {
-            const double* La = buf + (size_t)(base + 1 + a - col_ptr[jlo]) * 36;
-            const double* xa = yv + 6 * row_idx[base + 1 + a];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) acc += La[q * 6 + r] * xa[q];
+            const double2* Lt = reinterpret_cast<const double2*>(buf + (size_t)(base + 1 + a - col_ptr[jlo]) * 36 + r * 6);
+            const double2* xa = reinterpret_cast<const double2*>(yv + 6 * row_idx[base + 1 + a]);
+            const double2 l0 = Lt[0], l1 = Lt[1], l2 = Lt[2], x0 = xa[0], x1 = xa[1], x2 = xa[2];
+            acc += (l0.x * x0.x + l0.y * x0.y) + (l1.x * x1.x + l1.y * x1.y) + (l2.x * x2.x + l2.y * x2.y);
           }
         double tot = acc;
         tot += __shfl_down_sync(0xffffffffu, acc, 6);
