@@ -41,6 +41,7 @@ def main():
         f.write(f"{'kernel':60s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}\n")
         for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:60]:60s} {n:8d} {us:12.1f} {us / n:10.2f} {100 * us / allus:6.1f}%\n")
+    traffic = {}
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full.txt"), "w") as f:
         for rep in reps:
             hdr, units, data = raw(rep)
@@ -51,9 +52,21 @@ def main():
                 for w in WANT:
                     if w in hdr:
                         f.write(f"   {w:70s} {r[hdr.index(w)]:>16s} {units[hdr.index(w)]}\n")
+                import re
+                kname = re.sub(r"<[^<>]*>$", "", r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")).split("::")[-1]
+                if "dram__bytes_read.sum" in hdr:
+                    def to_bytes(col):
+                        v, u = float(r[hdr.index(col)]), units[hdr.index(col)].lower()
+                        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+                    traffic[kname] = int(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
                 st = sorted(((float(r[hdr.index(h)] or 0), h) for h in stall), reverse=True)[:6]
                 f.write("   top stalls (warps per issue): " + ", ".join(
                     f"{h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}={v:.2f}" for v, h in st) + "\n")
+    import json
+    traffic["source"] = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/{tag}_ncu_full.txt); "
+                         "the 200 KF window stays L2-resident between the iterations of a step")
+    with open(os.path.join(ROOT, "profiles", "kernel_traffic.json"), "w") as jf:
+        json.dump(traffic, jf, indent=1)
     print("wrote profiles/", tag)
 
 
