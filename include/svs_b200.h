@@ -249,6 +249,30 @@ int svs_dt_jacobian_reduction(svs_dt *h, int level, const double T_cur_from_prev
 /* DenseTracker::denseTrackingGpu (dense_tracking.cpp:62-193): coarse-to-fine LM, T updated in place */
 int svs_dt_track(svs_dt *h, double T_cur_from_actkey[7], svs_dt_stats *stats);
 
+/* ---- the tracker the reference builds WITHOUT SCAVISLAM_CUDA_SUPPORT:
+ * DenseTracker::denseTrackingCpu / computeDensePointCloudCpu (dense_tracking.cpp:222-423): every 4th pixel,
+ * previous intensity from the uint8 pyramid, residual clamped to +-0.1, exact software bilinear taps, FP64
+ * point transform, border test isInFrame(uv, 2), disparity scaled by 2^-level, H not damped.  Level sizes
+ * must be multiples of 4 (the reference asserts the same).  Pixel sums are FP64 (reference: sequential FP32). */
+typedef struct svs_dtc svs_dtc;
+int svs_dtc_create(int device, int w0, int h0, int nlevels, svs_dtc **out);
+void svs_dtc_destroy(svs_dtc *h);
+const char *svs_dtc_last_error(const svs_dtc *h);
+/* frame_data_.prev_left().pyr_uint8[level]; on_device != 0: img is a device pointer (e.g. svs_prep_level) */
+int svs_dtc_set_prev_u8(svs_dtc *h, int level, const unsigned char *img, int pitch, int on_device);
+/* frame_data_.pyr_float32 / pyr_float32_dx / pyr_float32_dy [level]; NULL planes are left as they are */
+int svs_dtc_set_cur(svs_dtc *h, int level, const float *cur, const float *dx, const float *dy, int stride_floats,
+                    int on_device);
+/* frame_data_.disp (level-0 float disparity, host) */
+int svs_dtc_set_disparity(svs_dtc *h, const float *disp, int stride_floats);
+/* computeDensePointCloudCpu(T_cur_from_actkey) with cam_vec[level] = cams[level] */
+int svs_computeDensePointCloudCpu(svs_dtc *h, const double T_cur_from_actkey[7], const svs_cam *cams);
+/* ref_dense_points_[level]: (h/4) x (w/4) float4, tightly packed */
+int svs_dtc_get_point_cloud(svs_dtc *h, int level, float *cloud_xyzw);
+int svs_dtc_set_point_cloud(svs_dtc *h, int level, const float *cloud_xyzw);
+/* denseTrackingCpu(&T_cur_from_actkey): coarse-to-fine, T updated in place */
+int svs_denseTrackingCpu(svs_dtc *h, const svs_cam *cams, double T_cur_from_actkey[7], svs_dt_stats *stats);
+
 /* ------------------------------------------------------------------ guided patch matcher */
 
 typedef struct svs_matcher svs_matcher;

@@ -206,6 +206,34 @@ class DenseTracker {
   bool ok_ = false;
 };
 
+// ScaViSLAM::DenseTracker as built without SCAVISLAM_CUDA_SUPPORT (dense_tracking.cpp:222-423)
+class DenseTrackerCpuVariant {
+ public:
+  DenseTrackerCpuVariant(int w, int h, int nlevels) { ok_ = svs_dtc_create(-1, w, h, nlevels, &h_) == SVS_OK; }
+  ~DenseTrackerCpuVariant() { if (h_) svs_dtc_destroy(h_); }
+  DenseTrackerCpuVariant(const DenseTrackerCpuVariant&) = delete;
+  DenseTrackerCpuVariant& operator=(const DenseTrackerCpuVariant&) = delete;
+  bool valid() const { return ok_; }
+  svs_dtc* handle() { return h_; }
+  // computeDensePointCloudCpu(T_cur_from_actkey); cam_vec = one svs_cam per pyramid level
+  bool computeDensePointCloudCpu(const SE3d& T, const std::vector<svs_cam>& cam_vec) {
+    const double t7[7] = {T.q[0], T.q[1], T.q[2], T.q[3], T.t[0], T.t[1], T.t[2]};
+    return ok_ && svs_computeDensePointCloudCpu(h_, t7, cam_vec.data()) == SVS_OK;
+  }
+  // denseTrackingCpu(&T_cur_from_actkey)
+  bool denseTrackingCpu(SE3d* T, const std::vector<svs_cam>& cam_vec, svs_dt_stats* stats = nullptr) {
+    double t7[7] = {T->q[0], T->q[1], T->q[2], T->q[3], T->t[0], T->t[1], T->t[2]};
+    if (!ok_ || svs_denseTrackingCpu(h_, cam_vec.data(), t7, stats) != SVS_OK) return false;
+    for (int k = 0; k < 4; ++k) T->q[k] = t7[k];
+    for (int k = 0; k < 3; ++k) T->t[k] = t7[4 + k];
+    return true;
+  }
+
+ private:
+  svs_dtc* h_ = nullptr;
+  bool ok_ = false;
+};
+
 // ScaViSLAM::GuidedMatcher<StereoCamera>
 class GuidedMatcher {
  public:

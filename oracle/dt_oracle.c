@@ -215,3 +215,162 @@ void odt_make_TQ(const double T_cur_from_actkey[7], double f, double px, double 
       TQ[c * 4 + r] = (float)s;
     }
 }
+
+/* ================================================================ the reference's non-CUDA tracker (a18)
+ * dense_tracking.cpp:222-423, maths_utils.cpp:33-65, transformations.h:116-140, stereo_camera.cpp:24-34.
+ * TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED. */
+#include "ba_oracle.h"
+
+#define ODTC_NTH 4 /* DenseTracker::EVERY_NTH_PIXEL, dense_tracking.h:82 */
+
+/* computeDensePointCloudCpu, dense_tracking.cpp:393-422 */
+void odtc_point_cloud(const double T[7], double f, double px, double py, double b, const float *disp, int disp_stride,
+                      int level, int w, int h, float *cloud) {
+  double Ti[7], R[9];
+  oba_se3_inv(T, Ti);
+  {
+    const double x = Ti[0], y = Ti[1], z = Ti[2], ww = Ti[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * ww); R[2] = 2 * (x * z + y * ww);
+    R[3] = 2 * (x * y + z * ww); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * ww);
+    R[6] = 2 * (x * z - y * ww); R[7] = 2 * (y * z + x * ww); R[8] = 1 - 2 * (x * x + y * y);
+  }
+  const double M[16] = {R[0], R[1], R[2], Ti[4], R[3], R[4], R[5], Ti[5], R[6], R[7], R[8], Ti[6], 0, 0, 0, 1};
+  const double Q[16] = {1, 0, 0, -px, 0, 1, 0, -py, 0, 0, 0, f, 0, 0, 1. / b, 0};
+  double TQ[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += M[r * 4 + k] * Q[k * 4 + c];
+      TQ[r * 4 + c] = s;
+    }
+  const int gw = w / ODTC_NTH, gh = h / ODTC_NTH;
+  const double inv_factor = 1. / (double)(1 << level); /* pyrFromZero_d(1., level) */
+  for (int v = 0; v < gh; ++v)
+    for (int u = 0; u < gw; ++u) {
+      /* interpolateDisparity(disp, (u*4, v*4), level), maths_utils.cpp:37-44 */
+      const double d = (double)disp[(size_t)((v * 4) << level) * disp_stride + ((u * 4) << level)] * inv_factor;
+      float *o = cloud + 4 * ((size_t)v * gw + u);
+      if (d <= 0) {
+        o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; o[3] = -1.f;
+      } else {
+        const double uvd[4] = {(double)(u * ODTC_NTH), (double)(v * ODTC_NTH), d, 1.};
+        double p[4];
+        for (int r = 0; r < 4; ++r) p[r] = TQ[r * 4] * uvd[0] + TQ[r * 4 + 1] * uvd[1] + TQ[r * 4 + 2] * uvd[2] + TQ[r * 4 + 3] * uvd[3];
+        o[0] = (float)(p[0] / p[3]); o[1] = (float)(p[1] / p[3]); o[2] = (float)(p[2] / p[3]); o[3] = 1.f;
+      }
+    }
+}
+
+/* interpolateMat_32f, maths_utils.cpp:46-65 */
+static float interp32f(const float *img, int stride, float u, float v) {
+  const float x = floorf(u), y = floorf(v);
+  const float sx = u - x, sy = v - y;
+  const float wx0 = 1 - sx, wx1 = sx, wy0 = 1 - sy, wy1 = sy;
+  const int xi = (int)x, yi = (int)y;
+  const float v00 = img[(size_t)yi * stride + xi], v01 = img[(size_t)(yi + 1) * stride + xi];
+  const float v10 = img[(size_t)yi * stride + xi + 1], v11 = img[(size_t)(yi + 1) * stride + xi + 1];
+  return (wx0 * wy0) * v00 + (wx0 * wy1) * v01 + (wx1 * wy0) * v10 + (wx1 * wy1) * v11;
+}
+
+void odtc_pass(const odtc_level *L, const double T[7], double *chi2, double H21[21], double Jres[6], int *n_valid) {
+  const int gw = L->w / ODTC_NTH, gh = L->h / ODTC_NTH;
+  double c2 = 0;
+  int nv = 0;
+  if (H21) memset(H21, 0, sizeof(double) * 21);
+  if (Jres) memset(Jres, 0, sizeof(double) * 6);
+  for (int v = 0; v < gh; ++v)
+    for (int u = 0; u < gw; ++u) {
+      const float *c4 = L->cloud + 4 * ((size_t)v * gw + u);
+      if (!(c4[3] > 0)) continue;
+      const double xp[3] = {c4[0], c4[1], c4[2]};
+      double xc[3];
+      oba_se3_act(T, xp, xc);
+      /* cam.map(project2d(xyz_cur)).cast<float>() */
+      const float uc = (float)(L->f * (xc[0] / xc[2]) + L->px), vc = (float)(L->f * (xc[1] / xc[2]) + L->py);
+      const int ui = (int)uc, vi = (int)vc; /* cast<int>: truncation */
+      if (!(ui >= 2 && ui < L->w - 2 && vi >= 2 && vi < L->h - 2)) continue; /* isInFrame(uv, 2) */
+      const float ip = (float)((1. / 255.) * L->prev_u8[(size_t)(v * ODTC_NTH) * L->pitch_u8 + u * ODTC_NTH]);
+      const float ic = interp32f(L->cur, L->stride, uc, vc);
+      float res = ip - ic;
+      if (res > 0.1) res = 0.1f;
+      if (res < -0.1) res = -0.1f;
+      c2 += (double)(res * res);
+      ++nv;
+      if (H21) {
+        const float dx = (float)(0.5 * interp32f(L->dx, L->stride, uc, vc));
+        const float dy = (float)(0.5 * interp32f(L->dy, L->stride, uc, vc));
+        /* frame_jac_xyz2uv, transformations.h:116-140 */
+        const double x = xc[0], y = xc[1], z = xc[2], z2 = z * z, f = L->f;
+        const double r0[6] = {-1. / z * f, 0, x / z2 * f, x * y / z2 * f, -(1 + (x * x / z2)) * f, y / z * f};
+        const double r1[6] = {0, -1. / z * f, y / z2 * f, (1 + y * y / z2) * f, -x * y / z2 * f, -x / z * f};
+        double J[6];
+        for (int k = 0; k < 6; ++k) J[k] = dx * r0[k] + dy * r1[k];
+        int q = 0;
+        for (int r = 0; r < 6; ++r) {
+          for (int c = r; c < 6; ++c) H21[q++] += J[r] * J[c];
+          Jres[r] += J[r] * res;
+        }
+      }
+    }
+  *chi2 = c2;
+  if (n_valid) *n_valid = nv;
+}
+
+/* H x = -Jres, H from its upper triangle (Eigen ldlt() in the reference, dense_tracking.cpp:332) */
+static void odtc_solve(const double H21[21], const double Jres[6], double x[6]) {
+  double A[6][6], Lm[6][6], D[6], y[6];
+  int q = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) { A[r][c] = A[c][r] = H21[q++]; }
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= Lm[j][k] * Lm[j][k] * D[k];
+    D[j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      double s = A[i][j];
+      for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k] * D[k];
+      Lm[i][j] = d != 0. ? s / d : 0.;
+    }
+  }
+  for (int i = 0; i < 6; ++i) {
+    double s = -Jres[i];
+    for (int k = 0; k < i; ++k) s -= Lm[i][k] * y[k];
+    y[i] = s;
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = D[i] != 0. ? y[i] / D[i] : 0.;
+    for (int k = i + 1; k < 6; ++k) s -= Lm[k][i] * x[k];
+    x[i] = s;
+  }
+}
+
+void odtc_track(const odtc_level *levels, int nlevels, double T[7], odt_stats *st) {
+  if (st) memset(st, 0, sizeof *st);
+  for (int level = nlevels - 1; level >= 0; --level) {
+    const odtc_level *L = levels + level;
+    double chi2, H[21], Jr[6];
+    int passes = 1;
+    odtc_pass(L, T, &chi2, H, Jr, NULL); /* :229-262 and the first :276-331 sweep see the same pose */
+    for (int i = 0; i < 15; ++i) {
+      double x[6], dT[7], Tn[7], chin, Hn[21], Jn[6];
+      odtc_solve(H, Jr, x);
+      oba_se3_exp(x, dT);
+      oba_se3_mul(dT, T, Tn);
+      odtc_pass(L, Tn, &chin, Hn, Jn, NULL);
+      ++passes;
+      const double rho = chi2 - chin;
+      if (rho > 0) { /* :368-376 */
+        memcpy(T, Tn, sizeof Tn);
+        chi2 = chin;
+        memcpy(H, Hn, sizeof H);
+        memcpy(Jr, Jn, sizeof Jr);
+        double nm = 0;
+        for (int k = 0; k < 6; ++k) nm = fmax(nm, fabs(x[k]));
+        if (nm <= 0.0000000001) break; /* stop = norm_max(x) <= EPS */
+      } else {
+        break; /* :378-385: the identical trial is rejected once more (trial == 2) and the level ends */
+      }
+    }
+    if (st) { st->chi2[level] = chi2; st->passes[level] = passes; }
+  }
+}

@@ -454,3 +454,60 @@ def calc_fast_motion_only(obs_point_id, obs_uvu, point_xyz, cam, T_frame, robust
                                 int(num_iter), float(initial_mu), float(tau), _dp(T), C.byref(st))
     return T, dict(initial_chi2=st.initial_chi2, chi2=st.chi2, max_err=st.max_err, num_obs=st.num_obs,
                    iterations=st.iterations, trials=st.trials, nan_error=st.nan_error)
+
+
+# ---------------------------------------------------------------- dense tracker, non-CUDA build of the reference (a18)
+class ODtcLevel(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("stride", C.c_int), ("pitch_u8", C.c_int),
+                ("f", C.c_double), ("px", C.c_double), ("py", C.c_double), ("b", C.c_double),
+                ("prev_u8", C.c_void_p), ("cur", c_fp), ("dx", c_fp), ("dy", c_fp), ("cloud", c_fp)]
+
+
+def dtc_point_cloud(T, cam, disp, level, w, h):
+    """cam = (f, px, py, b) of the level camera, (w, h) = level size; returns (h/4, w/4, 4) float32."""
+    L = lib()
+    L.odtc_point_cloud.argtypes = [c_dp, C.c_double, C.c_double, C.c_double, C.c_double, c_fp, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, c_fp]
+    L.odtc_point_cloud.restype = None
+    d = _f32(disp)
+    out = np.zeros((h // 4, w // 4, 4), np.float32)
+    L.odtc_point_cloud(_dp(np.ascontiguousarray(T, np.float64)), float(cam[0]), float(cam[1]), float(cam[2]), float(cam[3]),
+                       d.ctypes.data_as(c_fp), d.shape[1], int(level), int(w), int(h), out.ctypes.data_as(c_fp))
+    return out
+
+
+def dtc_levels(levels):
+    """levels: list of dicts(prev_u8, cur, dx, dy, cloud[h/4, w/4, 4], cam=(f, px, py, b))."""
+    arr = (ODtcLevel * len(levels))()
+    keep = []
+    for i, lv in enumerate(levels):
+        p8 = np.ascontiguousarray(lv["prev_u8"], np.uint8)
+        ims = {k: _f32(lv[k]) for k in ("cur", "dx", "dy", "cloud")}
+        keep.append((p8, ims))
+        h, w = ims["cur"].shape
+        f, px, py, b = [float(x) for x in lv["cam"][:4]]
+        arr[i] = ODtcLevel(w, h, w, p8.strides[0], f, px, py, b, p8.ctypes.data,
+                           *[ims[k].ctypes.data_as(c_fp) for k in ("cur", "dx", "dy", "cloud")])
+    return arr, keep
+
+
+def dtc_pass(level, T):
+    L = lib()
+    L.odtc_pass.argtypes = [C.POINTER(ODtcLevel), c_dp, c_dp, c_dp, c_dp, C.POINTER(C.c_int)]
+    L.odtc_pass.restype = None
+    arr, keep = dtc_levels([level])
+    chi, n = np.zeros(1), C.c_int()
+    H, b = np.zeros(21), np.zeros(6)
+    L.odtc_pass(arr, _dp(np.ascontiguousarray(T, np.float64)), _dp(chi), _dp(H), _dp(b), C.byref(n))
+    return float(chi[0]), H, b, n.value
+
+
+def dtc_track(levels, T):
+    L = lib()
+    L.odtc_track.argtypes = [C.POINTER(ODtcLevel), C.c_int, c_dp, C.POINTER(ODtStats)]
+    L.odtc_track.restype = None
+    arr, keep = dtc_levels(levels)
+    T = np.ascontiguousarray(T, np.float64).copy()
+    st = ODtStats()
+    L.odtc_track(arr, len(levels), _dp(T), C.byref(st))
+    return T, dict(chi2=list(st.chi2[:len(levels)]), passes=list(st.passes[:len(levels)]))

@@ -121,6 +121,9 @@ EXPORTS = [
     "svs_matcher_set_pyramid_device",
     "svs_pose_create", "svs_pose_destroy", "svs_pose_last_error", "svs_calcFastMotionOnly",
     "svs_calcFastMotionOnly_matched",
+    "svs_dtc_create", "svs_dtc_destroy", "svs_dtc_last_error", "svs_dtc_set_prev_u8", "svs_dtc_set_cur",
+    "svs_dtc_set_disparity", "svs_computeDensePointCloudCpu", "svs_dtc_get_point_cloud", "svs_dtc_set_point_cloud",
+    "svs_denseTrackingCpu",
 ]
 
 
@@ -198,6 +201,18 @@ def lib():
     L.svs_dt_set_images_device.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.svs_dt_swap_prev_cur.argtypes = [vp]
     L.svs_matcher_set_pyramid_device.argtypes = [vp, C.c_int, c_dp, C.POINTER(C.c_void_p), c_ip]
+    L.svs_dtc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.svs_dtc_destroy.argtypes = [vp]
+    L.svs_dtc_destroy.restype = None
+    L.svs_dtc_last_error.argtypes = [vp]
+    L.svs_dtc_last_error.restype = C.c_char_p
+    L.svs_dtc_set_prev_u8.argtypes = [vp, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.svs_dtc_set_cur.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.svs_dtc_set_disparity.argtypes = [vp, c_fp, C.c_int]
+    L.svs_computeDensePointCloudCpu.argtypes = [vp, c_dp, C.POINTER(SvsCam)]
+    L.svs_dtc_get_point_cloud.argtypes = [vp, C.c_int, c_fp]
+    L.svs_dtc_set_point_cloud.argtypes = [vp, C.c_int, c_fp]
+    L.svs_denseTrackingCpu.argtypes = [vp, C.POINTER(SvsCam), c_dp, C.POINTER(SvsDtStats)]
     L.svs_pose_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.svs_pose_destroy.argtypes = [vp]
     L.svs_pose_destroy.restype = None
@@ -724,3 +739,75 @@ class PoseOptimizer:
         st = SvsPoseStats()
         self._ck(lib().svs_calcFastMotionOnly_matched(self._h, matcher._h, C.byref(c), C.byref(p), _dp(T), C.byref(st)))
         return T, self._stats(st)
+
+
+class DenseTrackerCpuVariant:
+    """DenseTracker as the reference builds it without SCAVISLAM_CUDA_SUPPORT (dense_tracking.cpp:222-423):
+    denseTrackingCpu / computeDensePointCloudCpu semantics, executed on the GPU."""
+
+    def __init__(self, w, h, nlevels=3, device=-1):
+        self._h = C.c_void_p()
+        rc = lib().svs_dtc_create(device, w, h, nlevels, C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_dtc_create failed (no CUDA device, or a level size is not a multiple of 4)")
+        self.w, self.h, self.nlevels = w, h, nlevels
+
+    def close(self):
+        if self._h:
+            lib().svs_dtc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SvsError(rc, lib().svs_dtc_last_error(self._h).decode())
+
+    @staticmethod
+    def _cams(cams):
+        arr = (SvsCam * len(cams))()
+        for i, c in enumerate(cams):
+            arr[i] = SvsCam(*[float(x) for x in c[:4]])
+        return arr
+
+    def set_prev_u8(self, level, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        self._ck(lib().svs_dtc_set_prev_u8(self._h, level, img.ctypes.data, img.strides[0], 0))
+
+    def set_prev_u8_device(self, level, ptr, pitch):
+        self._ck(lib().svs_dtc_set_prev_u8(self._h, level, ptr, pitch, 1))
+
+    def set_cur(self, level, cur, dx, dy):
+        ims = [np.ascontiguousarray(x, np.float32) for x in (cur, dx, dy)]
+        self._ck(lib().svs_dtc_set_cur(self._h, level, ims[0].ctypes.data, ims[1].ctypes.data, ims[2].ctypes.data,
+                                       ims[0].shape[1], 0))
+
+    def set_cur_device(self, level, cur, dx, dy, stride):
+        self._ck(lib().svs_dtc_set_cur(self._h, level, cur, dx, dy, stride, 1))
+
+    def set_disparity(self, disp):
+        d = np.ascontiguousarray(disp, np.float32)
+        self._ck(lib().svs_dtc_set_disparity(self._h, d.ctypes.data_as(C.POINTER(C.c_float)), d.shape[1]))
+
+    def compute_point_cloud(self, T, cams):
+        T = np.ascontiguousarray(T, np.float64)
+        self._ck(lib().svs_computeDensePointCloudCpu(self._h, _dp(T), self._cams(cams)))
+
+    def point_cloud(self, level):
+        out = np.zeros(((self.h >> level) // 4, (self.w >> level) // 4, 4), np.float32)
+        self._ck(lib().svs_dtc_get_point_cloud(self._h, level, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def set_point_cloud(self, level, cloud):
+        c = np.ascontiguousarray(cloud, np.float32)
+        self._ck(lib().svs_dtc_set_point_cloud(self._h, level, c.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def track(self, T, cams):
+        T = np.array(T, np.float64).copy()
+        st = SvsDtStats()
+        self._ck(lib().svs_denseTrackingCpu(self._h, self._cams(cams), _dp(T), C.byref(st)))
+        return T, dict(chi2=list(st.chi2[:self.nlevels]), passes=list(st.passes[:self.nlevels]), ms_total=st.ms_total)
