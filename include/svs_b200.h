@@ -386,6 +386,23 @@ int svs_calcFastMotionOnly(svs_pose *h, int n, const int *obs_point_id, const do
 int svs_calcFastMotionOnly_matched(svs_pose *h, svs_matcher *m, const svs_cam *cam, const svs_pose_params *params,
                                    double T_frame[7], svs_pose_stats *stats);
 
+/* ------------------------------------------------------------------ pose-pose constraint weights
+ * ("next" row).  SlamGraph::computeConstraint (slam_graph.cpp:785-846) for a batch of pose
+ * pairs: T_1_from_2 = T_1 T_2^-1, n = number of points in both feature tables, median distance of those
+ * points in frame 1, Lambda = n diag((350 |t_12| / median)^2 I3, 100^2 I3) (row-major 6x6).
+ * Inputs: T_me_from_world[P][7]; the feature_table keys of every pose as CSR (feat_ptr[P+1], feat_point,
+ * strictly ascending per pose); for every point the index of its anchor pose and xyz_anchor.  Anchor frames
+ * outside the double window (computeAbsolutePose in the reference) are passed like any other pose.
+ * A pair without shared points gets Lambda = 0 and visibility_strength = 0. */
+typedef struct svs_constraints svs_constraints;
+int svs_constraints_create(int device, svs_constraints **out);
+void svs_constraints_destroy(svs_constraints *h);
+const char *svs_constraints_last_error(const svs_constraints *h);
+int svs_computeConstraint_batch(svs_constraints *h, int P, const double *T_me_from_world, const int *feat_ptr,
+                                const int *feat_point, int L, const int *point_anchor, const double *xyz_anchor,
+                                int npairs, const int *v1, const int *v2, double *T_1_from_2, double *Lambda,
+                                int *visibility_strength);
+
 /* Library/device info: writes "name;sm;SMs;..." into buf. */
 int svs_device_info(char *buf, int buflen);
 

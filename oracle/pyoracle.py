@@ -511,3 +511,23 @@ def dtc_track(levels, T):
     st = ODtStats()
     L.odtc_track(arr, len(levels), _dp(T), C.byref(st))
     return T, dict(chi2=list(st.chi2[:len(levels)]), passes=list(st.passes[:len(levels)]))
+
+
+# ---------------------------------------------------------------- pose-pose constraint weights (constraint_oracle.c)
+def compute_constraints(poses, feat_ptr, feat_point, point_anchor, xyz_anchor, v1, v2):
+    L = lib()
+    c_ip_ = C.POINTER(C.c_int)
+    L.occ_compute_constraints.argtypes = [C.c_int, c_dp, c_ip_, c_ip_, C.c_int, c_ip_, c_dp, C.c_int, c_ip_, c_ip_, c_dp, c_dp,
+                                          c_ip_]
+    L.occ_compute_constraints.restype = None
+    poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+    fp, fpt = np.ascontiguousarray(feat_ptr, np.int32), np.ascontiguousarray(feat_point, np.int32)
+    pa = np.ascontiguousarray(point_anchor, np.int32)
+    xyz = np.ascontiguousarray(xyz_anchor, np.float64).reshape(-1, 3)
+    v1, v2 = np.ascontiguousarray(v1, np.int32), np.ascontiguousarray(v2, np.int32)
+    n = len(v1)
+    T, Lam, ns = np.zeros((n, 7)), np.zeros((n, 36)), np.zeros(n, np.int32)
+    ip = lambda a: a.ctypes.data_as(c_ip_)
+    L.occ_compute_constraints(len(poses), _dp(poses), ip(fp), ip(fpt), len(pa), ip(pa), _dp(xyz), n, ip(v1), ip(v2), _dp(T),
+                              _dp(Lam), ip(ns))
+    return T, Lam.reshape(n, 6, 6), ns

@@ -124,6 +124,7 @@ EXPORTS = [
     "svs_dtc_create", "svs_dtc_destroy", "svs_dtc_last_error", "svs_dtc_set_prev_u8", "svs_dtc_set_cur",
     "svs_dtc_set_disparity", "svs_computeDensePointCloudCpu", "svs_dtc_get_point_cloud", "svs_dtc_set_point_cloud",
     "svs_denseTrackingCpu",
+    "svs_constraints_create", "svs_constraints_destroy", "svs_constraints_last_error", "svs_computeConstraint_batch",
 ]
 
 
@@ -201,6 +202,13 @@ def lib():
     L.svs_dt_set_images_device.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.svs_dt_swap_prev_cur.argtypes = [vp]
     L.svs_matcher_set_pyramid_device.argtypes = [vp, C.c_int, c_dp, C.POINTER(C.c_void_p), c_ip]
+    L.svs_constraints_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.svs_constraints_destroy.argtypes = [vp]
+    L.svs_constraints_destroy.restype = None
+    L.svs_constraints_last_error.argtypes = [vp]
+    L.svs_constraints_last_error.restype = C.c_char_p
+    L.svs_computeConstraint_batch.argtypes = [vp, C.c_int, c_dp, c_ip, c_ip, C.c_int, c_ip, c_dp, C.c_int, c_ip, c_ip,
+                                              c_dp, c_dp, c_ip]
     L.svs_dtc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.svs_dtc_destroy.argtypes = [vp]
     L.svs_dtc_destroy.restype = None
@@ -811,3 +819,39 @@ class DenseTrackerCpuVariant:
         st = SvsDtStats()
         self._ck(lib().svs_denseTrackingCpu(self._h, self._cams(cams), _dp(T), C.byref(st)))
         return T, dict(chi2=list(st.chi2[:self.nlevels]), passes=list(st.passes[:self.nlevels]), ms_total=st.ms_total)
+
+
+class ConstraintBuilder:
+    """SlamGraph::computeConstraint (reference slam_graph.cpp:785-846) for a batch of pose pairs."""
+
+    def __init__(self, device=-1):
+        self._h = C.c_void_p()
+        rc = lib().svs_constraints_create(device, C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_constraints_create failed (no CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().svs_constraints_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute(self, poses, feat_ptr, feat_point, point_anchor, xyz_anchor, v1, v2):
+        """Returns (T_1_from_2[n,7], Lambda[n,6,6], visibility_strength[n])."""
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        fp, fpt = np.ascontiguousarray(feat_ptr, np.int32), np.ascontiguousarray(feat_point, np.int32)
+        pa = np.ascontiguousarray(point_anchor, np.int32)
+        xyz = np.ascontiguousarray(xyz_anchor, np.float64).reshape(-1, 3)
+        v1, v2 = np.ascontiguousarray(v1, np.int32), np.ascontiguousarray(v2, np.int32)
+        n = len(v1)
+        T, Lam, ns = np.zeros((n, 7)), np.zeros((n, 36)), np.zeros(n, np.int32)
+        rc = lib().svs_computeConstraint_batch(self._h, len(poses), _dp(poses), _ip(fp), _ip(fpt), len(pa), _ip(pa), _dp(xyz),
+                                               n, _ip(v1), _ip(v2), _dp(T), _dp(Lam), _ip(ns))
+        if rc != 0:
+            raise SvsError(rc, lib().svs_constraints_last_error(self._h).decode())
+        return T, Lam.reshape(n, 6, 6), ns
