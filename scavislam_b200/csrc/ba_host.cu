@@ -26,6 +26,8 @@ struct svs_ba {
   cudaStream_t stream = nullptr;
   std::string err;
   bool has_problem = false;
+  double* d_raw = nullptr; double* h_raw = nullptr; size_t raw_cap = 0;   // user-order observations + weights (6 doubles per edge)
+  int host_threads = 4;  // OpenMP threads of the per-landmark host loops (SVS_HOST_THREADS)
   int cur_known = -1;   // host mirror of LmCtl::cur (index of the accepted state buffers), -1 = ask the device
   BaDev d{};
   // one device arena + one pinned staging arena, grown on demand and reused across set_problem calls
@@ -46,7 +48,8 @@ struct svs_ba {
   std::vector<int> w_eptr, w_eord, w_fill, w_anchor, w_K, w_order, w_lm_eptr, w_lm_sptr, w_lm_anchor, w_ie_pose, w_bucket;
   std::vector<unsigned char> w_self, w_lm_self, w_adj;
   std::vector<unsigned long long> w_key;
-  std::vector<double> w_obs, w_w, w_psi;
+  std::vector<double> w_psi;
+  std::vector<int> w_edge_src;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> tev;   // per-trial timing events
   // last optimize() settings
@@ -132,6 +135,9 @@ void free_problem(svs_ba* h) {
 void free_arena(svs_ba* h) {
   if (h->arena) cudaFree(h->arena);
   if (h->stage) cudaFreeHost(h->stage);
+  if (h->d_raw) cudaFree(h->d_raw);
+  if (h->h_raw) cudaFreeHost(h->h_raw);
+  h->d_raw = h->h_raw = nullptr; h->raw_cap = 0;
   h->arena = nullptr; h->stage = nullptr; h->arena_cap = h->stage_cap = 0;
 }
 
@@ -287,6 +293,7 @@ int svs_ba_create(const svs_ba_opts* opts, svs_ba** out) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SVS_ERR_NOGPU;
   svs_ba* h = new svs_ba();
   h->flags = opts ? opts->flags : 0;
+  if (const char* ht = getenv("SVS_HOST_THREADS")) h->host_threads = std::max(1, atoi(ht));
   int dev = opts ? opts->device : -1;
   if (dev < 0) cudaGetDevice(&dev);
   h->device = dev;
@@ -334,6 +341,8 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   CK(cudaStreamSynchronize(h->stream));   // the arena and the staging buffer are about to be reused
   free_problem(h);
   const bool host_timing = getenv("SVS_HOST_TIMING") != nullptr;
+  const int nthr = h->host_threads;
+  (void)nthr;
   auto tp0 = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
     if (!host_timing) return;
@@ -342,6 +351,33 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     tp0 = now;
   };
 
+  // ---- observations and weights go to the device in the caller's edge order NOW: the DMA runs under the
+  //      structure analysis below, and a gather kernel brings them into the internal order afterwards
+  if (E > 0) {
+    const size_t need = 6 * (size_t)E;
+    if (need > h->raw_cap) {
+      if (h->d_raw) cudaFree(h->d_raw);
+      if (h->h_raw) cudaFreeHost(h->h_raw);
+      h->d_raw = h->h_raw = nullptr; h->raw_cap = 0;
+      const size_t want = need + need / 4;
+      CK(cudaMalloc((void**)&h->d_raw, want * sizeof(double)));
+      CK(cudaMallocHost((void**)&h->h_raw, want * sizeof(double)));
+      h->raw_cap = want;
+    }
+    const size_t bytes = 3 * (size_t)E * sizeof(double);
+    const int parts = 4;
+#pragma omp parallel for num_threads(4)
+    for (int q = 0; q < 2 * parts; ++q) {
+      const char* src = reinterpret_cast<const char*>(q < parts ? e_obs : e_info);
+      char* dst = reinterpret_cast<char*>(h->h_raw) + (q < parts ? 0 : bytes);
+      const int qq = q % parts;
+      const size_t b0 = bytes * qq / parts, b1 = bytes * (qq + 1) / parts;
+      memcpy(dst + b0, src + b0, b1 - b0);
+    }
+    lap("raw memcpy");
+    CK(cudaMemcpyAsync(h->d_raw, h->h_raw, 2 * bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  lap("raw enqueue");
   // ---- group edges per landmark (counting sort), flat arrays only: this runs on the caller's
   //      thread inside the end-to-end time, like g2o's buildStructure does in the reference.
   //      Scratch lives in the handle; the per-landmark and per-edge loops use a few host threads.
@@ -357,7 +393,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   l_anchor.assign(L, -1); l_K.assign(L, 0); l_self.assign(L, 0); key.resize(L);
   int Kmax = 1;
   int bad = 0;
-#pragma omp parallel for schedule(static) reduction(max : Kmax) reduction(max : bad) num_threads(4) if (L > 4096)
+#pragma omp parallel for schedule(static) reduction(max : Kmax) reduction(max : bad) num_threads(nthr) if (L > 4096)
   for (int l = 0; l < L; ++l) {
     const int b = eptr[l], en = eptr[l + 1];
     key[l] = ~0ull;   // landmarks without observations go last
@@ -410,15 +446,15 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     cur.assign(bucket.begin(), bucket.end() - 1);
     for (int l = 0; l < L; ++l) order[cur[l_anchor[l] < 0 ? P : l_anchor[l]]++] = l;
   }
-#pragma omp parallel for schedule(dynamic, 16) num_threads(4) if (L > 4096)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthr) if (L > 4096)
   for (int a = 0; a <= P; ++a)
     std::sort(order.begin() + bucket[a], order.begin() + bucket[a + 1],
               [&](int x, int y) { return key[x] != key[y] ? key[x] < key[y] : x < y; });
   h->lm_to_user = order;
   auto& lm_eptr = h->w_lm_eptr; auto& lm_sptr = h->w_lm_sptr; auto& lm_anchor = h->w_lm_anchor; auto& ie_pose = h->w_ie_pose;
-  auto& lm_self = h->w_lm_self; auto& ie_obs = h->w_obs; auto& ie_w = h->w_w; auto& ipsi = h->w_psi;
+  auto& lm_self = h->w_lm_self; auto& edge_src = h->w_edge_src; auto& ipsi = h->w_psi;
   lm_eptr.assign(L + 1, 0); lm_sptr.assign(L + 1, 0); lm_anchor.assign(L, 0); ie_pose.resize(E);
-  lm_self.assign(L, 0); ie_obs.resize(3 * (size_t)E); ie_w.resize(3 * (size_t)E); ipsi.resize(3 * (size_t)L);
+  lm_self.assign(L, 0); edge_src.assign(E, 0); ipsi.resize(3 * (size_t)L);
   for (int li = 0; li < L; ++li) {
     const int l = order[li];
     lm_eptr[li + 1] = lm_eptr[li] + (eptr[l + 1] - eptr[l]);
@@ -426,7 +462,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   }
   const int ne = lm_eptr[L], ns = lm_sptr[L];
   (void)ne;
-#pragma omp parallel for schedule(static) num_threads(4) if (L > 4096)
+#pragma omp parallel for schedule(static) num_threads(nthr) if (L > 4096)
   for (int li = 0; li < L; ++li) {
     const int l = order[li];
     for (int q = 0; q < 3; ++q) ipsi[3 * (size_t)li + q] = psi[3 * (size_t)l + q];
@@ -436,10 +472,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     for (int k = eptr[l]; k < eptr[l + 1]; ++k, ++at) {
       const int e = eord[k];
       ie_pose[at] = e_pose[e];
-      for (int q = 0; q < 3; ++q) {
-        ie_obs[(size_t)q * E + at] = e_obs[3 * (size_t)e + q];
-        ie_w[(size_t)q * E + at] = e_info[3 * (size_t)e + q];
-      }
+      edge_src[at] = e;   // the doubles follow on the device (k_regroup)
     }
   }
   // ---- work lists of the fused kernel: runs of landmarks with identical slot lists (<= 8 frames)
@@ -478,7 +511,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     auto& A = h->w_adj;
     A.assign((size_t)P * P, 0);
     // (concurrent writers only ever store 1 into a byte: benign)
-#pragma omp parallel for schedule(static) num_threads(4) if (L > 4096)
+#pragma omp parallel for schedule(static) num_threads(nthr) if (L > 4096)
     for (int l = 0; l < L; ++l) {
       if (l_anchor[l] < 0) continue;
       int ps[kMaxTrack + 1];
@@ -546,7 +579,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     h->arena_off = 0;
 #define UP(field, vec) dev_upload(h, &d.field, vec)
     UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self);
-    UP(e_pose, ie_pose); UP(e_obs, ie_obs); UP(e_w, ie_w);
+    UP(e_pose, ie_pose); UP(edge_src, edge_src);
     UP(task_lm, task_lm); UP(task_cnt, task_cnt); UP(gen_lm, gen_lm);
     UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
     UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab); UP(urg_dst, sy.urg_dst);
@@ -559,6 +592,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
     upload_bytes = h->arena_off;
 #define AL(field, n) dev_alloc(h, &d.field, (size_t)(n))
     for (int b = 0; b < 2; ++b) { AL(pose[b], 7 * (size_t)P); AL(Rt[b], 12 * (size_t)P); AL(psi[b], 3 * (size_t)L); }
+    AL(e_obs_w, 3 * (size_t)E); AL(e_w_w, 3 * (size_t)E);
     AL(W, 18 * (size_t)ns); AL(Dbl, 12 * (size_t)L); AL(chi_l, L); AL(chi_new_l, L); AL(scale_l, L);
     AL(S, 36 * (size_t)sy.nblk); AL(bp, 6 * (size_t)P); AL(bc, 6 * (size_t)P); AL(x, 6 * (size_t)P);
     AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
@@ -576,6 +610,8 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   h->d_pose0 = const_cast<double*>(d_pose0c);
   h->d_psi0 = const_cast<double*>(d_psi0c);
   CK(cudaMemcpyAsync(h->arena, h->stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
+  d.e_obs = d.e_obs_w; d.e_w = d.e_w_w;
+  launch_regroup(d, h->d_raw, h->stream);   // [3][E] internal order <- [E][3] user order
   CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
   h->max_col_blocks = sy.max_col_sep; h->max_col_branch = sy.max_col_branch;
   d.nbranch = h->nbranch;

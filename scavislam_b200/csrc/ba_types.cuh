@@ -51,6 +51,8 @@ struct BaDev {
   int ntasks, ngen;
   // edges (internal order)
   const int* e_pose;    // [E]
+  const int* edge_src;  // internal edge -> index in the caller's arrays
+  double* e_obs_w; double* e_w_w;   // writable views of e_obs / e_w (filled by k_regroup)
   const double* e_obs;  // [3][E]
   const double* e_w;    // [3][E] diagonal of Lambda
   // per-trial products of the fused kernel

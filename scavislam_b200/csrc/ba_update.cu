@@ -275,6 +275,25 @@ __global__ void k_prep(BaDev d, int buf) {
   d.Rt[buf][12 * (size_t)p + 11] = T[6];
 }
 
+// ------------------------------------------------------------------ k_regroup: user edge order -> internal SoA
+// raw = [E][3] observations followed by [E][3] weights as the caller passed them; the internal order groups
+// the edges of a landmark (set_problem), stored [3][E] so that a wave of edges reads coalesced
+__global__ void k_regroup(BaDev d, const double* __restrict__ raw) {
+  const int at = blockIdx.x * blockDim.x + threadIdx.x;
+  if (at >= d.E) return;
+  const size_t e = (size_t)d.edge_src[at];
+  const double* o = raw + 3 * e;
+  const double* w = raw + 3 * (size_t)d.E + 3 * e;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    d.e_obs_w[(size_t)q * d.E + at] = o[q];
+    d.e_w_w[(size_t)q * d.E + at] = w[q];
+  }
+}
+void launch_regroup(const BaDev& d, const double* raw, cudaStream_t st) {
+  if (d.E > 0) k_regroup<<<(d.E + 255) / 256, 256, 0, st>>>(d, raw);
+}
+
 void launch_prep(const BaDev& d, int buf, cudaStream_t st) {
   if (d.P == 0) return;
   k_prep<<<(d.P + 127) / 128, 128, 0, st>>>(d, buf);

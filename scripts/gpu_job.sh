@@ -1,3 +1,3 @@
 #!/bin/bash
 cd /root/repo
-timeout 600 python -m pytest tests/test_constraint_gpu.py -x -q 2>&1 | tail -25
+SVS_HOST_TIMING=1 python scripts/dev_e2e.py 2>&1 | tail -10
