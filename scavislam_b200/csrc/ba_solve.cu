@@ -3,18 +3,22 @@
 //   replaces g2o::LinearSolverCSparse<Matrix6d>::solve (instantiated at slam_graph.cpp:55-60) and
 //   G2oVertexSE3::oplusImpl (anchored_points.cpp:53-58).
 //
-// The factor is a latency chain of P block columns.  What bounds it is the dependent chain per
-// column (6 pivots: rsqrt -> mul -> fma), two CTA barriers and shared-memory round trips -- not
-// HBM and not the tensor cores (6x6 blocks, FP64).  So the design removes everything else from
-// that chain:
-//   * blocks live in a shared-memory ring that covers the next `cap` blocks in column-major
-//     order (the whole band of a SLAM window); trailing updates are shared-memory RMWs,
-//     blocks outside the ring (far fill) fall back to global RMWs;
-//   * ring refills are LDGSTS (cp.async) issued after a column's update and only waited for
-//     before the next column's update, so they fly under the pivot chain;
-//   * each thread that owns a panel row factors the 6x6 diagonal block redundantly in
-//     registers (no warp-cooperative pivoting, no divisions: rsqrt + multiplies);
-//   * the right-hand side rides along as one more row of the panel (forward solve for free).
+// The factor is a latency chain of P block columns.  What bounds it is not HBM and not the tensor
+// cores (6x6 blocks, FP64) but the instruction latency of the three things a column step waits for --
+// the pivot chain (6 pivots: rsqrt -> mul -> fma), the part of the update that lands in the next
+// column, and the rest of the trailing update -- plus two barriers.  The design:
+//   * blocks live in a shared-memory ring that covers the next `cap` blocks in column-major order
+//     (the whole band of a SLAM window); trailing updates are shared-memory RMWs, blocks outside the
+//     ring (far fill) fall back to global RMWs; ring refills are LDGSTS (cp.async) every few columns;
+//   * look-ahead: panel warps factor column j+1 while update warps apply column j's trailing update
+//     in quarter-block units (at most one per thread), read from a list staged in shared memory;
+//   * the diagonal block is updated by 21 lanes and factored redundantly in registers by every lane of
+//     the chain warp (no shuffles or shared-memory round trips between pivots; rsqrt + multiplies);
+//   * warp roles follow the schedulers (warp % 4): the chain warp shares its scheduler with the
+//     least loaded update warp (scripts/ubench/chol.cu, fp64_lanes.cu);
+//   * two teams factor the window from both ends concurrently and meet in a separator;
+//   * the right-hand side rides along as one more row of the panel (forward solve for free); the
+//     backward solve streams the transposed factor back through the ring.
 #include "ba_dev.cuh"
 #include "ba_kernels.cuh"
 
@@ -28,46 +32,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-// Lower Cholesky of a symmetric 6x6 (lower triangle read from `A`, row-major, lambda added to
-// the diagonal) and the inverse of the factor, all in registers.  l[], li[] are packed lower
-// triangles (index r*(r+1)/2 + c).  Returns false when a pivot is not positive.
-__device__ __forceinline__ bool chol6_regs(const double* __restrict__ A, double dlam, double l[21], double li[21]) {
-  double a[21];
-#pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = 0; c <= r; ++c) a[r * (r + 1) / 2 + c] = A[r * 6 + c] + (r == c ? dlam : 0.);
-  bool ok = true;
-  double rinv[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    const double dv = a[c * (c + 1) / 2 + c];
-    ok = ok && (dv > 0.);
-    rinv[c] = rsqrt(dv);
-    l[c * (c + 1) / 2 + c] = dv * rinv[c];
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r) l[r * (r + 1) / 2 + c] = a[r * (r + 1) / 2 + c] * rinv[c];
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r)
-#pragma unroll
-      for (int c2 = c + 1; c2 <= r; ++c2)
-        a[r * (r + 1) / 2 + c2] -= l[r * (r + 1) / 2 + c] * l[c2 * (c2 + 1) / 2 + c];
-  }
-  // inverse of the lower-triangular factor, column by column
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    li[c * (c + 1) / 2 + c] = rinv[c];
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r) {
-      double v = 0.;
-#pragma unroll
-      for (int q = c; q < r; ++q) v -= l[r * (r + 1) / 2 + q] * li[q * (q + 1) / 2 + c];
-      li[r * (r + 1) / 2 + c] = v * rinv[r];
-    }
-  }
-  return ok;
-}
 
 constexpr int kUpdStage = 128;    // update-list entries of a column staged in shared memory one column ahead
 constexpr int kMaxTeams = 4;      // independent branches of the elimination tree factored concurrently
