@@ -403,6 +403,32 @@ int svs_computeConstraint_batch(svs_constraints *h, int P, const double *T_me_fr
                                 int npairs, const int *v1, const int *v2, double *T_1_from_2, double *Lambda,
                                 int *visibility_strength);
 
+/* ------------------------------------------------------------------ device-resident map and window assembly
+ * ("next" row).  The part of SlamGraph the optimiser reads (slam_graph.hpp:65-137) kept in device
+ * memory -- vertices with T_me_from_world, points with anchorframe_id / xyz_anchor, observations as CSR per point
+ * (vis_set order: vertex, feature centre (u, v, u_right) at level 0, pyramid level) -- and copyDataToG2o /
+ * copyPosesToG2o / addPointToG2o / addObsToG2o (slam_graph.cpp:907-1032) as kernels: for the double window
+ * `window_vertex` (BA pose i = vertex window_vertex[i]) and the active points (BA point l = map point
+ * active_point[l]) every observation whose frame is in the window becomes an edge, in the reference's order;
+ * psi = invert_depth(xyz_anchor), Lambda = diag(s, s, 0.333^2) with s = (2^-level)^2.  Observations and weights
+ * never leave the device; only the index triples return to the host for the structure analysis.
+ * Pose-pose constraints are passed as for svs_ba_set_problem (indices into the window). */
+typedef struct svs_map svs_map;
+int svs_map_create(int device, svs_map **out);
+void svs_map_destroy(svs_map *h);
+const char *svs_map_last_error(const svs_map *h);
+int svs_map_set(svs_map *h, int V, const double *T_me_from_world, int Np, const int *point_anchor,
+                const double *xyz_anchor, const int *vis_ptr, const int *vis_pose, const double *feat_center,
+                const int *feat_level);
+/* restoreDataFromG2o's counterpart for the map: overwrite the poses of n vertices */
+int svs_map_update_poses(svs_map *h, int n, const int *vertex, const double *T_me_from_world);
+/* = svs_ba_set_problem on the window assembled from the map; *num_edges receives E */
+int svs_ba_set_problem_from_map(svs_ba *ba, svs_map *map, int P, const int *window_vertex, const unsigned char *fixed,
+                                int L, const int *active_point, int C, const int *c_i, const int *c_j,
+                                const double *c_T_ji, const double *c_Lambda, const svs_cam *cam, int *num_edges);
+/* the edge list of the last assembly (any output may be NULL); E must equal *num_edges */
+int svs_map_last_edges(svs_map *h, int E, int *e_point, int *e_pose, int *e_anchor, double *e_obs, double *e_info);
+
 /* Library/device info: writes "name;sm;SMs;..." into buf. */
 int svs_device_info(char *buf, int buflen);
 

@@ -531,3 +531,27 @@ def compute_constraints(poses, feat_ptr, feat_point, point_anchor, xyz_anchor, v
     L.occ_compute_constraints(len(poses), _dp(poses), ip(fp), ip(fpt), len(pa), ip(pa), _dp(xyz), n, ip(v1), ip(v2), _dp(T),
                               _dp(Lam), ip(ns))
     return T, Lam.reshape(n, 6, 6), ns
+
+
+# ---------------------------------------------------------------- window assembly (plain Python restatement)
+def copy_data_to_g2o(m, window_vertex, active_point):
+    """SlamGraph::copyDataToG2o / copyPosesToG2o / addPointToG2o / addObsToG2o (reference slam_graph.cpp:907-1032,
+    slam_graph-impl.cpp:29-126) on the tables of scavislam_b200.synth_graph.make_map: returns dict(pose_qt, psi,
+    e_point, e_pose, e_anchor, e_obs, e_info).  TEST INFRASTRUCTURE ONLY."""
+    win = {int(v): i for i, v in enumerate(window_vertex)}
+    pose_qt = np.array([m["poses"][v] for v in window_vertex], np.float64)
+    psi, ep, es, ea, obs, info = [], [], [], [], [], []
+    for l, p in enumerate(active_point):
+        x, y, z = m["xyz_anchor"][p]
+        psi.append([x / z, y / z, 1.0 / z])                       # invert_depth (maths_utils.h:66-69)
+        a = win[int(m["point_anchor"][p])]
+        for i in range(m["vis_ptr"][p], m["vis_ptr"][p + 1]):     # for pose_id in p.vis_set (ascending ids)
+            v = int(m["vis_pose"][i])
+            if v not in win:                                       # :1004-1005
+                continue
+            s = (1.0 / (1 << int(m["feat_level"][i]))) ** 2        # Po2(pyrFromZero_d(1., level)), :1010-1015
+            ep.append(l); es.append(win[v]); ea.append(a)
+            obs.append(m["feat_center"][i]); info.append([s, s, 0.333 * 0.333])
+    return dict(pose_qt=pose_qt, psi=np.array(psi, np.float64).reshape(-1, 3), e_point=np.array(ep, np.int32),
+                e_pose=np.array(es, np.int32), e_anchor=np.array(ea, np.int32),
+                e_obs=np.array(obs, np.float64).reshape(-1, 3), e_info=np.array(info, np.float64).reshape(-1, 3))

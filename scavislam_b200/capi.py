@@ -125,6 +125,8 @@ EXPORTS = [
     "svs_dtc_set_disparity", "svs_computeDensePointCloudCpu", "svs_dtc_get_point_cloud", "svs_dtc_set_point_cloud",
     "svs_denseTrackingCpu",
     "svs_constraints_create", "svs_constraints_destroy", "svs_constraints_last_error", "svs_computeConstraint_batch",
+    "svs_map_create", "svs_map_destroy", "svs_map_last_error", "svs_map_set", "svs_map_update_poses",
+    "svs_ba_set_problem_from_map", "svs_map_last_edges",
 ]
 
 
@@ -202,6 +204,16 @@ def lib():
     L.svs_dt_set_images_device.argtypes = [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.svs_dt_swap_prev_cur.argtypes = [vp]
     L.svs_matcher_set_pyramid_device.argtypes = [vp, C.c_int, c_dp, C.POINTER(C.c_void_p), c_ip]
+    L.svs_map_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.svs_map_destroy.argtypes = [vp]
+    L.svs_map_destroy.restype = None
+    L.svs_map_last_error.argtypes = [vp]
+    L.svs_map_last_error.restype = C.c_char_p
+    L.svs_map_set.argtypes = [vp, C.c_int, c_dp, C.c_int, c_ip, c_dp, c_ip, c_ip, c_dp, c_ip]
+    L.svs_map_update_poses.argtypes = [vp, C.c_int, c_ip, c_dp]
+    L.svs_ba_set_problem_from_map.argtypes = [vp, vp, C.c_int, c_ip, c_up, C.c_int, c_ip, C.c_int, c_ip, c_ip, c_dp, c_dp,
+                                              C.POINTER(SvsCam), c_ip]
+    L.svs_map_last_edges.argtypes = [vp, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp]
     L.svs_constraints_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.svs_constraints_destroy.argtypes = [vp]
     L.svs_constraints_destroy.restype = None
@@ -855,3 +867,66 @@ class ConstraintBuilder:
         if rc != 0:
             raise SvsError(rc, lib().svs_constraints_last_error(self._h).decode())
         return T, Lam.reshape(n, 6, 6), ns
+
+
+class DeviceMap:
+    """The part of SlamGraph the optimiser reads, kept on the device (reference slam_graph.hpp:65-137), and
+    copyDataToG2o (slam_graph.cpp:985-1032) as kernels feeding a BundleAdjuster."""
+
+    def __init__(self, device=-1):
+        self._h = C.c_void_p()
+        rc = lib().svs_map_create(device, C.byref(self._h))
+        if rc != 0:
+            raise SvsError(rc, "svs_map_create failed (no CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().svs_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SvsError(rc, lib().svs_map_last_error(self._h).decode())
+
+    def set(self, poses, point_anchor, xyz_anchor, vis_ptr, vis_pose, feat_center, feat_level):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        pa = np.ascontiguousarray(point_anchor, np.int32)
+        xyz = np.ascontiguousarray(xyz_anchor, np.float64).reshape(-1, 3)
+        vp_, vs = np.ascontiguousarray(vis_ptr, np.int32), np.ascontiguousarray(vis_pose, np.int32)
+        cen = np.ascontiguousarray(feat_center, np.float64).reshape(-1, 3)
+        lvl = np.ascontiguousarray(feat_level, np.int32)
+        self._ck(lib().svs_map_set(self._h, len(poses), _dp(poses), len(pa), _ip(pa), _dp(xyz), _ip(vp_), _ip(vs), _dp(cen),
+                                   _ip(lvl)))
+
+    def update_poses(self, vertex, poses):
+        v = np.ascontiguousarray(vertex, np.int32)
+        T = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        self._ck(lib().svs_map_update_poses(self._h, len(v), _ip(v), _dp(T)))
+
+    def set_problem(self, ba, window_vertex, active_point, cam, fixed=None, c_i=(), c_j=(), c_T=None, c_Lambda=None):
+        """Assembles the window on the device and loads it into `ba` (a BundleAdjuster).  Returns E."""
+        win = np.ascontiguousarray(window_vertex, np.int32)
+        act = np.ascontiguousarray(active_point, np.int32)
+        fx = None if fixed is None else np.ascontiguousarray(fixed, np.uint8)
+        ci, cj = np.ascontiguousarray(c_i, np.int32), np.ascontiguousarray(c_j, np.int32)
+        cT = np.zeros((0, 7)) if c_T is None else np.ascontiguousarray(c_T, np.float64)
+        cL = np.zeros((0, 36)) if c_Lambda is None else np.ascontiguousarray(c_Lambda, np.float64)
+        cm = SvsCam(*[float(x) for x in cam])
+        E = C.c_int()
+        self._ck(lib().svs_ba_set_problem_from_map(ba._h, self._h, len(win), _ip(win),
+                                                   None if fx is None else fx.ctypes.data_as(c_up), len(act), _ip(act),
+                                                   len(ci), _ip(ci), _ip(cj), _dp(cT), _dp(cL), C.byref(cm), C.byref(E)))
+        ba.P, ba.L = len(win), len(act)
+        return E.value
+
+    def last_edges(self, E):
+        ep, es, ea = np.zeros(E, np.int32), np.zeros(E, np.int32), np.zeros(E, np.int32)
+        obs, info = np.zeros((E, 3)), np.zeros((E, 3))
+        self._ck(lib().svs_map_last_edges(self._h, E, _ip(ep), _ip(es), _ip(ea), _dp(obs), _dp(info)))
+        return ep, es, ea, obs, info

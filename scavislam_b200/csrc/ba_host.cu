@@ -322,13 +322,15 @@ void svs_ba_destroy(svs_ba* h) {
 
 const char* svs_last_error(const svs_ba* h) { return h ? h->err.c_str() : "null handle"; }
 
-int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char* fixed, int L, const double* psi,
-                       int E, const int* e_point, const int* e_pose, const int* e_anchor, const double* e_obs,
-                       const double* e_info, int C, const int* c_i, const int* c_j, const double* c_T,
-                       const double* c_Lambda, const svs_cam* cam) {
+// d_obs_info != nullptr: the observations [E][3] followed by the weights [E][3] already lie on this device in
+// the caller's edge order (assembled there, svs_ba_set_problem_from_map) and e_obs / e_info are not read.
+static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned char* fixed, int L, const double* psi,
+                            int E, const int* e_point, const int* e_pose, const int* e_anchor, const double* e_obs,
+                            const double* e_info, int C, const int* c_i, const int* c_j, const double* c_T,
+                            const double* c_Lambda, const svs_cam* cam, const double* d_obs_info) {
   if (!h) return SVS_ERR_INVALID;
   if (P < 0 || L < 0 || E < 0 || C < 0 || !cam) return fail(h, SVS_ERR_INVALID, "negative size or null camera");
-  if ((P && !T_qt) || (L && !psi) || (E && (!e_point || !e_pose || !e_anchor || !e_obs || !e_info)) ||
+  if ((P && !T_qt) || (L && !psi) || (E && (!e_point || !e_pose || !e_anchor || (!d_obs_info && (!e_obs || !e_info)))) ||
       (C && (!c_i || !c_j || !c_T || !c_Lambda)))
     return fail(h, SVS_ERR_INVALID, "null array");
   for (int e = 0; e < E; ++e)
@@ -353,7 +355,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
 
   // ---- observations and weights go to the device in the caller's edge order NOW: the DMA runs under the
   //      structure analysis below, and a gather kernel brings them into the internal order afterwards
-  if (E > 0) {
+  if (E > 0 && !d_obs_info) {
     const size_t need = 6 * (size_t)E;
     if (need > h->raw_cap) {
       if (h->d_raw) cudaFree(h->d_raw);
@@ -611,7 +613,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   h->d_psi0 = const_cast<double*>(d_psi0c);
   CK(cudaMemcpyAsync(h->arena, h->stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
   d.e_obs = d.e_obs_w; d.e_w = d.e_w_w;
-  launch_regroup(d, h->d_raw, h->stream);   // [3][E] internal order <- [E][3] user order
+  launch_regroup(d, d_obs_info ? d_obs_info : h->d_raw, h->stream);   // [3][E] internal order <- [E][3] user order
   CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
   h->max_col_blocks = sy.max_col_sep; h->max_col_branch = sy.max_col_branch;
   d.nbranch = h->nbranch;
@@ -623,6 +625,14 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
   h->C_edges = C;
   h->has_problem = true;
   return svs_ba_reset_state(h);
+}
+
+int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char* fixed, int L, const double* psi,
+                       int E, const int* e_point, const int* e_pose, const int* e_anchor, const double* e_obs,
+                       const double* e_info, int C, const int* c_i, const int* c_j, const double* c_T,
+                       const double* c_Lambda, const svs_cam* cam) {
+  return set_problem_impl(h, P, T_qt, fixed, L, psi, E, e_point, e_pose, e_anchor, e_obs, e_info, C, c_i, c_j, c_T, c_Lambda,
+                          cam, nullptr);
 }
 
 int svs_ba_reset_state(svs_ba* h) {
@@ -979,3 +989,17 @@ int svs_ba_lm_stats(svs_ba* h, svs_ba_stats* st) {
 }
 
 }  // extern "C"
+
+// ---- hooks for the other modules of the library (internal.cuh)
+namespace svs {
+int ba_set_problem_device_obs(svs_ba* h, int P, const double* T_qt, const unsigned char* fixed, int L, const double* psi, int E,
+                              const int* e_point, const int* e_pose, const int* e_anchor, const double* d_obs_info, int C,
+                              const int* c_i, const int* c_j, const double* c_T, const double* c_Lambda, const svs_cam* cam) {
+  const int rc = set_problem_impl(h, P, T_qt, fixed, L, psi, E, e_point, e_pose, e_anchor, nullptr, nullptr, C, c_i, c_j, c_T,
+                                  c_Lambda, cam, d_obs_info);
+  if (rc == SVS_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) return SVS_ERR_CUDA;   // d_obs_info may be reused now
+  return rc;
+}
+int ba_device(const svs_ba* h) { return h->device; }
+}  // namespace svs
+

@@ -1,0 +1,316 @@
+// graph.cu -- the SLAM map kept on the device and the assembly of a double-window problem from it
+// (a "next" row): SlamGraph::copyDataToG2o / copyPosesToG2o / addPointToG2o /
+// addObsToG2o (scavislam/slam_graph.cpp:907-1032, slam_graph-impl.cpp:29-126) without the O(E) walk over
+// hash maps on the host: vertices (T_me_from_world), points (anchorframe_id, xyz_anchor) and the
+// observations (vis_set + feature_table: centre and pyramid level) live in device memory; a window is
+// assembled by three kernels (count the visible poses of every active point that lie in the window,
+// exclusive scan, emit the edges in the reference's order: active points in list order, vis_set order inside)
+// and handed to the bundle adjuster where it lies -- only the edge index triples come back to the host,
+// for the structure analysis of svs_ba_set_problem.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/svs_b200.h"
+#include "internal.cuh"
+
+namespace {
+
+struct MapDev {
+  int V, Np;
+  const double* pose;       // [V][7]
+  const int* anchor;        // [Np] vertex index
+  const double* xyz;        // [Np][3]
+  const int* vis_ptr;       // [Np+1]
+  const int* vis_pose;      // [nnz] vertex index
+  const double* center;     // [nnz][3]  (u, v, u_right) at level 0
+  const int* level;         // [nnz]
+};
+
+// edges of active point l = observations whose pose is in the window (slam_graph.cpp:1001-1027)
+__global__ void k_count(MapDev m, const int* __restrict__ win_pos, const int* __restrict__ active, int L, int* __restrict__ cnt,
+                        int* __restrict__ bad) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const int p = active[l];
+  if (win_pos[m.anchor[p]] < 0) atomicAdd(bad, 1);   // the anchor frame must be a vertex of the problem
+  int c = 0;
+  for (int i = m.vis_ptr[p]; i < m.vis_ptr[p + 1]; ++i) c += win_pos[m.vis_pose[i]] >= 0;
+  cnt[l] = c;
+}
+
+// single-CTA exclusive scan (L is a few 10^4..10^5)
+__global__ void k_scan(const int* __restrict__ cnt, int L, int* __restrict__ ptr) {
+  __shared__ int sw[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < L; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < L ? cnt[i] : 0;
+    int s = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if ((threadIdx.x & 31) >= o) s += t; }
+    if ((threadIdx.x & 31) == 31) sw[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = threadIdx.x < (blockDim.x >> 5) ? sw[threadIdx.x] : 0;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += t; }
+      sw[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int before = (threadIdx.x >> 5) ? sw[(threadIdx.x >> 5) - 1] : 0;
+    if (i < L) ptr[i] = carry + before + s - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += before + s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ptr[L] = carry;
+}
+
+__global__ void k_emit(MapDev m, const int* __restrict__ win_pos, const int* __restrict__ active, int L,
+                       const int* __restrict__ ptr, int E, int* __restrict__ e_point, int* __restrict__ e_pose,
+                       int* __restrict__ e_anchor, double* __restrict__ obs_info, double* __restrict__ psi) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const int p = active[l];
+  {   // addPointToG2o: psi = invert_depth(xyz_anchor) (slam_graph.cpp:907-920, maths_utils.h:66-69)
+    const double x = m.xyz[3 * (size_t)p], y = m.xyz[3 * (size_t)p + 1], z = m.xyz[3 * (size_t)p + 2];
+    psi[3 * (size_t)l] = x / z; psi[3 * (size_t)l + 1] = y / z; psi[3 * (size_t)l + 2] = 1. / z;
+  }
+  const int a = win_pos[m.anchor[p]];
+  int at = ptr[l];
+  for (int i = m.vis_ptr[p]; i < m.vis_ptr[p + 1]; ++i) {
+    const int w = win_pos[m.vis_pose[i]];
+    if (w < 0) continue;
+    e_point[at] = l; e_pose[at] = w; e_anchor[at] = a;
+    double* o = obs_info + 3 * (size_t)at;
+    o[0] = m.center[3 * (size_t)i]; o[1] = m.center[3 * (size_t)i + 1]; o[2] = m.center[3 * (size_t)i + 2];
+    // Lambda = diag(s, s, 0.333^2), s = (2^-level)^2 (slam_graph.cpp:1010-1015)
+    const double f = 1. / (double)(1 << m.level[i]), s = f * f;
+    double* wq = obs_info + 3 * (size_t)E + 3 * (size_t)at;
+    wq[0] = s; wq[1] = s; wq[2] = 0.333 * 0.333;
+    ++at;
+  }
+}
+
+__global__ void k_gather_poses(MapDev m, const int* __restrict__ window, int P, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 7 * P) return;
+  out[i] = m.pose[7 * (size_t)window[i / 7] + i % 7];
+}
+
+}  // namespace
+
+struct svs_map {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int V = 0, Np = 0, nnz = 0;
+  char* d_map = nullptr; size_t map_cap = 0;
+  MapDev m{};
+  char* d_work = nullptr; size_t work_cap = 0;
+  std::vector<int> h_ep, h_es, h_ea, h_winpos;
+  std::vector<double> h_pose, h_psi;
+  const double* d_oi_last = nullptr;   // [E][3] observations, [E][3] weights of the last assembly
+  int last_E = 0;
+};
+
+#define GCK(call)                                                       \
+  do {                                                                  \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess) {                                            \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+      return SVS_ERR_CUDA;                                              \
+    }                                                                   \
+  } while (0)
+
+static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" {
+
+int svs_map_create(int device, svs_map** out) {
+  if (!out) return SVS_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SVS_ERR_NOGPU;
+  svs_map* h = new svs_map();
+  if (device < 0) cudaGetDevice(&device);
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return SVS_ERR_CUDA;
+  }
+  *out = h;
+  return SVS_OK;
+}
+
+void svs_map_destroy(svs_map* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_map); cudaFree(h->d_work);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* svs_map_last_error(const svs_map* h) { return h ? h->err.c_str() : "null handle"; }
+
+int svs_map_set(svs_map* h, int V, const double* T_me_from_world, int Np, const int* point_anchor, const double* xyz_anchor,
+                const int* vis_ptr, const int* vis_pose, const double* feat_center, const int* feat_level) {
+  if (!h || V <= 0 || Np < 0 || !T_me_from_world || (Np && (!point_anchor || !xyz_anchor || !vis_ptr))) return SVS_ERR_INVALID;
+  const int nnz = Np ? vis_ptr[Np] : 0;
+  if (nnz < 0 || (nnz && (!vis_pose || !feat_center || !feat_level))) return SVS_ERR_INVALID;
+  for (int p = 0; p < Np; ++p) {
+    if (point_anchor[p] < 0 || point_anchor[p] >= V) { h->err = "point anchored in a vertex outside [0, V)"; return SVS_ERR_INVALID; }
+    if (vis_ptr[p + 1] < vis_ptr[p]) { h->err = "vis_ptr not ascending"; return SVS_ERR_INVALID; }
+  }
+  for (int i = 0; i < nnz; ++i)
+    if (vis_pose[i] < 0 || vis_pose[i] >= V || feat_level[i] < 0 || feat_level[i] > 30) {
+      h->err = "observation names a vertex outside [0, V) or a bad pyramid level";
+      return SVS_ERR_INVALID;
+    }
+  cudaSetDevice(h->device);
+  size_t off = 0;
+  const size_t o_pose = off; off += al256(sizeof(double) * 7 * (size_t)V);
+  const size_t o_anch = off; off += al256(sizeof(int) * (size_t)std::max(Np, 1));
+  const size_t o_xyz = off; off += al256(sizeof(double) * 3 * (size_t)std::max(Np, 1));
+  const size_t o_vptr = off; off += al256(sizeof(int) * ((size_t)Np + 1));
+  const size_t o_vpose = off; off += al256(sizeof(int) * (size_t)std::max(nnz, 1));
+  const size_t o_cen = off; off += al256(sizeof(double) * 3 * (size_t)std::max(nnz, 1));
+  const size_t o_lvl = off; off += al256(sizeof(int) * (size_t)std::max(nnz, 1));
+  GCK(cudaStreamSynchronize(h->stream));
+  if (off > h->map_cap) {
+    cudaFree(h->d_map); h->d_map = nullptr; h->map_cap = 0;
+    GCK(cudaMalloc(&h->d_map, off + off / 4));
+    h->map_cap = off + off / 4;
+  }
+  char* B = h->d_map;
+  GCK(cudaMemcpyAsync(B + o_pose, T_me_from_world, sizeof(double) * 7 * (size_t)V, cudaMemcpyHostToDevice, h->stream));
+  if (Np) {
+    GCK(cudaMemcpyAsync(B + o_anch, point_anchor, sizeof(int) * (size_t)Np, cudaMemcpyHostToDevice, h->stream));
+    GCK(cudaMemcpyAsync(B + o_xyz, xyz_anchor, sizeof(double) * 3 * (size_t)Np, cudaMemcpyHostToDevice, h->stream));
+    GCK(cudaMemcpyAsync(B + o_vptr, vis_ptr, sizeof(int) * ((size_t)Np + 1), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (nnz) {
+    GCK(cudaMemcpyAsync(B + o_vpose, vis_pose, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    GCK(cudaMemcpyAsync(B + o_cen, feat_center, sizeof(double) * 3 * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    GCK(cudaMemcpyAsync(B + o_lvl, feat_level, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+  }
+  GCK(cudaStreamSynchronize(h->stream));
+  h->V = V; h->Np = Np; h->nnz = nnz;
+  h->m.V = V; h->m.Np = Np;
+  h->m.pose = reinterpret_cast<const double*>(B + o_pose); h->m.anchor = reinterpret_cast<const int*>(B + o_anch);
+  h->m.xyz = reinterpret_cast<const double*>(B + o_xyz); h->m.vis_ptr = reinterpret_cast<const int*>(B + o_vptr);
+  h->m.vis_pose = reinterpret_cast<const int*>(B + o_vpose); h->m.center = reinterpret_cast<const double*>(B + o_cen);
+  h->m.level = reinterpret_cast<const int*>(B + o_lvl);
+  return SVS_OK;
+}
+
+int svs_map_update_poses(svs_map* h, int n, const int* vertex, const double* T_me_from_world) {
+  if (!h || n < 0 || (n && (!vertex || !T_me_from_world)) || !h->d_map) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  for (int i = 0; i < n; ++i) {
+    if (vertex[i] < 0 || vertex[i] >= h->V) { h->err = "vertex outside [0, V)"; return SVS_ERR_INVALID; }
+    GCK(cudaMemcpyAsync(const_cast<double*>(h->m.pose) + 7 * (size_t)vertex[i], T_me_from_world + 7 * (size_t)i, sizeof(double) * 7,
+                        cudaMemcpyHostToDevice, h->stream));
+  }
+  GCK(cudaStreamSynchronize(h->stream));
+  return SVS_OK;
+}
+
+int svs_ba_set_problem_from_map(svs_ba* ba, svs_map* h, int P, const int* window_vertex, const unsigned char* fixed, int L,
+                                const int* active_point, int C, const int* c_i, const int* c_j, const double* c_T,
+                                const double* c_Lambda, const svs_cam* cam, int* num_edges) {
+  if (!ba || !h || P <= 0 || L < 0 || C < 0 || !window_vertex || (L && !active_point) || !cam || !h->d_map) return SVS_ERR_INVALID;
+  if (svs::ba_device(ba) != h->device) { h->err = "map and bundle adjuster live on different devices"; return SVS_ERR_INVALID; }
+  // window position of every vertex (-1 = outside the double window)
+  h->h_winpos.assign(h->V, -1);
+  for (int i = 0; i < P; ++i) {
+    const int v = window_vertex[i];
+    if (v < 0 || v >= h->V || h->h_winpos[v] >= 0) { h->err = "window names a vertex twice or outside [0, V)"; return SVS_ERR_INVALID; }
+    h->h_winpos[v] = i;
+  }
+  for (int l = 0; l < L; ++l)
+    if (active_point[l] < 0 || active_point[l] >= h->Np) { h->err = "active point outside [0, Np)"; return SVS_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  // work arena: win_pos, window, active, cnt, ptr, bad | poses, psi | edges (sized for every observation of the map)
+  size_t off = 0;
+  const size_t o_wp = off; off += al256(sizeof(int) * (size_t)h->V);
+  const size_t o_win = off; off += al256(sizeof(int) * (size_t)P);
+  const size_t o_act = off; off += al256(sizeof(int) * (size_t)std::max(L, 1));
+  const size_t o_cnt = off; off += al256(sizeof(int) * (size_t)std::max(L, 1));
+  const size_t o_ptr = off; off += al256(sizeof(int) * ((size_t)L + 1));
+  const size_t o_bad = off; off += 256;
+  const size_t o_pose = off; off += al256(sizeof(double) * 7 * (size_t)P);
+  const size_t o_psi = off; off += al256(sizeof(double) * 3 * (size_t)std::max(L, 1));
+  const size_t emax = (size_t)std::max(h->nnz, 1);
+  const size_t o_ep = off; off += al256(sizeof(int) * emax);
+  const size_t o_es = off; off += al256(sizeof(int) * emax);
+  const size_t o_ea = off; off += al256(sizeof(int) * emax);
+  const size_t o_oi = off; off += al256(sizeof(double) * 6 * emax);
+  GCK(cudaStreamSynchronize(h->stream));
+  if (off > h->work_cap) {
+    cudaFree(h->d_work); h->d_work = nullptr; h->work_cap = 0;
+    GCK(cudaMalloc(&h->d_work, off + off / 4));
+    h->work_cap = off + off / 4;
+  }
+  char* W = h->d_work;
+  int* d_wp = reinterpret_cast<int*>(W + o_wp); int* d_win = reinterpret_cast<int*>(W + o_win);
+  int* d_act = reinterpret_cast<int*>(W + o_act); int* d_cnt = reinterpret_cast<int*>(W + o_cnt);
+  int* d_ptr = reinterpret_cast<int*>(W + o_ptr); int* d_bad = reinterpret_cast<int*>(W + o_bad);
+  double* d_pose = reinterpret_cast<double*>(W + o_pose); double* d_psi = reinterpret_cast<double*>(W + o_psi);
+  int* d_ep = reinterpret_cast<int*>(W + o_ep); int* d_es = reinterpret_cast<int*>(W + o_es); int* d_ea = reinterpret_cast<int*>(W + o_ea);
+  double* d_oi = reinterpret_cast<double*>(W + o_oi);
+  GCK(cudaMemcpyAsync(d_wp, h->h_winpos.data(), sizeof(int) * (size_t)h->V, cudaMemcpyHostToDevice, h->stream));
+  GCK(cudaMemcpyAsync(d_win, window_vertex, sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, h->stream));
+  if (L) GCK(cudaMemcpyAsync(d_act, active_point, sizeof(int) * (size_t)L, cudaMemcpyHostToDevice, h->stream));
+  GCK(cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
+  int E = 0, bad = 0;
+  if (L) {
+    k_count<<<(L + 255) / 256, 256, 0, h->stream>>>(h->m, d_wp, d_act, L, d_cnt, d_bad);
+    k_scan<<<1, 1024, 0, h->stream>>>(d_cnt, L, d_ptr);
+    GCK(cudaMemcpyAsync(&E, d_ptr + L, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    GCK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    GCK(cudaStreamSynchronize(h->stream));
+    if (bad) { h->err = "an active point is anchored in a frame outside the window"; return SVS_ERR_INVALID; }
+    // obs_info = [E][3] observations followed by [E][3] weights: the emit kernel needs E for the second half
+    k_emit<<<(L + 255) / 256, 256, 0, h->stream>>>(h->m, d_wp, d_act, L, d_ptr, E, d_ep, d_es, d_ea, d_oi, d_psi);
+  }
+  k_gather_poses<<<(7 * P + 255) / 256, 256, 0, h->stream>>>(h->m, d_win, P, d_pose);
+  GCK(cudaGetLastError());
+  // only the index triples, psi and the window's poses go back: structure analysis and initial state of the BA handle
+  h->h_ep.resize(std::max(E, 1)); h->h_es.resize(std::max(E, 1)); h->h_ea.resize(std::max(E, 1));
+  h->h_pose.resize(7 * (size_t)P); h->h_psi.resize(3 * (size_t)std::max(L, 1));
+  if (E) {
+    GCK(cudaMemcpyAsync(h->h_ep.data(), d_ep, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost, h->stream));
+    GCK(cudaMemcpyAsync(h->h_es.data(), d_es, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost, h->stream));
+    GCK(cudaMemcpyAsync(h->h_ea.data(), d_ea, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (L) GCK(cudaMemcpyAsync(h->h_psi.data(), d_psi, sizeof(double) * 3 * (size_t)L, cudaMemcpyDeviceToHost, h->stream));
+  GCK(cudaMemcpyAsync(h->h_pose.data(), d_pose, sizeof(double) * 7 * (size_t)P, cudaMemcpyDeviceToHost, h->stream));
+  GCK(cudaStreamSynchronize(h->stream));
+  if (num_edges) *num_edges = E;
+  h->d_oi_last = d_oi; h->last_E = E;
+  const int rc = svs::ba_set_problem_device_obs(ba, P, h->h_pose.data(), fixed, L, h->h_psi.data(), E, h->h_ep.data(), h->h_es.data(),
+                                                h->h_ea.data(), d_oi, C, c_i, c_j, c_T, c_Lambda, cam);
+  if (rc != SVS_OK) h->err = std::string("svs_ba_set_problem: ") + svs_last_error(ba);
+  return rc;
+}
+
+// the assembled edge list of the last svs_ba_set_problem_from_map, for inspection
+int svs_map_last_edges(svs_map* h, int E, int* e_point, int* e_pose, int* e_anchor, double* e_obs, double* e_info) {
+  if (!h || E != h->last_E || !h->d_work) return SVS_ERR_INVALID;
+  if (E == 0) return SVS_OK;
+  if (e_point) memcpy(e_point, h->h_ep.data(), sizeof(int) * (size_t)E);
+  if (e_pose) memcpy(e_pose, h->h_es.data(), sizeof(int) * (size_t)E);
+  if (e_anchor) memcpy(e_anchor, h->h_ea.data(), sizeof(int) * (size_t)E);
+  cudaSetDevice(h->device);
+  if (e_obs) GCK(cudaMemcpy(e_obs, h->d_oi_last, sizeof(double) * 3 * (size_t)E, cudaMemcpyDeviceToHost));
+  if (e_info) GCK(cudaMemcpy(e_info, h->d_oi_last + 3 * (size_t)E, sizeof(double) * 3 * (size_t)E, cudaMemcpyDeviceToHost));
+  return SVS_OK;
+}
+
+}  // extern "C"

@@ -18,3 +18,41 @@ def graph_tables(pb):
     xyz = np.stack([psi[:, 0] / psi[:, 2], psi[:, 1] / psi[:, 2], 1.0 / psi[:, 2]], 1)
     return dict(poses=pb.pose_qt.copy(), feat_ptr=feat_ptr, feat_point=e_point.astype(np.int32), point_anchor=anchor,
                 xyz_anchor=xyz)
+
+
+def make_map(pb, extra_vertices=4, extra_points=10, seed=0):
+    """A map that contains the window `pb` plus vertices and points outside it: returns (map tables, window_vertex,
+    active_point).  Vertex ids are a permutation of the BA pose indices; every point's observations are listed by
+    ascending vertex id (Point::vis_set is a std::set<int>, reference slam_graph.hpp:102-137); pyramid levels are
+    recovered from the window's information values."""
+    rng = np.random.default_rng(seed)
+    P, L = pb.P, pb.L
+    V, Np = P + extra_vertices, L + extra_points
+    perm = rng.permutation(V)
+    window_vertex = perm[:P].astype(np.int32)                     # BA pose i lives in vertex window_vertex[i]
+    outside = perm[P:]
+    point_perm = rng.permutation(Np)
+    active_point = point_perm[:L].astype(np.int32)                # BA point l is map point active_point[l]
+    poses = np.zeros((V, 7)); poses[:, 3] = 1.0
+    poses[window_vertex] = pb.pose_qt
+    poses[outside, 4:] = rng.normal(0, 1, (len(outside), 3))
+    xyz = np.stack([rng.uniform(-1, 1, Np), rng.uniform(-1, 1, Np), rng.uniform(2, 9, Np)], 1)
+    psi = pb.psi
+    xyz[active_point] = np.stack([psi[:, 0] / psi[:, 2], psi[:, 1] / psi[:, 2], 1.0 / psi[:, 2]], 1)
+    anchor = np.full(Np, window_vertex[0], np.int32)
+    a_of_l = np.zeros(L, np.int64); a_of_l[pb.e_point] = pb.e_anchor
+    anchor[active_point] = window_vertex[a_of_l]
+    level = np.where(pb.e_info[:, 0] > 0.5, 0, 1).astype(np.int32)   # s = (2^-level)^2 in {1, 1/4}
+    rows = [(int(active_point[pb.e_point[e]]), int(window_vertex[pb.e_pose[e]]), pb.e_obs[e], int(level[e])) for e in range(pb.E)]
+    for p in active_point[: max(1, L // 3)]:                       # observations from frames outside the window
+        for v in outside[: 1 + int(p) % len(outside)]:
+            rows.append((int(p), int(v), rng.uniform(0, 600, 3), int(rng.integers(0, 3))))
+    for p in point_perm[L:]:                                       # points that are not active
+        rows.append((int(p), int(window_vertex[0]), rng.uniform(0, 600, 3), 0))
+    rows.sort(key=lambda r: (r[0], r[1]))
+    vis_point = np.array([r[0] for r in rows])
+    vis_ptr = np.searchsorted(vis_point, np.arange(Np + 1)).astype(np.int32)
+    m = dict(poses=poses, point_anchor=anchor, xyz_anchor=xyz, vis_ptr=vis_ptr,
+             vis_pose=np.array([r[1] for r in rows], np.int32), feat_center=np.array([r[2] for r in rows], np.float64),
+             feat_level=np.array([r[3] for r in rows], np.int32))
+    return m, window_vertex, active_point

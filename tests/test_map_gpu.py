@@ -1,0 +1,64 @@
+"""GPU tests of the device-resident map and window assembly (svs_map_*,
+svs_ba_set_problem_from_map) against the plain-Python restatement of copyDataToG2o, through the C ABI.
+The assembled edge list is bit-exact; optimising the assembled window gives the result of loading the same window
+through svs_ba_set_problem (to the last bits: FP64 atomics) and the oracle's result to 1e-6."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from scavislam_b200 import synth, synth_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _assembled_problem(pb, g):
+    return dataclasses.replace(pb, E=len(g["e_point"]), pose_qt=g["pose_qt"], psi=g["psi"], e_point=g["e_point"],
+                               e_pose=g["e_pose"], e_anchor=g["e_anchor"], e_obs=g["e_obs"], e_info=g["e_info"])
+
+
+@pytest.mark.parametrize("P,L,seed", [(8, 200, 5), (30, 3000, 6)])
+def test_assembled_window_equals_the_restatement_and_optimises_identically(svs, oracle, P, L, seed):
+    pb = synth.make_window(P, L, seed=seed)
+    m, win, act = synth_graph.make_map(pb, seed=seed)
+    g = oracle.copy_data_to_g2o(m, win, act)
+    dm, ba, ba2 = svs.DeviceMap(), svs.BundleAdjuster(), svs.BundleAdjuster()
+    dm.set(m["poses"], m["point_anchor"], m["xyz_anchor"], m["vis_ptr"], m["vis_pose"], m["feat_center"], m["feat_level"])
+    E = dm.set_problem(ba, win, act, pb.cam, c_i=pb.c_i, c_j=pb.c_j, c_T=pb.c_T, c_Lambda=pb.c_Lambda)
+    assert E == len(g["e_point"]) == pb.E
+    ep, es, ea, obs, info = dm.last_edges(E)
+    np.testing.assert_array_equal(ep, g["e_point"]); np.testing.assert_array_equal(es, g["e_pose"])
+    np.testing.assert_array_equal(ea, g["e_anchor"])
+    np.testing.assert_array_equal(obs, g["e_obs"]); np.testing.assert_array_equal(info, g["e_info"])
+    np.testing.assert_array_equal(ba.poses(), g["pose_qt"])
+    np.testing.assert_array_equal(ba.points(), g["psi"])
+    pa = _assembled_problem(pb, g)
+    it, st = ba.optimize(3)
+    ba2.set_problem(pa)
+    it2, st2 = ba2.optimize(3)
+    assert it == it2 == 3
+    # same edge order -> same internal order; the Schur scatter uses FP64 atomics, so the last bits may differ
+    np.testing.assert_allclose(st["chi2_iter"], st2["chi2_iter"], rtol=1e-12)
+    np.testing.assert_allclose(ba.poses(), ba2.poses(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(ba.points(), ba2.points(), rtol=1e-10, atol=1e-12)
+    p_o, s_o, _ = oracle.optimize(pa, 3)
+    assert np.abs(ba.poses() - p_o).max() <= 1e-6 * np.abs(p_o).max()
+    assert np.abs(ba.points() - s_o).max() <= 1e-6 * np.abs(s_o).max()
+    for h in (dm, ba, ba2):
+        h.close()
+
+
+def test_pose_updates_and_invalid_windows(svs, oracle):
+    pb = synth.make_window(8, 200, seed=5)
+    m, win, act = synth_graph.make_map(pb)
+    dm, ba = svs.DeviceMap(), svs.BundleAdjuster()
+    dm.set(m["poses"], m["point_anchor"], m["xyz_anchor"], m["vis_ptr"], m["vis_pose"], m["feat_center"], m["feat_level"])
+    newT = oracle.se3_exp(np.array([0.1, 0.2, -0.1, 0.01, 0.0, 0.02]))
+    dm.update_poses([win[3]], [newT])                             # restoreDataFromG2o's direction
+    dm.set_problem(ba, win, act, pb.cam)
+    np.testing.assert_array_equal(ba.poses()[3], newT)
+    with pytest.raises(svs.SvsError):                             # a window without the anchor frame of an active point
+        dm.set_problem(ba, win[1:], act, pb.cam)
+    with pytest.raises(svs.SvsError):                             # the same vertex twice
+        dm.set_problem(ba, np.concatenate([win, win[:1]]), act, pb.cam)
+    dm.close(); ba.close()
