@@ -470,24 +470,18 @@ static void add_AtWB(double *C, const double *A, int na, const double *B, int nb
     }
 }
 
-/* g2o BlockSolver::buildSystem: Hpp, Hpl(W), Hll(D), b at the given state.  Returns robust chi2. */
-static double sys_build(sys_t *s, const oba_problem *p, const double *poses, const double *psi,
-                        int robust, double delta) {
-  const int P = s->P, L = s->L;
+/* one landmark's edges of g2o BlockSolver::buildSystem; Hpp / bp are the shared arrays (single thread) or a
+ * thread's private copies (oba_set_threads > 1); D, bl, W rows belong to the landmark alone */
+static void build_landmark(sys_t *s, const oba_problem *p, const double *poses, const double *psi, int robust,
+                           double delta, int l, double *Hpp, double *bp, double *chi) {
+  const int P = s->P;
   const double cam[4] = {p->f, p->px, p->py, p->b};
-  memset(s->Hpp, 0, (size_t)s->nblk * 36 * sizeof(double));
-  memset(s->bp, 0, 6 * P * sizeof(double));
-  memset(s->W, 0, (size_t)s->slot_ptr[L] * 18 * sizeof(double));
-  memset(s->D, 0, (size_t)L * 9 * sizeof(double));
-  memset(s->bl, 0, (size_t)L * 3 * sizeof(double));
-  double chi = 0;
-  for (int l = 0; l < L; ++l) {
     const int sb = s->slot_ptr[l];
     for (int k = s->lm_ptr[l]; k < s->lm_ptr[l + 1]; ++k) {
       const int e = s->lm_edge[k];
       const int ip = p->e_pose[e], ia = p->e_anchor[e];
       double err[3], w;
-      chi += edge_chi2_terms(p, poses, psi, e, robust, delta, err, &w);
+      *chi += edge_chi2_terms(p, poses, psi, e, robust, delta, err, &w);
       double Jpsi[9], Jp[18], Ja[18];
       oba_edge_jacobians(cam, poses + 7 * ip, poses + 7 * ia, psi + 3 * l, Jpsi, Jp, Ja);
       const int fp = p->fixed && p->fixed[ip], fa = p->fixed && p->fixed[ia];
@@ -503,25 +497,60 @@ static double sys_build(sys_t *s, const oba_problem *p, const double *poses, con
         for (int k2 = 0; k2 < 3; ++k2) s->bl[3 * l + i] += Jpsi[k2 * 3 + i] * we[k2];
       (void)one;
       /* vertex 1: pose ; vertex 2: anchor */
-      double *App = s->Hpp + 36 * (size_t)s->tbl[(size_t)ip * P + ip];
-      double *Aaa = s->Hpp + 36 * (size_t)s->tbl[(size_t)ia * P + ia];
+      double *App = Hpp + 36 * (size_t)s->tbl[(size_t)ip * P + ip];
+      double *Aaa = Hpp + 36 * (size_t)s->tbl[(size_t)ia * P + ia];
       add_AtWB(App, Jp, 6, Jp, 6, wo, 0);
       add_AtWB(Aaa, Ja, 6, Ja, 6, wo, 0);
       for (int i = 0; i < 6; ++i)
         for (int k2 = 0; k2 < 3; ++k2) {
-          s->bp[6 * ip + i] += Jp[k2 * 6 + i] * we[k2];
-          s->bp[6 * ia + i] += Ja[k2 * 6 + i] * we[k2];
+          bp[6 * ip + i] += Jp[k2 * 6 + i] * we[k2];
+          bp[6 * ia + i] += Ja[k2 * 6 + i] * we[k2];
         }
       /* off-diagonal (1,2): upper block of Hpp; when ip==ia it aliases the diagonal
        * block and receives Jp^T W Ja once (g2o mapHessianMemory quirk) */
       {
         const int lo = ip <= ia ? ip : ia, hi = ip <= ia ? ia : ip;
-        double *Apa = s->Hpp + 36 * (size_t)s->tbl[(size_t)lo * P + hi];
+        double *Apa = Hpp + 36 * (size_t)s->tbl[(size_t)lo * P + hi];
         add_AtWB(Apa, Jp, 6, Ja, 6, wo, ip > ia);
       }
       /* Hpl blocks (pose x point) */
       add_AtWB(s->W + 18 * (size_t)(sb + s->edge_slot[e]), Jp, 6, Jpsi, 3, wo, 0);
       add_AtWB(s->W + 18 * (size_t)sb, Ja, 6, Jpsi, 3, wo, 0);
+    }
+}
+
+static int g_threads = 1;
+/* number of OpenMP threads of the build and Schur loops (1 = the sequential restatement, the default) */
+void oba_set_threads(int n) { g_threads = n > 1 ? n : 1; }
+
+/* g2o BlockSolver::buildSystem: Hpp, Hpl(W), Hll(D), b at the given state.  Returns robust chi2. */
+static double sys_build(sys_t *s, const oba_problem *p, const double *poses, const double *psi,
+                        int robust, double delta) {
+  const int P = s->P, L = s->L;
+  memset(s->Hpp, 0, (size_t)s->nblk * 36 * sizeof(double));
+  memset(s->bp, 0, 6 * P * sizeof(double));
+  memset(s->W, 0, (size_t)s->slot_ptr[L] * 18 * sizeof(double));
+  memset(s->D, 0, (size_t)L * 9 * sizeof(double));
+  memset(s->bl, 0, (size_t)L * 3 * sizeof(double));
+  double chi = 0;
+  if (g_threads <= 1) {
+    for (int l = 0; l < L; ++l) build_landmark(s, p, poses, psi, robust, delta, l, s->Hpp, s->bp, &chi);
+  } else {
+    /* timing variant: landmarks split over threads, private pose blocks summed afterwards (the sum order, and
+     * with it the last bits, differ from the sequential restatement) */
+#pragma omp parallel num_threads(g_threads)
+    {
+      double *H = calloc((size_t)s->nblk * 36, sizeof(double)), *b = calloc(6 * (size_t)P, sizeof(double));
+      double c = 0;
+#pragma omp for schedule(static)
+      for (int l = 0; l < L; ++l) build_landmark(s, p, poses, psi, robust, delta, l, H, b, &c);
+#pragma omp critical
+      {
+        for (size_t i = 0; i < (size_t)s->nblk * 36; ++i) s->Hpp[i] += H[i];
+        for (int i = 0; i < 6 * P; ++i) s->bp[i] += b[i];
+        chi += c;
+      }
+      free(H); free(b);
     }
   }
   for (int c = 0; c < p->C; ++c) {
@@ -579,19 +608,11 @@ static void inv3(const double A[9], double Ai[9]) {
   Ai[6] = c02 * id; Ai[7] = (A[1] * A[6] - A[0] * A[7]) * id; Ai[8] = (A[0] * A[4] - A[1] * A[3]) * id;
 }
 
-/* g2o BlockSolver::solve, Schur part: S = Hpp + lambda I - Hpl (Hll + lambda I)^-1 Hpl^T */
-static void sys_schur(sys_t *s, const oba_problem *p, double lambda) {
-  const int P = s->P, L = s->L;
-  memcpy(s->S, s->Hpp, (size_t)s->nblk * 36 * sizeof(double));
-  for (int i = 0; i < P; ++i) {
-    double *d = s->S + 36 * (size_t)s->tbl[(size_t)i * P + i];
-    for (int a = 0; a < 6; ++a) d[a * 7] += lambda;
-    if (p->fixed && p->fixed[i]) for (int a = 0; a < 6; ++a) d[a * 7] += 1.;
-  }
-  memcpy(s->bs, s->bp, 6 * P * sizeof(double));
-  for (int l = 0; l < L; ++l) {
+/* one landmark of the Schur complement; S / bs are the shared arrays or a thread's private copies */
+static void schur_landmark(sys_t *s, double lambda, int l, double *S, double *bs) {
+  const int P = s->P;
     const int sb = s->slot_ptr[l], se = s->slot_ptr[l + 1];
-    if (sb == se) continue;
+    if (sb == se) return;
     double Dl[9], Di[9], db[3];
     memcpy(Dl, s->D + 9 * l, sizeof Dl);
     Dl[0] += lambda; Dl[4] += lambda; Dl[8] += lambda;
@@ -605,17 +626,44 @@ static void sys_schur(sys_t *s, const oba_problem *p, double lambda) {
         for (int c = 0; c < 3; ++c)
           Y[r * 3 + c] = Ba[r * 3] * Di[c] + Ba[r * 3 + 1] * Di[3 + c] + Ba[r * 3 + 2] * Di[6 + c];
       for (int r = 0; r < 6; ++r)
-        s->bs[6 * ia + r] -= Ba[r * 3] * db[0] + Ba[r * 3 + 1] * db[1] + Ba[r * 3 + 2] * db[2];
+        bs[6 * ia + r] -= Ba[r * 3] * db[0] + Ba[r * 3 + 1] * db[1] + Ba[r * 3 + 2] * db[2];
       for (int b = sb; b < se; ++b) {
         const int ib = s->slot_pose[b];
         if (ib < ia) continue;
         if (ib == ia && b != a) continue; /* cannot happen: slots hold distinct poses */
         const double *Bb = s->W + 18 * (size_t)b;
-        double *Sab = s->S + 36 * (size_t)s->tbl[(size_t)ia * P + ib];
+        double *Sab = S + 36 * (size_t)s->tbl[(size_t)ia * P + ib];
         for (int r = 0; r < 6; ++r)
           for (int c = 0; c < 6; ++c)
             Sab[r * 6 + c] -= Y[r * 3] * Bb[c * 3] + Y[r * 3 + 1] * Bb[c * 3 + 1] + Y[r * 3 + 2] * Bb[c * 3 + 2];
       }
+    }
+}
+
+/* g2o BlockSolver::solve, Schur part: S = Hpp + lambda I - Hpl (Hll + lambda I)^-1 Hpl^T */
+static void sys_schur(sys_t *s, const oba_problem *p, double lambda) {
+  const int P = s->P, L = s->L;
+  memcpy(s->S, s->Hpp, (size_t)s->nblk * 36 * sizeof(double));
+  for (int i = 0; i < P; ++i) {
+    double *d = s->S + 36 * (size_t)s->tbl[(size_t)i * P + i];
+    for (int a = 0; a < 6; ++a) d[a * 7] += lambda;
+    if (p->fixed && p->fixed[i]) for (int a = 0; a < 6; ++a) d[a * 7] += 1.;
+  }
+  memcpy(s->bs, s->bp, 6 * P * sizeof(double));
+  if (g_threads <= 1) {
+    for (int l = 0; l < L; ++l) schur_landmark(s, lambda, l, s->S, s->bs);
+  } else {
+#pragma omp parallel num_threads(g_threads)
+    {
+      double *St = calloc((size_t)s->nblk * 36, sizeof(double)), *bt = calloc(6 * (size_t)P, sizeof(double));
+#pragma omp for schedule(static)
+      for (int l = 0; l < L; ++l) schur_landmark(s, lambda, l, St, bt);
+#pragma omp critical
+      {
+        for (size_t i = 0; i < (size_t)s->nblk * 36; ++i) s->S[i] += St[i];
+        for (int i = 0; i < 6 * P; ++i) s->bs[i] += bt[i];
+      }
+      free(St); free(bt);
     }
   }
 }

@@ -90,6 +90,9 @@ double oba_full_system(const oba_problem *p, int robust, double huber_delta,
 /* g2o SparseOptimizer::optimize(num_iters) with OptimizationAlgorithmLevenberg,
  * BlockSolver_6_3 (Schur) and a sparse block Cholesky.  pose_out [P][7], psi_out [L][3].
  * Returns iterations performed (0 on solver failure in the last iteration, -1 if empty). */
+/* OpenMP threads of the build and Schur loops: 1 (default) = the sequential restatement every parity test uses;
+ * > 1 = a timing variant whose sums are accumulated in per-thread copies (last bits differ) */
+void oba_set_threads(int n);
 int oba_optimize(const oba_problem *p, int num_iters, int robust, double huber_delta,
                  double lambda_init, int max_trials,
                  double *pose_out, double *psi_out, oba_stats *stats);

@@ -231,6 +231,12 @@ def full_system(pb, robust=True, delta=1.0):
     return H, b, chi
 
 
+def set_threads(n):
+    """Timing variant only: OpenMP threads of the oracle's build and Schur loops (1 = sequential restatement)."""
+    L = lib(); L.oba_set_threads.argtypes = [C.c_int]; L.oba_set_threads.restype = None
+    L.oba_set_threads(int(n))
+
+
 def optimize(pb, num_iters, robust=True, delta=1.0, lambda_init=50.0, max_trials=5):
     s, keep = as_c_problem(pb)
     poses, psi = f64(pb.P, 7), f64(pb.L, 3)

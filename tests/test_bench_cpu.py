@@ -24,6 +24,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0
     assert d["config"]["workload"].startswith("C2") and d["config"]["E"] == 120597
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["multi_thread"]["cores"] >= 1 and d["cpu_baseline"]["multi_thread"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -242,3 +242,20 @@ def test_golden_vectors(oracle):
     np.testing.assert_allclose(p5, g["poses_it5"], rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(s5, g["psi_it5"], rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(st5["chi2_iter"], g["chi2_iter5"], rtol=1e-10)
+
+
+def test_threaded_timing_variant_agrees_with_the_sequential_restatement(oracle):
+    """oba_set_threads(n > 1) only reorders sums (per-thread copies of the pose blocks); bench.py reports it beside
+    the single-thread figure.  Every parity test runs with one thread."""
+    pb = synth.make_window(12, 400, seed=8)
+    p1, s1, st1 = oracle.optimize(pb, 4)
+    try:
+        oracle.set_threads(4)
+        p4, s4, st4 = oracle.optimize(pb, 4)
+    finally:
+        oracle.set_threads(1)
+    assert st1["trials_iter"] == st4["trials_iter"]
+    np.testing.assert_allclose(p4, p1, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(s4, s1, rtol=1e-9, atol=1e-12)
+    p1b, s1b, _ = oracle.optimize(pb, 4)
+    assert np.array_equal(p1, p1b) and np.array_equal(s1, s1b)
