@@ -314,5 +314,71 @@ class BA_SE3_XYZ_STEREO {
   bool ok_ = false;
 };
 
+// FrameGrabber::preprocessing (frame_grabber.cpp:287-336): pyramids and derivative images, kept on the device
+class FramePreprocessor {
+ public:
+  FramePreprocessor(int w, int h, int nlevels) { ok_ = svs_prep_create(-1, w, h, nlevels, &h_) == SVS_OK; }
+  ~FramePreprocessor() { if (h_) svs_prep_destroy(h_); }
+  FramePreprocessor(const FramePreprocessor&) = delete;
+  FramePreprocessor& operator=(const FramePreprocessor&) = delete;
+  bool valid() const { return ok_; }
+  svs_prep* handle() { return h_; }
+  bool preprocessing(const unsigned char* left, int pitch) { return ok_ && svs_prep_process(h_, left, pitch) == SVS_OK; }
+  // device pointers of one level: hand them to svs_fast_set_image_device / svs_dt_set_images_device / ...
+  struct Level { int w, h, pitch_u8, stride_f32; const unsigned char* u8; const float *f32, *dx, *dy; };
+  bool level(int l, Level* out) {
+    return ok_ && svs_prep_level(h_, l, &out->w, &out->h, &out->u8, &out->pitch_u8, &out->f32, &out->dx, &out->dy,
+                                 &out->stride_f32) == SVS_OK;
+  }
+
+ private:
+  svs_prep* h_ = nullptr;
+  bool ok_ = false;
+};
+
+// SlamGraph::computeConstraint (slam_graph.cpp:785-846) for a batch of pose pairs
+class ConstraintBuilder {
+ public:
+  ConstraintBuilder() { ok_ = svs_constraints_create(-1, &h_) == SVS_OK; }
+  ~ConstraintBuilder() { if (h_) svs_constraints_destroy(h_); }
+  ConstraintBuilder(const ConstraintBuilder&) = delete;
+  ConstraintBuilder& operator=(const ConstraintBuilder&) = delete;
+  bool valid() const { return ok_; }
+  const char* last_error() const { return svs_constraints_last_error(h_); }
+  // poses [P][7]; feature tables as CSR (ascending point ids); per point its anchor pose index and xyz_anchor
+  bool computeConstraints(const std::vector<double>& T_me_from_world, const std::vector<int>& feat_ptr,
+                          const std::vector<int>& feat_point, const std::vector<int>& point_anchor,
+                          const std::vector<double>& xyz_anchor, const std::vector<int>& v1, const std::vector<int>& v2,
+                          std::vector<double>* T_1_from_2, std::vector<double>* Lambda, std::vector<int>* visibility_strength) {
+    const int n = (int)v1.size();
+    T_1_from_2->resize(7 * (size_t)n); Lambda->resize(36 * (size_t)n); visibility_strength->resize(n);
+    return ok_ && v2.size() == v1.size() &&
+           svs_computeConstraint_batch(h_, (int)(T_me_from_world.size() / 7), T_me_from_world.data(), feat_ptr.data(),
+                                       feat_point.data(), (int)point_anchor.size(), point_anchor.data(), xyz_anchor.data(), n,
+                                       v1.data(), v2.data(), T_1_from_2->data(), Lambda->data(),
+                                       visibility_strength->data()) == SVS_OK;
+  }
+
+ private:
+  svs_constraints* h_ = nullptr;
+  bool ok_ = false;
+};
+
+// The part of SlamGraph the optimiser reads, kept on the device; copyDataToG2o as kernels (slam_graph.cpp:907-1032)
+class DeviceMap {
+ public:
+  DeviceMap() { ok_ = svs_map_create(-1, &h_) == SVS_OK; }
+  ~DeviceMap() { if (h_) svs_map_destroy(h_); }
+  DeviceMap(const DeviceMap&) = delete;
+  DeviceMap& operator=(const DeviceMap&) = delete;
+  bool valid() const { return ok_; }
+  svs_map* handle() { return h_; }
+  const char* last_error() const { return svs_map_last_error(h_); }
+
+ private:
+  svs_map* h_ = nullptr;
+  bool ok_ = false;
+};
+
 }  // namespace svs
 #endif
