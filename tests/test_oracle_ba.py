@@ -259,3 +259,26 @@ def test_threaded_timing_variant_agrees_with_the_sequential_restatement(oracle):
     np.testing.assert_allclose(s4, s1, rtol=1e-9, atol=1e-12)
     p1b, s1b, _ = oracle.optimize(pb, 4)
     assert np.array_equal(p1, p1b) and np.array_equal(s1, s1b)
+
+
+def test_se3_exp_log_match_the_matrix_exponential(oracle):
+    """Independent pin of the Sophus restatement (SURVEY A.1): SE3::exp([upsilon; omega]) is the matrix exponential
+    of the twist [[hat(omega), upsilon], [0, 0]] (scipy.linalg.expm), log its inverse, including tiny angles."""
+    from scipy.linalg import expm, logm
+    rng = np.random.default_rng(3)
+    for scale in (1.0, 1e-3, 1e-9, 2.5):
+        d = rng.normal(0, 1, 6) * scale
+        d[3:] *= min(1.0, 3.0 / max(np.linalg.norm(d[3:]), 1e-30))        # keep the angle below pi
+        w = d[3:]
+        X = np.zeros((4, 4))
+        X[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]
+        X[:3, 3] = d[:3]
+        M = expm(X)
+        T = oracle.se3_exp(d)
+        R = np.array([oracle.se3_act(np.concatenate([T[:4], [0, 0, 0]]), e) for e in np.eye(3)]).T
+        np.testing.assert_allclose(R, M[:3, :3], atol=1e-12)
+        np.testing.assert_allclose(T[4:], M[:3, 3], atol=1e-12 * max(1.0, np.abs(M[:3, 3]).max()))
+        np.testing.assert_allclose(oracle.se3_log(T), d, atol=1e-9 * max(1.0, scale), rtol=1e-9)
+        if scale >= 1e-3:
+            Lg = np.real(logm(M))
+            np.testing.assert_allclose(oracle.se3_log(T)[:3], Lg[:3, 3], atol=1e-9)
