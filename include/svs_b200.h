@@ -74,7 +74,7 @@ typedef struct {
   float ms_build;                       /* fused linearise + Schur kernel, summed over trials */
   float ms_solve;                       /* reduced-system factor + solve + pose update */
   float ms_update;                      /* back-substitution + point update + trial chi2 */
-  float ms_control;                     /* LM decision kernel */
+  float ms_control;                     /* sharded window: the two all-reduces + LM decision kernel per trial */
   int launches;                         /* kernels launched by this call */
 } svs_ba_stats;
 
@@ -148,6 +148,28 @@ int svs_ba_system_buffers(svs_ba *h, double **S, long long *nS, double **bp, dou
 int svs_ba_trial_solve(svs_ba *h, int robust, double huber_delta);
 int svs_ba_trial_decide(svs_ba *h, int *again, int *stop, int *iterations_done);
 int svs_ba_lm_stats(svs_ba *h, svs_ba_stats *stats);
+
+/* The same sharding driven INSIDE the library (one process per GPU): after svs_ba_comm_init the handle
+ * owns an NCCL communicator, svs_ba_set_problem_sharded takes the WHOLE window on every rank and keeps
+ * landmarks l with l % nranks == rank (poses replicated, pose-pose edges on rank 0, block pattern of the
+ * whole window), and svs_ba_optimize runs every Levenberg trial as
+ *   fused build -> ncclAllReduce(S | bp | bc, one packed buffer) -> replicated solve -> local
+ *   back-substitution -> ncclAllReduce(3 scalars) -> identical decision on every rank
+ * on the handle's stream without a host synchronisation in between (SlamGraph::optimize,
+ * slam_graph.cpp:319-355, on a window too large for one GPU's latency budget).
+ *   svs_comm_unique_id: rank 0 creates the 128-byte rendezvous id; the caller broadcasts it (MPI,
+ *   torch.distributed, a socket).  NCCL is bound at run time (libnccl.so.2); SVS_ERR_STATE without it. */
+int svs_comm_unique_id(char id[128]);
+int svs_ba_comm_init(svs_ba *h, int nranks, int rank, const char id[128]);
+int svs_ba_set_problem_sharded(svs_ba *h, int P, const double *T_qt, const unsigned char *fixed,
+                               int L, const double *psi,
+                               int E, const int *e_point, const int *e_pose, const int *e_anchor,
+                               const double *e_obs, const double *e_info_diag,
+                               int C, const int *c_i, const int *c_j, const double *c_T_ji,
+                               const double *c_Lambda, const svs_cam *cam);
+/* restoreDataFromG2o (slam_graph.cpp:1037-1058) for a sharded window: psi[L][3] of the WHOLE window on
+ * every rank (svs_ba_get_points fills only this rank's landmarks of the same full-size array). */
+int svs_ba_get_points_all(svs_ba *h, double *psi);
 
 /* Inspection hooks used by the parity tests (device results copied to host buffers). */
 /* g2o SparseOptimizer::activeRobustChi2 at the current state. */

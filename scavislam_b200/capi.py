@@ -109,6 +109,7 @@ EXPORTS = [
     "svs_ba_chi2", "svs_ba_reduced_system", "svs_ba_solve_reduced", "svs_device_info",
     "svs_ba_set_structure", "svs_ba_lm_begin", "svs_ba_trial_build", "svs_ba_system_buffers", "svs_ba_trial_solve",
     "svs_ba_trial_decide", "svs_ba_lm_stats",
+    "svs_comm_unique_id", "svs_ba_comm_init", "svs_ba_set_problem_sharded", "svs_ba_get_points_all",
     "svs_fast_create", "svs_fast_destroy", "svs_fast_last_error", "svs_fast_grid_init", "svs_fast_set_image",
     "svs_fast_set_image_device", "svs_fast_detect", "svs_fast_detect_adaptively",
     "svs_dt_create", "svs_dt_destroy", "svs_dt_last_error", "svs_dt_set_intrinsics", "svs_dt_set_images",
@@ -128,6 +129,15 @@ EXPORTS = [
     "svs_map_create", "svs_map_destroy", "svs_map_last_error", "svs_map_set", "svs_map_update_poses",
     "svs_ba_set_problem_from_map", "svs_map_last_edges",
 ]
+
+
+def comm_unique_id():
+    """128-byte NCCL rendezvous id (rank 0 creates it, the caller broadcasts it)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().svs_comm_unique_id(buf)
+    if rc != 0:
+        raise SvsError(rc, "svs_comm_unique_id: NCCL not loadable")
+    return buf.raw
 
 
 def lib():
@@ -165,6 +175,10 @@ def lib():
     L.svs_ba_trial_solve.argtypes = [vp, C.c_int, C.c_double]
     L.svs_ba_trial_decide.argtypes = [vp, c_ip, c_ip, c_ip]
     L.svs_ba_lm_stats.argtypes = [vp, C.POINTER(SvsBaStats)]
+    L.svs_comm_unique_id.argtypes = [C.c_char_p]
+    L.svs_ba_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.svs_ba_set_problem_sharded.argtypes = [vp] + prob
+    L.svs_ba_get_points_all.argtypes = [vp, c_dp]
     L.svs_fast_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.svs_fast_destroy.argtypes = [vp]
     L.svs_fast_destroy.restype = None
@@ -398,6 +412,23 @@ class BundleAdjuster:
         a, s, i = C.c_int(), C.c_int(), C.c_int()
         self._check(lib().svs_ba_trial_decide(self._h, C.byref(a), C.byref(s), C.byref(i)))
         return a.value, s.value, i.value
+
+    # ---- one window sharded by landmarks across GPUs, driven inside the library (NCCL on the handle's stream)
+    def comm_init(self, nranks, rank, unique_id):
+        """unique_id: the 128 bytes rank 0 got from `comm_unique_id()`, broadcast by the caller."""
+        self._check(lib().svs_ba_comm_init(self._h, int(nranks), int(rank), bytes(unique_id)))
+
+    def set_problem_sharded(self, pb):
+        """Every rank passes the WHOLE window; the library keeps landmarks l % nranks == rank."""
+        k = self._arrays(pb)
+        args, cam = self._prob_args(pb, k)
+        self._check(lib().svs_ba_set_problem_sharded(self._h, *args))
+        self.P, self.L = pb.P, pb.L
+
+    def points_all(self):
+        out = np.zeros((self.L, 3))
+        self._check(lib().svs_ba_get_points_all(self._h, _dp(out)))
+        return out
 
     def lm_stats(self):
         st = SvsBaStats()

@@ -192,20 +192,19 @@ k_build(BaDev d, const int* __restrict__ lm_list, int n_list, int Kmax, int robu
 }
 
 void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st);
+void launch_build_long(const BaDev& d, int robust, double delta, cudaStream_t st);
 
 // Dispatch: landmark groups with <= 8 frames go to k_build_wave (ba_build_wave.cu); the rest (long
 // tracks, landmarks without observations) and the pose-pose constraints to k_build.
 void launch_build(const BaDev& d, int Kmax, int robust, double delta, cudaStream_t st) {
   constexpr int WARPS = 8;
   launch_build_wave(d, robust, delta, st);
+  launch_build_long(d, robust, delta, st);
   const int n_lm_blocks = (d.ngen + WARPS - 1) / WARPS;
   const int n_c_blocks = 0;   // the pose-pose constraints ride on k_build_wave's launch
   const size_t smem = build_smem_bytes(WARPS, Kmax);
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (device_needs_smem_optin(1, smem))
     cudaFuncSetAttribute(k_build<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   if (n_lm_blocks + n_c_blocks == 0) return;
   k_build<WARPS><<<n_lm_blocks + n_c_blocks, WARPS * 32, smem, st>>>(d, d.gen_lm, d.ngen, Kmax, robust, delta, n_lm_blocks);
 }

@@ -312,11 +312,9 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
 
 void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st) {
   if (d.ntasks == 0 && d.C == 0) return;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in above 48 KB of dynamic shared memory is per device: handles may live on several GPUs of one process
+  if (device_needs_smem_optin(0, build_wave_smem_bytes()))
     cudaFuncSetAttribute(k_build_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_wave_smem_bytes());
-    configured = true;
-  }
   const int task_blocks = (d.ntasks + kWvWarps - 1) / kWvWarps;
   const int c_blocks = (d.C + kWvWarps * 32 - 1) / (kWvWarps * 32);
   k_build_wave<<<task_blocks + c_blocks, kWvWarps * 32, build_wave_smem_bytes(), st>>>(d, robust, delta, task_blocks);

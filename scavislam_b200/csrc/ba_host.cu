@@ -17,8 +17,16 @@
 
 #include "../../include/svs_b200.h"
 #include "ba_kernels.cuh"
+#include "nccl_dyn.cuh"
 
 using namespace svs;
+
+// Symbolic analysis of the reduced camera system (see analyse() below)
+struct Symbolic {
+  std::vector<int> perm, pos, col_ptr, row_idx, upd_ptr, upd_dst, upd_ab, urg_dst, tbl, branch_ptr;
+  int max_col_branch = 0, max_col_sep = 0;
+  int nblk = 0;
+};
 
 struct svs_ba {
   int device = 0;
@@ -42,8 +50,13 @@ struct svs_ba {
   int Kmax_gen = 1;
   int nnzb_S = 0;
   int C_edges = 0;
-  int max_col_blocks = 0, max_col_branch = 0, nbranch = 1;
+  int max_col_blocks = 0, max_col_branch = 0, nbranch = 1, nsep_blk = 0;
   std::vector<int> extra_pairs;   // svs_ba_set_structure: pose pairs added to the block pattern
+  // one window sharded by landmarks across ranks: NCCL communicator of this handle
+  NcclComm comm = nullptr; int comm_rank = 0, comm_size = 1;
+  size_t sys_count = 0;            // doubles of the packed S | bp | bc buffer (one all-reduce per trial)
+  int L_full = 0;                  // svs_ba_set_problem_sharded: landmarks of the whole window, 0 = not sharded
+  double* d_psi_all = nullptr; size_t psi_all_cap = 0;
   // host scratch of set_problem, kept across calls (fresh multi-MB vectors page-fault every time)
   std::vector<int> w_eptr, w_eord, w_fill, w_anchor, w_K, w_order, w_lm_eptr, w_lm_sptr, w_lm_anchor, w_ie_pose, w_bucket;
   std::vector<unsigned char> w_self, w_lm_self, w_adj;
@@ -51,6 +64,18 @@ struct svs_ba {
   std::vector<double> w_psi;
   std::vector<int> w_edge_src;
   cudaEvent_t ev[8] = {};
+  // structure of the last problem (index arrays as the caller passed them): a call with the same structure --
+  // the second optimize() of a back-end tick (backend.cpp:186-197), repeated measurement -- skips the structure
+  // analysis and re-sends only the numbers
+  std::vector<int> k_epoint, k_epose, k_eanchor, k_ci, k_cj, k_extra;
+  std::vector<unsigned char> k_fixed;
+  int k_P = -1, k_L = -1, k_E = -1, k_C = -1, k_flags = 0;
+  size_t off_num = 0, off_cT = 0, off_cLam = 0, off_pose0 = 0, off_psi0 = 0, upload_bytes = 0;
+  int reuse_hits = 0;
+  // symbolic factorisation of the last pose graph: reused while the co-visibility pattern (P x P) stays the same,
+  // which it does from tick to tick unless a keyframe enters or leaves the double window
+  Symbolic k_sy; std::vector<unsigned char> k_adj; int k_adjP = -1, k_nbranch = 1, k_nsep = 0, k_nnzb = 0; bool k_natural = false;
+  int symbolic_hits = 0;
   std::vector<cudaEvent_t> tev;   // per-trial timing events
   // last optimize() settings
 };
@@ -144,11 +169,6 @@ void free_arena(svs_ba* h) {
 // Symbolic analysis of the reduced camera system: elimination order (greedy minimum degree on
 // the pose graph, the role AMD plays inside LinearSolverCSparse), block fill, and the update
 // lists of the right-looking block Cholesky.
-struct Symbolic {
-  std::vector<int> perm, pos, col_ptr, row_idx, upd_ptr, upd_dst, upd_ab, urg_dst, tbl, branch_ptr;
-  int max_col_branch = 0, max_col_sep = 0;
-  int nblk = 0;
-};
 
 // `order`: empty = greedy minimum degree (or the caller's order when `natural`), else the elimination
 // order to use (nested dissection, see choose_branches).
@@ -313,6 +333,8 @@ void svs_ba_destroy(svs_ba* h) {
   cudaStreamSynchronize(h->stream);
   free_problem(h);
   free_arena(h);
+  if (h->comm) { if (const NcclApi* nc = nccl_api()) nc->CommDestroy(h->comm); }
+  if (h->d_psi_all) cudaFree(h->d_psi_all);
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->tev) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -341,8 +363,53 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       return fail(h, SVS_ERR_INVALID, "pose-pose edge index out of range");
   cudaSetDevice(h->device);
   CK(cudaStreamSynchronize(h->stream));   // the arena and the staging buffer are about to be reused
-  free_problem(h);
   const bool host_timing = getenv("SVS_HOST_TIMING") != nullptr;
+  // ---- same structure as the problem on the device: only the numbers travel
+  if (h->has_problem && !getenv("SVS_NO_STRUCT_REUSE") && P == h->k_P && L == h->k_L && E == h->k_E && C == h->k_C &&
+      h->flags == h->k_flags && h->extra_pairs == h->k_extra &&
+      (E == 0 || (memcmp(e_point, h->k_epoint.data(), sizeof(int) * E) == 0 && memcmp(e_pose, h->k_epose.data(), sizeof(int) * E) == 0 &&
+                  memcmp(e_anchor, h->k_eanchor.data(), sizeof(int) * E) == 0)) &&
+      (C == 0 || (memcmp(c_i, h->k_ci.data(), sizeof(int) * C) == 0 && memcmp(c_j, h->k_cj.data(), sizeof(int) * C) == 0))) {
+    bool same_fixed = true;
+    for (int p = 0; p < P && same_fixed; ++p) same_fixed = (fixed ? fixed[p] : 0) == h->k_fixed[p];
+    if (same_fixed) {
+      BaDev& d = h->d;
+      d.f = cam->f; d.px = cam->px; d.py = cam->py; d.b = cam->b;
+      if (E > 0 && !d_obs_info) {
+        const size_t bytes = 3 * (size_t)E * sizeof(double);
+        const int parts = 4;
+#pragma omp parallel for num_threads(4)
+        for (int q = 0; q < 2 * parts; ++q) {
+          const char* src = reinterpret_cast<const char*>(q < parts ? e_obs : e_info);
+          char* dst = reinterpret_cast<char*>(h->h_raw) + (q < parts ? 0 : bytes);
+          const int qq = q % parts;
+          const size_t b0 = bytes * qq / parts, b1 = bytes * (qq + 1) / parts;
+          memcpy(dst + b0, src + b0, b1 - b0);
+        }
+        CK(cudaMemcpyAsync(h->d_raw, h->h_raw, 2 * bytes, cudaMemcpyHostToDevice, h->stream));
+      }
+      if (C) {
+        memcpy(h->stage + h->off_cT, c_T, 7 * (size_t)C * sizeof(double));
+        memcpy(h->stage + h->off_cLam, c_Lambda, 36 * (size_t)C * sizeof(double));
+      }
+      if (P) memcpy(h->stage + h->off_pose0, T_qt, 7 * (size_t)P * sizeof(double));
+      double* sp = reinterpret_cast<double*>(h->stage + h->off_psi0);
+      for (int li = 0; li < L; ++li) {
+        const double* src = psi + 3 * (size_t)h->lm_to_user[li];
+        sp[3 * (size_t)li] = src[0]; sp[3 * (size_t)li + 1] = src[1]; sp[3 * (size_t)li + 2] = src[2];
+      }
+      CK(cudaMemcpyAsync(h->arena + h->off_num, h->stage + h->off_num, h->upload_bytes - h->off_num, cudaMemcpyHostToDevice,
+                         h->stream));
+      launch_regroup(d, d_obs_info ? d_obs_info : h->d_raw, h->stream);
+      CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
+      CK(cudaMemsetAsync(d.chi_c, 0, std::max(C, 1) * sizeof(double), h->stream));
+      CK(cudaMemsetAsync(d.chi_c_new, 0, std::max(C, 1) * sizeof(double), h->stream));
+      ++h->reuse_hits;
+      if (host_timing) fprintf(stderr, "set_problem: structure reused (%d)\n", h->reuse_hits);
+      return svs_ba_reset_state(h);
+    }
+  }
+  free_problem(h);
   const int nthr = h->host_threads;
   (void)nthr;
   auto tp0 = std::chrono::steady_clock::now();
@@ -424,18 +491,16 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     for (int k = b + 1; k < en; ++k)
       if (e_pose[eord[k]] == e_pose[eord[k - 1]]) bad = std::max(bad, 2);
     const int K = 1 + (en - b) - nself;
-    if (K > kMaxTrack) bad = std::max(bad, 3);
     l_anchor[l] = anchor; l_self[l] = (unsigned char)nself; l_K[l] = K;
     Kmax = std::max(Kmax, K);
     // locality key: track shape (self flag, length, first and last observer) inside an anchor, so that
     // neighbouring warps of the fused kernel scatter into the same blocks of the reduced system
     const unsigned long long first = (unsigned long long)(e_pose[eord[b + (nself ? 1 : 0) < en ? b + (nself ? 1 : 0) : b]] & 0xfffff);
     const unsigned long long last = (unsigned long long)(e_pose[eord[en - 1]] & 0xfffff);
-    key[l] = ((unsigned long long)(1 - nself) << 43) | ((unsigned long long)K << 40) | (first << 20) | last;
+    key[l] = ((unsigned long long)(nself ? 0 : 1) << 61) | ((unsigned long long)(K & 0xfffff) << 40) | (first << 20) | last;
   }
   if (bad == 1) return fail(h, SVS_ERR_UNSUPPORTED, "edges of one point name different anchor frames");
   if (bad == 2) return fail(h, SVS_ERR_UNSUPPORTED, "a point is observed twice by the same frame");
-  if (bad == 3) return fail(h, SVS_ERR_UNSUPPORTED, "landmark track longer than 31 frames + anchor");
   lap("group");
   // internal landmark order: bucket by anchor (counting sort), then by track shape inside a bucket
   auto& order = h->w_order; auto& bucket = h->w_bucket;
@@ -478,7 +543,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     }
   }
   // ---- work lists of the fused kernel: runs of landmarks with identical slot lists (<= 8 frames)
-  std::vector<int> task_lm, task_cnt, gen_lm;
+  std::vector<int> task_lm, task_cnt, gen_lm, long_lm;   // long_lm: more than kMaxTrack slots (streaming kernel, any length)
   int Kmax_gen = 1;
   {
     int chunk = L / (148 * 16);
@@ -494,6 +559,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     };
     for (int li = 0; li < L; ++li) {
       const int kk = lm_eptr[li + 1] - lm_eptr[li], KK = lm_sptr[li + 1] - lm_sptr[li];
+      if (kk > 0 && KK > kMaxTrack) { long_lm.push_back(li); continue; }
       if (chunk == 0 || kk == 0 || KK > 8) {
         gen_lm.push_back(li);
         Kmax_gen = std::max(Kmax_gen, KK);
@@ -513,15 +579,19 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     auto& A = h->w_adj;
     A.assign((size_t)P * P, 0);
     // (concurrent writers only ever store 1 into a byte: benign)
-#pragma omp parallel for schedule(static) num_threads(nthr) if (L > 4096)
-    for (int l = 0; l < L; ++l) {
-      if (l_anchor[l] < 0) continue;
-      int ps[kMaxTrack + 1];
-      int n = 0;
-      ps[n++] = l_anchor[l];
-      for (int k = eptr[l] + l_self[l]; k < eptr[l + 1]; ++k) ps[n++] = e_pose[eord[k]];
-      for (int x = 0; x < n; ++x)
-        for (int y = x + 1; y < n; ++y) { A[(size_t)ps[x] * P + ps[y]] = 1; A[(size_t)ps[y] * P + ps[x]] = 1; }
+#pragma omp parallel num_threads(nthr) if (L > 4096)
+    {
+      std::vector<int> ps;   // a track has no length limit (slam_graph.cpp:1001-1027)
+#pragma omp for schedule(static)
+      for (int l = 0; l < L; ++l) {
+        if (l_anchor[l] < 0) continue;
+        ps.clear();
+        ps.push_back(l_anchor[l]);
+        for (int k = eptr[l] + l_self[l]; k < eptr[l + 1]; ++k) ps.push_back(e_pose[eord[k]]);
+        const int n = (int)ps.size();
+        for (int x = 0; x < n; ++x)
+          for (int y = x + 1; y < n; ++y) { A[(size_t)ps[x] * P + ps[y]] = 1; A[(size_t)ps[y] * P + ps[x]] = 1; }
+      }
     }
     for (int c = 0; c < C; ++c) { A[(size_t)c_i[c] * P + c_j[c]] = 1; A[(size_t)c_j[c] * P + c_i[c]] = 1; }
     for (size_t q = 0; q + 1 < h->extra_pairs.size(); q += 2) {   // svs_ba_set_structure
@@ -540,16 +610,23 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   }
   lap("adjacency");
   Symbolic sy;
-  {
+  const bool natural_order = (h->flags & SVS_BA_NATURAL_ORDER) != 0;
+  const bool chain_only = getenv("SVS_SOLVE_CHAIN") != nullptr;
+  if (h->k_adjP == P && h->k_natural == natural_order && !chain_only && !getenv("SVS_NO_STRUCT_REUSE") &&
+      h->k_adj.size() == h->w_adj.size() && memcmp(h->k_adj.data(), h->w_adj.data(), h->w_adj.size()) == 0) {
+    sy = h->k_sy;
+    h->nbranch = h->k_nbranch; h->nsep_blk = h->k_nsep;
+    ++h->symbolic_hits;
+  } else {
     // two concurrent branches when the window is banded and each team's share of k_solve's
     // shared-memory ring holds its widest columns, else a single chain (minimum degree order)
-    const bool natural = (h->flags & SVS_BA_NATURAL_ORDER) != 0;
+    const bool natural = natural_order;
     int G = (natural || getenv("SVS_SOLVE_CHAIN")) ? 1 : 2;
     for (;;) {
       std::vector<int> order, bptr;
       G = G > 1 ? choose_branches(P, adj, order, bptr) : 1;
       analyse(P, adj, natural, order, sy);
-      if (G == 1) { sy.branch_ptr = {0, P}; }
+      if (G == 1) { sy.branch_ptr = {0, P}; h->nsep_blk = 0; }
       else sy.branch_ptr = bptr;
       const int sep0 = sy.branch_ptr[G];
       sy.max_col_branch = sy.max_col_sep = 0;
@@ -559,11 +636,14 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
         else sy.max_col_sep = std::max(sy.max_col_sep, nb);
       }
       if (G == 1) break;
-      const int cap = solve_ring_capacity(P, sy.nblk);
-      if (cap / G >= 4 * (sy.max_col_branch + 1) && cap >= 4 * (sy.max_col_sep + 1)) break;
+      // each end of the window is factored by its own CTA: its ring must hold four of the widest columns
+      const int nsep = sy.nblk - sy.col_ptr[sep0];
+      const int cap = solve_ring_capacity(P, sy.nblk, nsep);
+      if (cap >= 4 * (sy.max_col_branch + 1) && cap / 2 >= sy.max_col_sep + 2) { h->nsep_blk = nsep; break; }
       G /= 2;
     }
     h->nbranch = (int)sy.branch_ptr.size() - 1;
+    if (!chain_only) { h->k_sy = sy; h->k_adj = h->w_adj; h->k_adjP = P; h->k_natural = natural_order; h->k_nbranch = h->nbranch; h->k_nsep = h->nsep_blk; }
   }
   if (sy.nblk >= (1 << 20)) return fail(h, SVS_ERR_UNSUPPORTED, "reduced system factor has more than 2^20 blocks");
 
@@ -582,24 +662,36 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
 #define UP(field, vec) dev_upload(h, &d.field, vec)
     UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self);
     UP(e_pose, ie_pose); UP(edge_src, edge_src);
-    UP(task_lm, task_lm); UP(task_cnt, task_cnt); UP(gen_lm, gen_lm);
+    UP(task_lm, task_lm); UP(task_cnt, task_cnt); UP(gen_lm, gen_lm); UP(long_lm, long_lm);
     UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
     UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab); UP(urg_dst, sy.urg_dst);
     UP(branch_ptr, sy.branch_ptr);
     dev_upload(h, &d.c_i, c_i, (size_t)C); dev_upload(h, &d.c_j, c_j, (size_t)C);
-    dev_upload(h, &d.c_T, c_T, 7 * (size_t)C); dev_upload(h, &d.c_Lam, c_Lambda, 36 * (size_t)C);
+    h->off_num = h->off_cT = h->arena_off;   // the numbers (everything a same-structure call re-sends) lie last
+    dev_upload(h, &d.c_T, c_T, 7 * (size_t)C);
+    h->off_cLam = h->arena_off;
+    dev_upload(h, &d.c_Lam, c_Lambda, 36 * (size_t)C);
+    h->off_pose0 = h->arena_off;
     dev_upload(h, &d_pose0c, T_qt, 7 * (size_t)P);
+    h->off_psi0 = h->arena_off;
     dev_upload(h, &d_psi0c, ipsi.data(), 3 * (size_t)L);
 #undef UP
     upload_bytes = h->arena_off;
+    h->upload_bytes = upload_bytes;
 #define AL(field, n) dev_alloc(h, &d.field, (size_t)(n))
     for (int b = 0; b < 2; ++b) { AL(pose[b], 7 * (size_t)P); AL(Rt[b], 12 * (size_t)P); AL(psi[b], 3 * (size_t)L); }
     AL(e_obs_w, 3 * (size_t)E); AL(e_w_w, 3 * (size_t)E);
     AL(W, 18 * (size_t)ns); AL(Dbl, 12 * (size_t)L); AL(chi_l, L); AL(chi_new_l, L); AL(scale_l, L);
-    AL(S, 36 * (size_t)sy.nblk); AL(bp, 6 * (size_t)P); AL(bc, 6 * (size_t)P); AL(x, 6 * (size_t)P);
+    {   // reduced system S | bp | bc | totals in ONE buffer: a sharded window sums it with a single all-reduce
+      double* sys = nullptr;
+      dev_alloc(h, &sys, 36 * (size_t)sy.nblk + 12 * (size_t)P + 4);
+      if (!h->measuring) { d.S = sys; d.bp = sys + 36 * (size_t)sy.nblk; d.bc = d.bp + 6 * (size_t)P; d.totals = d.bc + 6 * (size_t)P; }
+      h->sys_count = 36 * (size_t)sy.nblk + 12 * (size_t)P;
+    }
+    AL(x, 6 * (size_t)P);
     AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
     AL(ctl, 1);
-    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 48); AL(totals, 4);
+    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 48);
 #undef AL
   };
   h->measuring = true;
@@ -621,9 +713,13 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   CK(cudaMemsetAsync(d.chi_c_new, 0, std::max(C, 1) * sizeof(double), h->stream));
   h->Kmax = Kmax;
   h->Kmax_gen = Kmax_gen;
-  d.ntasks = (int)task_lm.size(); d.ngen = (int)gen_lm.size();
+  d.ntasks = (int)task_lm.size(); d.ngen = (int)gen_lm.size(); d.nlong = (int)long_lm.size();
   h->C_edges = C;
   h->has_problem = true;
+  h->k_P = P; h->k_L = L; h->k_E = E; h->k_C = C; h->k_flags = h->flags; h->k_extra = h->extra_pairs;
+  h->k_epoint.assign(e_point, e_point + E); h->k_epose.assign(e_pose, e_pose + E); h->k_eanchor.assign(e_anchor, e_anchor + E);
+  h->k_ci.assign(c_i, c_i + C); h->k_cj.assign(c_j, c_j + C);
+  h->k_fixed = fx;
   return svs_ba_reset_state(h);
 }
 
@@ -631,6 +727,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
                        int E, const int* e_point, const int* e_pose, const int* e_anchor, const double* e_obs,
                        const double* e_info, int C, const int* c_i, const int* c_j, const double* c_T,
                        const double* c_Lambda, const svs_cam* cam) {
+  if (h) h->L_full = 0;
   return set_problem_impl(h, P, T_qt, fixed, L, psi, E, e_point, e_pose, e_anchor, e_obs, e_info, C, c_i, c_j, c_T, c_Lambda,
                           cam, nullptr);
 }
@@ -692,26 +789,45 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     CKO(cudaMemcpyAsync(d.ctl, h->h_ctl, sizeof(LmCtl), cudaMemcpyHostToDevice, h->stream));
   }
   if ((rc = clear_system(h))) return -100 + rc;
-  float ms[4] = {0, 0, 0, 0};  // build, solve, update(+decision)
+  float ms[4] = {0, 0, 0, 0};  // build, solve, update(+decision), collectives
   int launches = 0;
   CKO(cudaEventRecord(h->ev[0], h->stream));
   int it = 0;
-  const int per_trial = 2 + ((d.ntasks > 0 || d.C > 0) ? 1 : 0) + (d.ngen > 0 ? 1 : 0);
+  const NcclApi* nc = h->comm ? nccl_api() : nullptr;   // sharded window: sums across ranks on this stream
+  if (h->comm && !nc) { h->err = "NCCL library not loadable"; return -100 + SVS_ERR_STATE; }
+  const int per_trial = 2 + ((d.ntasks > 0 || d.C > 0) ? 1 : 0) + (d.ngen > 0 ? 1 : 0) + (d.nlong > 0 ? 1 : 0) + (nc ? 1 : 0);
+#define CKN(call)                                                       \
+  do {                                                                  \
+    const int e_ = (call);                                              \
+    if (e_ != 0) {                                                      \
+      h->err = std::string(#call) + ": " + nc->GetErrorString(e_);      \
+      return -100 + SVS_ERR_CUDA;                                       \
+    }                                                                   \
+  } while (0)
+  constexpr int kEv = 6;   // events per trial: start | built | summed | solved | updated | decided
   for (;;) {
     // Enqueue one Levenberg trial per remaining iteration without waiting for the device: every
     // trial is the same launch sequence, and the device-side control block decides whether a trial
     // is the next iteration or the retry of a rejected step.  Trials enqueued past the end (or after
     // Terminate) return at once (LmCtl::max_iters).  Only rejected steps cost another round trip.
     const int ntr = num_iters - it;
-    while ((int)h->tev.size() < 4 * ntr) { cudaEvent_t e; cudaEventCreate(&e); h->tev.push_back(e); }
+    while ((int)h->tev.size() < kEv * ntr) { cudaEvent_t e; cudaEventCreate(&e); h->tev.push_back(e); }
     for (int k = 0; k < ntr; ++k) {
-      CKO(cudaEventRecord(h->tev[4 * k + 0], h->stream));
+      CKO(cudaEventRecord(h->tev[kEv * k + 0], h->stream));
       launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
-      CKO(cudaEventRecord(h->tev[4 * k + 1], h->stream));
-      launch_solve(d, h->max_col_branch, h->max_col_blocks, h->stream);
-      CKO(cudaEventRecord(h->tev[4 * k + 2], h->stream));
-      launch_update(d, robust, huber_delta, 0, h->stream);
-      CKO(cudaEventRecord(h->tev[4 * k + 3], h->stream));
+      CKO(cudaEventRecord(h->tev[kEv * k + 1], h->stream));
+      // every rank holds the partial reduced system of its landmarks: ONE all-reduce of S | bp | bc
+      if (nc) CKN(nc->AllReduce(d.S, d.S, h->sys_count, kNcclFloat64, kNcclSum, h->comm, h->stream));
+      CKO(cudaEventRecord(h->tev[kEv * k + 2], h->stream));
+      launch_solve(d, h->max_col_branch, h->max_col_blocks, h->nsep_blk, h->stream);
+      CKO(cudaEventRecord(h->tev[kEv * k + 3], h->stream));
+      launch_update(d, robust, huber_delta, nc ? 1 : 0, h->stream);
+      CKO(cudaEventRecord(h->tev[kEv * k + 4], h->stream));
+      if (nc) {   // chi2 (accepted, trial) and the gain-ratio denominator of this rank's landmarks -> the same decision everywhere
+        CKN(nc->AllReduce(d.totals, d.totals, 3, kNcclFloat64, kNcclSum, h->comm, h->stream));
+        launch_decide_deferred(d, h->stream);
+      }
+      CKO(cudaEventRecord(h->tev[kEv * k + 5], h->stream));
     }
     CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
     CKO(cudaStreamSynchronize(h->stream));
@@ -719,12 +835,14 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     const int done_trials = h->h_ctl->trials_total - trials_seen;
     trials_seen = h->h_ctl->trials_total;
     launches += per_trial * done_trials;
-    for (int k = 0; k < done_trials && k < ntr; ++k)
-      for (int q = 0; q < 3; ++q) {
+    for (int k = 0; k < done_trials && k < ntr; ++k) {
+      static const int slot[kEv - 1] = {0, 3, 1, 2, 3};   // build | collective | solve | update | collective + decision
+      for (int q = 0; q < kEv - 1; ++q) {
         float t = 0;
-        cudaEventElapsedTime(&t, h->tev[4 * k + q], h->tev[4 * k + q + 1]);
-        ms[q] += t;
+        cudaEventElapsedTime(&t, h->tev[kEv * k + q], h->tev[kEv * k + q + 1]);
+        ms[slot[q]] += t;
       }
+    }
     it = h->h_ctl->iter;
     if (it >= num_iters || (h->h_ctl->stop && !h->h_ctl->again)) break;
   }
@@ -752,16 +870,19 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
   if (getenv("SVS_SOLVE_TIMING")) {
     long long dbg[48];
     cudaMemcpy(dbg, d.dbg, sizeof dbg, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "profile (SVS_SOLVE_PROFILE builds): panel diag-upd %lld chol %lld bar_panel %lld scale %lld bar_all %lld | "
-            "update work %lld bar_all %lld\n", dbg[24], dbg[25], dbg[26], dbg[27], dbg[28], dbg[37], dbg[38]);
-    fprintf(stderr, "k_solve cycles since setup (branches done, +barrier, separators done, back seps, back branches, end):\n");
-    for (int g = 0; g < 4; ++g) {
-      fprintf(stderr, "  team %d:", g);
+    fprintf(stderr, "k_solve cycles since setup (branch factored, cluster sync, separators factored, separators solved + sync, "
+            "branch solved, end):\n");
+    for (int g = 0; g < 2; ++g) {
+      fprintf(stderr, "  CTA %d:", g);
       for (int i = 0; i < 6; ++i) fprintf(stderr, " %lld", dbg[g * 6 + i]);
-      fprintf(stderr, "\n");
+      const long long* q = dbg + 12 + 12 * g;
+      fprintf(stderr, "\n     chain: hand-over %lld chol %lld wait-updates %lld load+publish %lld | helper 0: wait-factor %lld rows %lld "
+              "barrier %lld updates %lld | last helper: %lld %lld %lld %lld\n", q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8],
+              q[9], q[10], q[11]);
     }
   }
   return h->h_ctl->iter;
+#undef CKN
 #undef CKO
 }
 
@@ -792,8 +913,10 @@ int svs_ba_get_points(svs_ba* h, double* psi) {
   std::vector<double> tmp(3 * (size_t)L);
   if (L) CK(cudaMemcpyAsync(tmp.data(), h->d.psi[cur], 3 * (size_t)L * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  // a sharded window (svs_ba_set_problem_sharded) addresses the caller's full-size array: only this rank's entries are written
+  const size_t mul = h->L_full ? (size_t)h->comm_size : 1, add = h->L_full ? (size_t)h->comm_rank : 0;
   for (int li = 0; li < L; ++li)
-    for (int q = 0; q < 3; ++q) psi[3 * (size_t)h->lm_to_user[li] + q] = tmp[3 * (size_t)li + q];
+    for (int q = 0; q < 3; ++q) psi[3 * ((size_t)h->lm_to_user[li] * mul + add) + q] = tmp[3 * (size_t)li + q];
   return SVS_OK;
 }
 
@@ -896,7 +1019,7 @@ int svs_ba_solve_reduced(svs_ba* h, int robust, double huber_delta, double lambd
   if ((rc = set_lambda(h, lambda))) return rc;
   if ((rc = clear_system(h))) return rc;
   launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
-  launch_solve(d, h->max_col_branch, h->max_col_blocks, h->stream);
+  launch_solve(d, h->max_col_branch, h->max_col_blocks, h->nsep_blk, h->stream);
   if (d.P) CK(cudaMemcpyAsync(x, d.x, 6 * (size_t)d.P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -904,6 +1027,119 @@ int svs_ba_solve_reduced(svs_ba* h, int robust, double huber_delta, double lambd
   const int failed = h->h_ctl->chol_fail;
   if ((rc = clear_system(h))) return rc;
   return failed ? 1 : 0;
+}
+
+// ---- one window sharded by landmarks across GPUs, driven inside the library (BASELINE config C5)
+
+int svs_comm_unique_id(char id[128]) {
+  const NcclApi* nc = nccl_api();
+  if (!nc || !id) return SVS_ERR_STATE;
+  NcclUniqueId u;
+  if (nc->GetUniqueId(&u) != 0) return SVS_ERR_CUDA;
+  memcpy(id, u.internal, 128);
+  return SVS_OK;
+}
+
+int svs_ba_comm_init(svs_ba* h, int nranks, int rank, const char id[128]) {
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return SVS_ERR_INVALID;
+  const NcclApi* nc = nccl_api();
+  if (!nc) return fail(h, SVS_ERR_STATE, "NCCL library not loadable");
+  cudaSetDevice(h->device);
+  if (h->comm) { nc->CommDestroy(h->comm); h->comm = nullptr; }
+  NcclUniqueId u;
+  memcpy(u.internal, id, 128);
+  const int e = nc->CommInitRank(&h->comm, nranks, u, rank);
+  if (e != 0) { h->comm = nullptr; return fail(h, SVS_ERR_CUDA, std::string("ncclCommInitRank: ") + nc->GetErrorString(e)); }
+  h->comm_rank = rank; h->comm_size = nranks;
+  return SVS_OK;
+}
+
+// The whole window goes in on every rank; this rank keeps landmarks l with l % nranks == rank and their
+// edges (poses replicated, pose-pose constraints on rank 0) and the block pattern of the WHOLE window, so
+// that every rank's reduced system has the same layout and one all-reduce per trial sums them.
+int svs_ba_set_problem_sharded(svs_ba* h, int P, const double* T_qt, const unsigned char* fixed, int L, const double* psi,
+                               int E, const int* e_point, const int* e_pose, const int* e_anchor, const double* e_obs,
+                               const double* e_info, int C, const int* c_i, const int* c_j, const double* c_T,
+                               const double* c_Lambda, const svs_cam* cam) {
+  if (!h) return SVS_ERR_INVALID;
+  if (P < 0 || L < 0 || E < 0 || C < 0) return fail(h, SVS_ERR_INVALID, "negative size");
+  if (E && (!e_point || !e_pose || !e_anchor || !e_obs || !e_info)) return fail(h, SVS_ERR_INVALID, "null array");
+  const int W = h->comm_size, R = h->comm_rank;
+  for (int e = 0; e < E; ++e)
+    if (e_point[e] < 0 || e_point[e] >= L || e_pose[e] < 0 || e_pose[e] >= P || e_anchor[e] < 0 || e_anchor[e] >= P)
+      return fail(h, SVS_ERR_INVALID, "observation edge index out of range");
+  // block pattern of the whole window: pose pairs coupled by any landmark track (anchor included)
+  {
+    std::vector<int> ptr(L + 1, 0), ord(E);
+    for (int e = 0; e < E; ++e) ptr[e_point[e] + 1]++;
+    for (int l = 0; l < L; ++l) ptr[l + 1] += ptr[l];
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int e = 0; e < E; ++e) ord[fill[e_point[e]]++] = e;
+    std::vector<unsigned char> A((size_t)P * P, 0);
+    std::vector<int> ps;
+    h->extra_pairs.clear();
+    for (int l = 0; l < L; ++l) {
+      if (ptr[l] == ptr[l + 1]) continue;
+      ps.clear();
+      ps.push_back(e_anchor[ord[ptr[l]]]);
+      for (int k = ptr[l]; k < ptr[l + 1]; ++k) ps.push_back(e_pose[ord[k]]);
+      for (size_t x = 0; x < ps.size(); ++x)
+        for (size_t y = x + 1; y < ps.size(); ++y) {
+          const int a = std::min(ps[x], ps[y]), b = std::max(ps[x], ps[y]);
+          if (a != b && !A[(size_t)a * P + b]) { A[(size_t)a * P + b] = 1; h->extra_pairs.push_back(a); h->extra_pairs.push_back(b); }
+        }
+    }
+    for (int c = 0; c < C; ++c) {
+      const int a = std::min(c_i[c], c_j[c]), b = std::max(c_i[c], c_j[c]);
+      if (a < 0 || b >= P) return fail(h, SVS_ERR_INVALID, "pose-pose edge index out of range");
+      if (a != b && !A[(size_t)a * P + b]) { A[(size_t)a * P + b] = 1; h->extra_pairs.push_back(a); h->extra_pairs.push_back(b); }
+    }
+  }
+  // this rank's share
+  const int Ll = L > R ? (L - R + W - 1) / W : 0;
+  std::vector<double> lpsi(3 * (size_t)Ll);
+  for (int l = R, q = 0; l < L; l += W, ++q)
+    for (int k = 0; k < 3; ++k) lpsi[3 * (size_t)q + k] = psi[3 * (size_t)l + k];
+  std::vector<int> lp, lf, la;
+  std::vector<double> lo, li;
+  lp.reserve(E / W + 16); lf.reserve(E / W + 16); la.reserve(E / W + 16); lo.reserve(3 * (size_t)(E / W + 16)); li.reserve(3 * (size_t)(E / W + 16));
+  for (int e = 0; e < E; ++e) {
+    if (e_point[e] % W != R) continue;
+    lp.push_back(e_point[e] / W); lf.push_back(e_pose[e]); la.push_back(e_anchor[e]);
+    for (int k = 0; k < 3; ++k) { lo.push_back(e_obs[3 * (size_t)e + k]); li.push_back(e_info[3 * (size_t)e + k]); }
+  }
+  const int Cl = R == 0 ? C : 0;
+  const int rc = set_problem_impl(h, P, T_qt, fixed, Ll, lpsi.data(), (int)lp.size(), lp.data(), lf.data(), la.data(), lo.data(),
+                                  li.data(), Cl, c_i, c_j, c_T, c_Lambda, cam, nullptr);
+  h->extra_pairs.clear();
+  h->L_full = rc == SVS_OK ? L : 0;
+  return rc;
+}
+
+// restoreDataFromG2o on every rank: all landmarks of the sharded window (each rank contributes its own,
+// summed over the communicator)
+int svs_ba_get_points_all(svs_ba* h, double* psi) {
+  if (!h || !h->has_problem || !psi) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
+  if (!h->L_full) return svs_ba_get_points(h, psi);
+  const size_t n = 3 * (size_t)h->L_full;
+  std::fill(psi, psi + n, 0.);
+  int rc;
+  if ((rc = svs_ba_get_points(h, psi))) return rc;
+  if (!h->comm || h->comm_size == 1) return SVS_OK;
+  const NcclApi* nc = nccl_api();
+  if (!nc) return fail(h, SVS_ERR_STATE, "NCCL library not loadable");
+  if (n > h->psi_all_cap) {
+    if (h->d_psi_all) cudaFree(h->d_psi_all);
+    h->d_psi_all = nullptr; h->psi_all_cap = 0;
+    CK(cudaMalloc((void**)&h->d_psi_all, n * sizeof(double)));
+    h->psi_all_cap = n;
+  }
+  CK(cudaMemcpyAsync(h->d_psi_all, psi, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (nc->AllReduce(h->d_psi_all, h->d_psi_all, n, kNcclFloat64, kNcclSum, h->comm, h->stream) != 0)
+    return fail(h, SVS_ERR_CUDA, "ncclAllReduce failed");
+  CK(cudaMemcpyAsync(psi, h->d_psi_all, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SVS_OK;
 }
 
 // ---- stepwise Levenberg trial for a window whose landmarks are split across ranks
@@ -953,7 +1189,7 @@ int svs_ba_system_buffers(svs_ba* h, double** S, long long* nS, double** bp, dou
 int svs_ba_trial_solve(svs_ba* h, int robust, double huber_delta) {
   if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
   cudaSetDevice(h->device);
-  launch_solve(h->d, h->max_col_branch, h->max_col_blocks, h->stream);
+  launch_solve(h->d, h->max_col_branch, h->max_col_blocks, h->nsep_blk, h->stream);
   launch_update(h->d, robust, huber_delta, 1, h->stream);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));

@@ -8,7 +8,7 @@
 namespace svs {
 
 constexpr int kMaxIters = 64;
-constexpr int kMaxTrack = 32;  // slots per landmark (anchor + observers) the fused kernel stages in smem
+constexpr int kMaxTrack = 32;  // slots per landmark (anchor + observers) k_build stages in smem; longer tracks -> k_build_long
 
 // Levenberg-Marquardt control block, lives in device memory; mirrors the locals of
 // g2o::OptimizationAlgorithmLevenberg::solve (configured at slam_graph.cpp:336-346,1071-1073).
@@ -47,8 +47,9 @@ struct BaDev {
   // fused-kernel work lists: tasks = runs of landmarks with identical slot lists and <= 8 frames
   const int* task_lm;   // [ntasks] first landmark
   const int* task_cnt;  // [ntasks] landmarks in the task
-  const int* gen_lm;    // [ngen] landmarks handled one warp each (long tracks, no observations)
-  int ntasks, ngen;
+  const int* gen_lm;    // [ngen] landmarks handled one warp each (9..32 slots, no observations)
+  const int* long_lm;   // [nlong] landmarks with more than kMaxTrack slots (k_build_long)
+  int ntasks, ngen, nlong;
   // edges (internal order)
   const int* e_pose;    // [E]
   const int* edge_src;  // internal edge -> index in the caller's arrays

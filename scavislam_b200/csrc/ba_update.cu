@@ -3,7 +3,21 @@
 #include "ba_dev.cuh"
 #include "ba_kernels.cuh"
 
+#include <mutex>
+
 namespace svs {
+
+bool device_needs_smem_optin(int slot, size_t bytes) {
+  static size_t granted[64][4] = {};
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || slot < 0 || slot >= 4) return true;
+  std::lock_guard<std::mutex> lk(mu);
+  if (bytes <= granted[dev][slot]) return false;
+  granted[dev][slot] = bytes;
+  return true;
+}
 
 // ------------------------------------------------------------------ k_update (+ LM decision)
 

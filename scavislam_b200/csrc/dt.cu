@@ -145,6 +145,7 @@ __device__ void accumulate_pass(const DtLevel& L, const double T[7], int exact, 
     double s = 0;
     for (int w = 0; w < kThreads / 32; ++w) s += sred[w][threadIdx.x];
     partial[(size_t)blockIdx.x * kAcc + threadIdx.x] = s;
+    __threadfence();   // visible to the CTA that sums the partials (k_dt_track_level's ticket)
   }
   __syncthreads();
 }
@@ -188,39 +189,61 @@ __device__ void propose_step(DtCtl* c) {
 }
 
 // The LM loop of DenseTracker::denseTrackingGpu for one level (dense_tracking.cpp:90-178).
+// One grid-wide rendezvous per pass: every CTA publishes its partial sums and takes a ticket; the LAST CTA to
+// arrive sums the partials with all its threads in a fixed order (8 segments x 28 components, independent of
+// which CTA happens to be last), takes the Levenberg decision, writes the next pose and bumps a generation
+// counter the other CTAs spin on (all CTAs are co-resident: cooperative launch).
+constexpr int kSeg = 8;
 __global__ void __launch_bounds__(kThreads)
-k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, int exact, int level) {
+k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exact, int level) {
   __shared__ double sred[kThreads / 32][kAcc];
+  __shared__ double sseg[kSeg][kAcc];
   __shared__ double ssum[kAcc];
-  cg::grid_group grid = cg::this_grid();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int k = 0; k < 7; ++k) ctl->Teval[k] = ctl->T[k];
-    ctl->phase = 0; ctl->done = 0; ctl->passes = 0;
-  }
-  grid.sync();
-  for (;;) {
+  __shared__ unsigned sGen;
+  __shared__ int sLast;
+  if (threadIdx.x == 0) sGen = *(volatile unsigned*)&sync[1];   // no CTA can bump it before every CTA has arrived once
+  __syncthreads();
+  unsigned gen = sGen;
+  for (int pass = 0;; ++pass) {
     double Te[7];
+    const double* Tsrc = pass == 0 ? ctl->T : ctl->Teval;   // the first pass evaluates the incoming pose
 #pragma unroll
-    for (int k = 0; k < 7; ++k) Te[k] = __ldcg(&ctl->Teval[k]);
+    for (int k = 0; k < 7; ++k) Te[k] = __ldcg(&Tsrc[k]);
     accumulate_pass(L, Te, exact, true, partial, sred);
-    grid.sync();
-    if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      sLast = atomicAdd(&sync[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (sLast) {
+      __threadfence();
+      {
+        const int i = threadIdx.x & 31, seg = threadIdx.x >> 5;   // kThreads / 32 == kSeg
+        if (i < kAcc) {
+          double s = 0;
+          for (unsigned b = seg; b < gridDim.x; b += kSeg) s += __ldcg(&partial[(size_t)b * kAcc + i]);
+          sseg[seg][i] = s;
+        }
+      }
+      __syncthreads();
       if (threadIdx.x < kAcc) {
         double s = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partial[(size_t)b * kAcc + threadIdx.x]);
+#pragma unroll
+        for (int q = 0; q < kSeg; ++q) s += sseg[q][threadIdx.x];
         ssum[threadIdx.x] = s;
       }
       __syncthreads();
       if (threadIdx.x == 0) {
         DtCtl* c = ctl;
-        c->passes += 1;
-        if (c->phase == 0) {   // chi2 and (H, b) at the incoming pose
+        if (pass == 0) {   // chi2 and (H, b) at the incoming pose
+          c->passes = 1;
           for (int i = 0; i < 21; ++i) c->H[i] = ssum[i];
           for (int i = 0; i < 6; ++i) c->b[i] = ssum[21 + i];
           c->chi2 = ssum[27];
-          c->mu = (double)0.01f; c->nu = 2.; c->trial = 0; c->stop = 0; c->iter = 0; c->phase = 1;
+          c->mu = (double)0.01f; c->nu = 2.; c->trial = 0; c->stop = 0; c->iter = 0; c->phase = 1; c->done = 0;
           propose_step(c);
         } else {
+          c->passes += 1;
           const double chin = ssum[27];
           const double rho = c->chi2 - chin;
           bool finished = false;
@@ -252,10 +275,17 @@ k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, int exact, int level) {
             propose_step(c);
           }
         }
+        sync[0] = 0;
         __threadfence();
+        atomicAdd(&sync[1], 1u);   // releases the other CTAs
       }
     }
-    grid.sync();
+    if (threadIdx.x == 0) {
+      while (*(volatile unsigned*)&sync[1] == gen) {}
+      __threadfence();
+    }
+    __syncthreads();
+    ++gen;
     if (__ldcg(&ctl->done)) break;
   }
 }
@@ -309,7 +339,9 @@ struct svs_dt {
   DtCtl* h_ctl = nullptr;
   double* d_partial = nullptr;
   double* d_T = nullptr;
-  int max_blocks = 0;
+  unsigned* d_sync = nullptr;   // ticket, generation of k_dt_track_level
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int max_blocks = 0, track_blocks = 0;
   float* stage = nullptr;   // pinned staging for image uploads
   size_t stage_floats = 0;
 };
@@ -354,11 +386,16 @@ int svs_dt_create(int device, int w0, int h0, int nlevels, int flags, svs_dt** o
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dt_track_level, kThreads, 0);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     h->max_blocks = std::max(1, per_sm * sms);
+    // the tracker's passes are latency-bound (rendezvous + 6x6 solve per pass): two CTAs per SM keep the
+    // final sum short and still cover a 640x480 level with 4 pixels per thread
+    h->track_blocks = std::max(1, std::min(per_sm, 2) * sms);
   }
   const int part_blocks = std::max(h->max_blocks, (w0 * h0 + kThreads - 1) / kThreads);
   ok = ok && cudaMalloc(&h->d_ctl, sizeof(DtCtl)) == cudaSuccess && cudaMemset(h->d_ctl, 0, sizeof(DtCtl)) == cudaSuccess &&
        cudaMalloc(&h->d_partial, sizeof(double) * kAcc * (size_t)part_blocks) == cudaSuccess &&
        cudaMalloc(&h->d_T, sizeof(double) * 8) == cudaSuccess &&
+       cudaMalloc(&h->d_sync, sizeof(unsigned) * 2) == cudaSuccess && cudaMemset(h->d_sync, 0, sizeof(unsigned) * 2) == cudaSuccess &&
+       cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess &&
        cudaMallocHost(&h->h_ctl, sizeof(DtCtl)) == cudaSuccess;
   h->stage_floats = (size_t)h->disp_stride * h0 * 4;
   ok = ok && cudaMallocHost(&h->stage, sizeof(float) * h->stage_floats) == cudaSuccess;
@@ -378,7 +415,9 @@ void svs_dt_destroy(svs_dt* h) {
     for (int k = 0; k < 4; ++k) cudaFree(h->img[l][k]);
     cudaFree(h->cloud[l]);
   }
-  cudaFree(h->disp); cudaFree(h->d_ctl); cudaFree(h->d_partial); cudaFree(h->d_T);
+  cudaFree(h->disp); cudaFree(h->d_ctl); cudaFree(h->d_partial); cudaFree(h->d_T); cudaFree(h->d_sync);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->stage) cudaFreeHost(h->stage);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -539,17 +578,17 @@ int svs_dt_track(svs_dt* h, double T[7], svs_dt_stats* st) {
   if (!h || !T) return SVS_ERR_INVALID;
   cudaSetDevice(h->device);
   DCK(cudaMemcpyAsync(h->d_ctl, T, sizeof(double) * 7, cudaMemcpyHostToDevice, h->stream));   // DtCtl::T is first
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEvent_t e0 = h->ev0, e1 = h->ev1;   // created once with the handle: nothing is allocated per frame
   cudaEventRecord(e0, h->stream);
   int exact = (h->flags & SVS_DT_EXACT_BILINEAR) ? 1 : 0;
   for (int l = h->nlevels - 1; l >= 0; --l) {
     DtLevel L = h->lv[l];
-    int blocks = std::min(h->max_blocks, std::max(1, (L.w * L.h + kThreads - 1) / kThreads));
+    int blocks = std::min(h->track_blocks, std::max(1, (L.w * L.h + kThreads - 1) / kThreads));
     DtCtl* ctl = h->d_ctl;
     double* part = h->d_partial;
+    unsigned* sync = h->d_sync;
     int level = l;
-    void* args[] = {&L, &ctl, &part, &exact, &level};
+    void* args[] = {&L, &ctl, &part, &sync, &exact, &level};
     DCK(cudaLaunchCooperativeKernel((void*)k_dt_track_level, dim3(blocks), dim3(kThreads), args, 0, h->stream));
   }
   cudaEventRecord(e1, h->stream);
@@ -566,7 +605,6 @@ int svs_dt_track(svs_dt* h, double T[7], svs_dt_stats* st) {
       st->launches += 1;
     }
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return SVS_OK;
 }
 

@@ -271,3 +271,54 @@ def make_window(P: int, L: int, seed: int, T: int = 8, name: str = "",
 def make_config(name: str) -> BAProblem:
     P, L, idx = CONFIGS[name]
     return make_window(P, L, 1234 + idx, name=name)
+
+
+# ---------------------------------------------------------------- structure variants of a window (bench / parity extras)
+
+def with_dropouts(pb: BAProblem, frac: float = 0.2, seed: int = 0) -> BAProblem:
+    """The same window with `frac` of the non-anchor observations missing at random (matching failures): tracks
+    get holes, so neighbouring landmarks stop sharing one slot list."""
+    rng = np.random.default_rng(seed)
+    keep = (pb.e_pose == pb.e_anchor) | (rng.uniform(size=pb.E) >= frac)
+    out = pb.copy()
+    for k in ("e_point", "e_pose", "e_anchor", "e_obs", "e_info"):
+        setattr(out, k, np.ascontiguousarray(getattr(pb, k)[keep]))
+    out.E = int(keep.sum())
+    out.name = f"{pb.name}+dropouts{int(round(100 * frac))}"
+    return out
+
+
+def with_loop_closures(pb: BAProblem, n: int = 10, seed: int = 0, min_gap=None) -> BAProblem:
+    """The same window plus `n` loop-closure constraints between far-apart keyframes (both orders, as
+    copyContraintsToG2o adds them: slam_graph.cpp:941-980), measurements taken from the truth with a little noise.
+    They break the band of the reduced camera system."""
+    rng = np.random.default_rng(seed)
+    P = pb.P
+    gap = min_gap if min_gap is not None else P // 3
+    R = quat_to_R(pb.truth_pose_qt[:, :4])
+    t = pb.truth_pose_qt[:, 4:]
+    ci, cj, cT, cL = list(pb.c_i), list(pb.c_j), list(pb.c_T), list(pb.c_Lambda)
+    seen = set()
+    while len(seen) < n:
+        i = int(rng.integers(0, P - gap))
+        j = int(rng.integers(i + gap, P))
+        if (i, j) in seen:
+            continue
+        seen.add((i, j))
+        for (a, b) in ((i, j), (j, i)):
+            nR, nt = _exp_se3((rng.normal(0, 1, 6) * np.array([0.005] * 3 + [0.001] * 3))[None])
+            Rba = nR[0] @ (R[b] @ R[a].T)
+            tba = nR[0] @ (t[b] - R[b] @ R[a].T @ t[a]) + nt[0]
+            lam = np.zeros((6, 6))
+            lam[:3, :3] = np.eye(3) * 4e4
+            lam[3:, 3:] = np.eye(3) * 1e5
+            ci.append(a); cj.append(b)
+            cT.append(_to_qt(Rba[None], tba[None])[0])
+            cL.append(lam.reshape(36))
+    out = pb.copy()
+    out.C = len(ci)
+    out.c_i = np.asarray(ci, np.int32); out.c_j = np.asarray(cj, np.int32)
+    out.c_T = np.asarray(cT, np.float64).reshape(out.C, 7)
+    out.c_Lambda = np.asarray(cL, np.float64).reshape(out.C, 36)
+    out.name = f"{pb.name}+loops{n}"
+    return out

@@ -201,6 +201,18 @@ def test_long_tracks_use_the_generic_build_kernel(ba, oracle):
     assert st["max_track"] > 8
 
 
+def test_tracks_longer_than_32_frames(ba, oracle):
+    """A slowly moving camera: tracks of up to 50 frames + anchor.  The reference adds one edge per in-window
+    frame of vis_set without any cap (slam_graph.cpp:1001-1027): the streaming kernel k_build_long takes them."""
+    pb = synth.make_window(70, 900, seed=36, T=50)
+    st = _check_against_oracle(ba, oracle, pb)
+    assert st["max_track"] > 33
+    ba.set_problem(pb)   # back to the initial state (same structure: only the numbers travel)
+    S, bs, chi = ba.reduced_system(True, 1.0, 50.0)
+    So, bso, chio = oracle.reduced_system(pb, True, 1.0, 50.0)
+    assert _rel(S, So) < 1e-11 and _rel(bs, bso) < 1e-10 and abs(chi - chio) <= 1e-11 * abs(chio)
+
+
 def test_loop_closures_break_the_band(ba, oracle):
     """Constraints between far-apart keyframes: no two-ended split, minimum-degree order with fill."""
     pb = _add_constraints(synth.make_window(60, 3000, seed=32), [(0, 59), (59, 0), (5, 40), (12, 55), (20, 58)])
@@ -234,3 +246,18 @@ def test_two_ended_split_is_used_and_equals_the_chain(ba, oracle, svs):
         b2.close()
     finally:
         del os.environ["SVS_SOLVE_CHAIN"]
+
+
+# ---------------------------------------------------------------- C2-sized structure variants (bench extras)
+
+def test_c2_with_visibility_dropouts_full_size(ba, oracle):
+    """C2 with 20 % of the observations missing at random: tracks with holes, chunk-of-one tasks."""
+    pb = synth.with_dropouts(synth.make_config("C2"), 0.2, seed=1)
+    _check_against_oracle(ba, oracle, pb, iters=10)
+
+
+def test_c2_with_loop_closures_full_size(ba, oracle):
+    """C2 plus 10 loop-closure constraints between far-apart keyframes: the band is broken."""
+    pb = synth.with_loop_closures(synth.make_config("C2"), 10, seed=1)
+    st = _check_against_oracle(ba, oracle, pb, iters=10)
+    assert st["nnzb_L"] > st["nnzb_S"]

@@ -81,3 +81,19 @@ def test_two_gpu_nccl_sharded_window(svs, oracle):
         assert _rel(poses, p_o) < 1e-6
         psi[idx] = p
     assert _rel(psi, s_o) < 1e-6
+
+
+def test_in_library_nccl_window(svs, oracle):
+    """The sharded window driven inside the library (C ABI: svs_ba_comm_init / svs_ba_set_problem_sharded /
+    svs_ba_optimize with one ncclAllReduce of S|bp|bc per trial), one process per visible GPU (two when the
+    box has them, else a one-rank communicator: same code path, collectives degenerate)."""
+    import subprocess
+    import sys
+    import torch
+    n = min(2, torch.cuda.device_count())
+    port = 29700 + os.getpid() % 1000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(os.path.dirname(os.path.abspath(__file__)), "nccl_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "NCCL_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
