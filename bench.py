@@ -157,12 +157,18 @@ def run_reference(args):
 
 
 def run_ours(args):
-    import torch
-    from scavislam_b200 import capi, synth
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    seq = None
+    if rank == 0 and args.frames > 1:
+        # the synthetic 640x480 stereo sequence of config C3, rendered by a process pool BEFORE torch / CUDA exist in
+        # this process (input generation, untimed)
+        from scavislam_b200 import synth_images as si
+        seq = si.sequence(args.frames, workers=min(32, os.cpu_count() or 1))
+    import torch
+    from scavislam_b200 import capi, synth
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
@@ -296,7 +302,7 @@ def run_ours(args):
     (ms_max, e2e_max, e2e2_max), (tot_iters, tot_e2e, tot_launch, tot_e2e2) = sdist.reduce_job_totals(
         [ms, e2e_s, e2e2_s], [iters, e2e_iters, launches, e2e2_iters], dist, device="cuda")
     tot_launch = int(tot_launch)
-    fe = frontend_bench(local) if rank == 0 else None
+    fe = frontend_bench(local, seq) if (rank == 0 and seq is not None) else None
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -439,23 +445,20 @@ def c5_sharded_block(args, torch, dist, rank, world, local, flush):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
-def frontend_bench(device, n_frames=12):
-    """Second half of the BASELINE metric: front-end frames/sec at 640x480 (config C3) --
-    grid FAST (2 levels, adaptive) + dense tracking (3 levels) + dense point cloud + guided
-    matching against the previous frame, through the C ABI.  `fps_e2e` takes the raw left image and the disparity maps from
-    host memory each frame and includes the pyramid/gradient preprocessing (svs_prep_*); `fps_resident` re-runs the kernels on the data already on the device."""
+def frontend_bench(device, seq):
+    """Second half of the BASELINE metric: front-end frames/sec at 640x480 (config C3, SURVEY.md 8d: a 200-frame synthetic
+    stereo sequence, 2 cm / 0.2 deg per frame) -- preprocessing (pyramids, gradients) + grid FAST (2 levels, adaptive) +
+    dense tracking (3 levels) + dense point cloud + guided matching against the previous frame + motion-only LM, through the
+    C ABI.  `fps_e2e` takes the raw left image and the disparity map from host memory every frame; `fps_resident` re-runs
+    the kernels of the last frame pair on data already on the device."""
     import numpy as np
     import torch
     from oracle import pyoracle as po
-    from scavislam_b200 import capi, frontend_inputs as fi, synth_images as si
-    seq = si.sequence(4)
+    from scavislam_b200 import capi, frontend_inputs as fi
     cams = fi.level_cams()
     I7 = np.array([0, 0, 0, 1, 0, 0, 0.0])
     lv2 = [(640 >> l, 480 >> l, cams[l][0], cams[l][1], cams[l][2]) for l in range(2)]
-    frames = []
-    for f in seq:                      # host pyramids/gradients (OpenCV) feed the CPU baseline only
-        fp = fi.float_pyramid(f["img"])
-        frames.append(dict(img=f["img"], u8=fi.uint8_pyramid(f["img"], 2), f32=fp, grad=[fi.gradients(x) for x in fp], disp=f["disp"]))
+    n_frames = len(seq) - 1
     grids = [capi.FastGrid(640, 480, 222, 74, 25, 3, 3, device=device), capi.FastGrid(320, 240, 55, 18, 25, 3, 3, device=device)]
     dt = capi.DenseTracker(640, 480, 3, device=device)
     for l in range(3):
@@ -477,19 +480,22 @@ def frontend_bench(device, n_frames=12):
     state = {"k": 0}
 
     def one_frame(prev, cur, prev_xy, upload=True):
-        """upload=True: the per-frame host inputs are the raw left image and the disparity maps; pyramids
-        and gradients are made on the device (svs_prep_*) and handed over by pointer."""
+        """upload=True: the per-frame host inputs are the raw left image and the disparity maps; pyramids and gradients
+        are made on the device (svs_prep_*) and handed over by pointer; the FAST corners go to the matcher on the device."""
         if upload:
             state["k"] ^= 1
             pp, pq = pps[state["k"]], pps[state["k"] ^ 1]       # pp: current frame, pq: previous frame
             pp.process(cur["img"])
             lv = [pp.level(l) for l in range(3)]
-        feats = []
+        xy0 = None
         for l in range(2):
             if upload:
                 grids[l].set_image_device(lv[l]["u8"], lv[l]["pitch_u8"], lv[l]["w"], lv[l]["h"])
             xy, off = grids[l].detect_adaptively(6)
-            feats.append((xy, np.concatenate([np.arange(off[c + 1] - off[c]) for c in range(9)]).astype(np.int32)))
+            if l == 0:
+                xy0 = xy
+            if upload:
+                mt.set_features_from_fast(l, grids[l])
         if upload:
             dt.set_disparity(prev["disp"])
             dt.swap_prev_cur()                                   # FrameData::nextFrame
@@ -502,62 +508,77 @@ def frontend_bench(device, n_frames=12):
             mt.set_pyramid_device(0, [x["u8"] for x in lq], [x["pitch_u8"] for x in lq], I7)
             mt.set_pyramid_device(-1, [x["u8"] for x in lv[:2]], [x["pitch_u8"] for x in lv[:2]])
             mt.set_current_disparity(cur["disp"])
-            for l in range(2):
-                mt.set_features(l, *feats[l])
         res = mt.match(T, I7, make_points(prev, prev_xy), 4, 22, 10)
         nm = int(res["matched"].sum())
         if nm >= 20:                                             # stereo_frontend.cpp:1053-1063
             T, _ = pose.calc_fast_motion_only_matched(mt, cams[0][:4], T, True, 2.0, 15)
-        return feats[0][0], T, nm, st
+        return xy0, T, nm, st
 
-    order = [0, 1, 2, 3, 2, 1]                 # ping-pong so that every frame follows its neighbour
-    pps[0].process(frames[0]["img"])            # prime: frame 0 is "previous"
+    pps[0].process(seq[0]["img"])                # prime: frame 0 is "previous"
     for l in range(3):
         lv0 = pps[0].level(l)
         dt.set_images_device(l, lv0["f32"], lv0["f32"], lv0["dx"], lv0["dy"], lv0["stride_f32"])
-    prev_xy = one_frame(frames[0], frames[1], np.zeros((0, 2), np.int32))[0]
-    for i in range(2, 6):                       # warm-up once around
-        prev_xy = one_frame(frames[order[i - 1]], frames[order[i]], prev_xy)[0]
-    prev_xy = one_frame(frames[1], frames[0], prev_xy)[0]
+    prev_xy = one_frame(seq[0], seq[1], np.zeros((0, 2), np.int32))[0]
+    for i in range(1, min(4, n_frames)):         # warm-up on the first frames
+        prev_xy = one_frame(seq[i], seq[i + 1], prev_xy)[0]
+    # timed: the whole sequence once more from its start
+    pps[state["k"]].process(seq[0]["img"])
+    for l in range(3):
+        lv0 = pps[state["k"]].level(l)
+        dt.set_images_device(l, None, lv0["f32"], lv0["dx"], lv0["dy"], lv0["stride_f32"])
+    prev_xy = one_frame(seq[0], seq[1], np.zeros((0, 2), np.int32))[0]
     torch.cuda.synchronize()
-    e2e, matched, frame_ms = None, 0, []
-    for rep in range(3):                        # best of 3 passes (a single host hiccup would halve a 20 ms pass)
-        t0 = time.perf_counter()
-        m_rep = 0
-        for i in range(n_frames):
-            a, b = frames[order[i % 6]], frames[order[(i + 1) % 6]]
-            tf = time.perf_counter()
-            prev_xy, T, m, st = one_frame(a, b, prev_xy)
-            frame_ms.append((time.perf_counter() - tf) * 1e3)
-            m_rep += m
-        t_rep = time.perf_counter() - t0
-        if e2e is None or t_rep < e2e:
-            e2e, matched = t_rep, m_rep
+    frame_ms, matched, passes, dt_ms, dt_bytes = [], 0, np.zeros(3), 0.0, 0.0
     t0 = time.perf_counter()
-    for i in range(n_frames):
+    for i in range(1, n_frames):
+        tf = time.perf_counter()
+        prev_xy, T, m, st = one_frame(seq[i], seq[i + 1], prev_xy)
+        frame_ms.append((time.perf_counter() - tf) * 1e3)
+        matched += m
+        passes += np.asarray(st["passes"][:3])
+        dt_ms += st["ms_total"]
+        dt_bytes += sum(36.0 * st["passes"][l] * (640 >> l) * (480 >> l) for l in range(3))
+    e2e = time.perf_counter() - t0
+    timed = n_frames - 1
+    a, b = seq[n_frames - 1], seq[n_frames]
+    t0 = time.perf_counter()
+    nres = min(timed, 50)
+    for i in range(nres):
         one_frame(a, b, prev_xy, upload=False)
     res_s = time.perf_counter() - t0
-    # CPU oracle on the same frames (1 thread), bounded sample
+    # CPU oracle on frames of the same sequence (1 thread), bounded sample: >= 20 frames
+    ncpu = min(20, n_frames)
+    cpu_frames = []
+    for f in seq[:ncpu + 1]:                    # host pyramids/gradients (OpenCV) feed the CPU baseline only
+        fp = fi.float_pyramid(f["img"])
+        cpu_frames.append(dict(u8=fi.uint8_pyramid(f["img"], 2), f32=fp, grad=[fi.gradients(x) for x in fp], disp=f["disp"]))
     c0 = time.perf_counter()
-    ncpu = 2
     for i in range(ncpu):
-        a, b = frames[i], frames[i + 1]
+        fa, fb = cpu_frames[i], cpu_frames[i + 1]
         for l in range(2):
             g = po.fast_grid(640 >> l, 480 >> l, 222 if l == 0 else 55, 74 if l == 0 else 18, 25, 3, 3)
-            po.fast_detect_adaptively(b["u8"][l], g, 6)
-        lv = [dict(prev=a["f32"][l], cur=b["f32"][l], dx=b["grad"][l][0], dy=b["grad"][l][1], f=cams[l][0], px=cams[l][1],
-                   py=cams[l][2], cloud=po.dt_point_cloud(I7, cams[l], a["disp"], l, 640 >> l, 480 >> l)) for l in range(3)]
+            po.fast_detect_adaptively(fb["u8"][l], g, 6)
+        lv = [dict(prev=fa["f32"][l], cur=fb["f32"][l], dx=fb["grad"][l][0], dy=fb["grad"][l][1], f=cams[l][0], px=cams[l][1],
+                   py=cams[l][2], cloud=po.dt_point_cloud(I7, cams[l], fa["disp"], l, 640 >> l, 480 >> l)) for l in range(3)]
         po.dt_track(lv, I7)
     cpu_s = time.perf_counter() - c0
-    out = {"workload": "C3: 640x480 synthetic stereo stream; preprocessing (pyramids, gradients) + FAST grid (2 levels, "
-                       "6 trials) + dense tracking (3 levels) + point cloud + guided matching (radius 4) + motion-only LM (15 it)",
-           "fps_e2e": n_frames / e2e, "fps_resident": n_frames / res_s, "frames": n_frames,
+    peak, peak_src = load_peaks()
+    dt_gbs = dt_bytes / max(dt_ms * 1e-3, 1e-12) / 1e9
+    out = {"workload": f"C3: 640x480 synthetic stereo stream, {len(seq)} frames (2 cm / 0.2 deg per frame); preprocessing (pyramids, "
+                       "gradients) + FAST grid (2 levels, 6 trials) + dense tracking (3 levels) + point cloud + guided matching "
+                       "(radius 4, corners handed over on the device) + motion-only LM (15 it)",
+           "fps_e2e": timed / e2e, "fps_resident": nres / res_s, "frames": timed,
            "frame_ms_median": float(np.median(frame_ms)), "frame_ms_max": float(np.max(frame_ms)),
-           "timing": "wall clock, best of 3 passes of `frames` frames",
-           "matched_per_frame": matched / n_frames, "dense_tracking_passes": st["passes"],
-           "dense_tracking_ms": st["ms_total"],
+           "timing": "wall clock over the whole sequence, one pass",
+           "matched_per_frame": matched / timed, "dense_tracking_passes_per_frame": (passes / timed).tolist(),
+           "dense_tracking_ms_per_frame": dt_ms / timed,
+           "roofline": {"bound": "hbm", "kernel": "k_dt_track_level (fused chi2 + J^T J + J^T r pass, whole LM loop on the device)",
+                        "achieved": dt_gbs, "peak": peak, "unit": "GB/s", "frac": dt_gbs / peak, "traffic": None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_frame": dt_bytes / timed,
+                        "note": "36 B per pixel and pass (SURVEY.md 8d); latency-bound: one grid-wide rendezvous, a 28-value "
+                                "reduction and a 6x6 solve per pass, independent of the image size"},
            "cpu_baseline_fps": ncpu / cpu_s, "cpu_baseline": "oracle FAST + dense tracking (GPU semantics), 1 thread, "
-                                                               f"{ncpu} frames (matcher excluded: <5 ms)"}
+                                                               f"{ncpu} frames of the sequence (matcher excluded: <5 ms)"}
     for g in grids + pps + [pose]:
         g.close()
     dt.close()
@@ -571,6 +592,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=200, help="frames of the synthetic C3 sequence (0: skip the front-end part)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -341,6 +341,9 @@ int svs_matcher_set_current(svs_matcher *h, const unsigned char *const *pyr, con
                           int disp_pitch_floats);
 /* feature_tree.at(level): the FAST corners (x, y) and their quadtree content (index within the cell) */
 int svs_matcher_set_features(svs_matcher *h, int level, const int *xy, const int *content, int n);
+/* The same from the FAST handle's last svs_fast_detect* result where it lies on the device (content = ordinal of the
+ * corner inside its cell, fast_grid.cpp:75-80): the corners never travel through host memory. */
+int svs_matcher_set_features_from_fast(svs_matcher *h, int level, svs_fast *fast);
 /* GuidedMatcher<StereoCamera>::match (matcher.cpp:312-398).  T_actkey_from_w replaces
  * vertex_map[actkey_id].  Returns the number of matched points or a negative SVS_ERR_*. */
 int svs_match(svs_matcher *h, const double T_cur_from_actkey[7], const double T_actkey_from_w[7],
@@ -444,6 +447,14 @@ int svs_map_set(svs_map *h, int V, const double *T_me_from_world, int Np, const 
                 const int *feat_level);
 /* restoreDataFromG2o's counterpart for the map: overwrite the poses of n vertices */
 int svs_map_update_poses(svs_map *h, int n, const int *vertex, const double *T_me_from_world);
+/* ... and the anchored positions of n points (restoreDataFromG2o writes Point::xyz_anchor, slam_graph.cpp:1054) */
+int svs_map_update_points(svs_map *h, int n, const int *point, const double *xyz_anchor);
+/* read the map back (either output may be NULL): T_me_from_world[V][7], xyz_anchor[Np][3] */
+int svs_map_get(svs_map *h, double *T_me_from_world, double *xyz_anchor);
+/* SlamGraph::restoreDataFromG2o (slam_graph.cpp:1037-1058) device to device: after svs_ba_optimize on the window
+ * svs_ba_set_problem_from_map assembled last, the vertex poses and xyz_anchor = invert_depth(psi) of its points go
+ * back into the map without touching the host */
+int svs_map_absorb(svs_map *h, svs_ba *ba);
 /* = svs_ba_set_problem on the window assembled from the map; *num_edges receives E */
 int svs_ba_set_problem_from_map(svs_ba *ba, svs_map *map, int P, const int *window_vertex, const unsigned char *fixed,
                                 int L, const int *active_point, int C, const int *c_i, const int *c_j,

@@ -20,6 +20,8 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "svs_b200.h"
@@ -53,6 +55,7 @@ class StereoGraph {
   StereoGraph(const StereoGraph&) = delete;
   StereoGraph& operator=(const StereoGraph&) = delete;
   bool valid() const { return ok_; }
+  svs_ba* handle() { return h_; }
   const char* last_error() const { return h_ ? svs_last_error(h_) : "svs_ba_create failed (no CUDA device)"; }
 
   void clear() { pose_id_.clear(); T_.clear(); fixed_.clear(); point_id_.clear(); psi_.clear(); ep_.clear(); ef_.clear();
@@ -88,7 +91,7 @@ class StereoGraph {
     if (!remap(ep_, point_id_, ep) || !remap(ef_, pose_id_, ef) || !remap(ea_, pose_id_, ea) ||
         !remap(ci_, pose_id_, ci) || !remap(cj_, pose_id_, cj))
       return -100 + SVS_ERR_INVALID;
-    svs_ba_stats st;
+    svs_ba_stats st{};
     const int it = svs_optimiseInnerAndOuterWindow(
         h_, (int)pose_id_.size(), T_.data(), fixed_.data(), (int)point_id_.size(), psi_.data(), (int)ep.size(), ep.data(),
         ef.data(), ea.data(), obs_.data(), info_.data(), (int)ci.size(), ci.data(), cj.data(), cT_.data(), cL_.data(), &cam_,
@@ -112,16 +115,18 @@ class StereoGraph {
 
  private:
   static void push7(std::vector<double>& v, const SE3d& T) { v.insert(v.end(), T.q, T.q + 4); v.insert(v.end(), T.t, T.t + 3); }
+  // id -> index through a sorted copy of the id table (ids may be sparse or hashed); a duplicate id is an error
   static bool remap(const std::vector<int>& ids, const std::vector<int>& table, std::vector<int>& out) {
-    // ids are small windows: sort-free lookup through a flat map over the id range would also do;
-    // a linear probe per distinct id keeps this header free of <unordered_map>
-    int lo = 0, hi = -1;
-    for (int id : table) { if (hi < lo) { lo = hi = id; } if (id < lo) lo = id; if (id > hi) hi = id; }
-    std::vector<int> lut(hi >= lo ? (size_t)(hi - lo + 1) : 0, -1);
-    for (size_t k = 0; k < table.size(); ++k) lut[(size_t)(table[k] - lo)] = (int)k;
+    std::vector<std::pair<int, int>> sorted(table.size());
+    for (size_t k = 0; k < table.size(); ++k) sorted[k] = std::make_pair(table[k], (int)k);
+    std::sort(sorted.begin(), sorted.end());
+    for (size_t k = 1; k < sorted.size(); ++k)
+      if (sorted[k].first == sorted[k - 1].first) return false;
     for (size_t k = 0; k < ids.size(); ++k) {
-      if (ids[k] < lo || ids[k] > hi || lut[(size_t)(ids[k] - lo)] < 0) return false;
-      out[k] = lut[(size_t)(ids[k] - lo)];
+      auto it = std::lower_bound(sorted.begin(), sorted.end(), std::make_pair(ids[k], 0),
+                                 [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+      if (it == sorted.end() || it->first != ids[k]) return false;
+      out[k] = it->second;
     }
     return true;
   }
@@ -149,7 +154,17 @@ class FastGrid {
   FastGrid(const FastGrid&) = delete;
   FastGrid& operator=(const FastGrid&) = delete;
   bool valid() const { return ok_; }
+  svs_fast* handle() { return h_; }
   const std::vector<svs_fast_cell>& cell_grid2d() const { return cells_; }
+  // the same on an image that already lies on the device (a FramePreprocessor level)
+  int detectAdaptivelyDevice(const unsigned char* d_img, int pitch, int w, int h, int trials, std::vector<int>* xy,
+                             std::vector<int>* cell_off) {
+    if (!ok_ || svs_fast_set_image_device(h_, d_img, pitch, w, h) != SVS_OK) return -1;
+    xy->resize(2 * (size_t)max_kp_); cell_off->resize(cells_.size() + 1);
+    const int n = svs_fast_detect_adaptively(h_, &grid_, cells_.data(), trials, xy->data(), max_kp_, cell_off->data());
+    if (n >= 0) xy->resize(2 * (size_t)(n < max_kp_ ? n : max_kp_));
+    return n;
+  }
   // detectAdaptively(img, trials, qt)
   int detectAdaptively(const unsigned char* img, int pitch, int w, int h, int trials, std::vector<int>* xy,
                        std::vector<int>* cell_off) {
@@ -246,6 +261,8 @@ class GuidedMatcher {
   GuidedMatcher& operator=(const GuidedMatcher&) = delete;
   bool valid() const { return ok_; }
   svs_matcher* handle() { return h_; }
+  // feature_tree of one pyramid level = the corners FastGrid::detect* left on the device
+  bool setFeatureTree(int level, FastGrid& fast_grid) { return ok_ && svs_matcher_set_features_from_fast(h_, level, fast_grid.handle()) == SVS_OK; }
   // match(keyframe_map, T_cur_from_actkey, cur_frame, feature_tree, cam_vec, actkey_id, vertex_map, ap_map,
   //       SEARCHRADIUS, thr_mean, thr_std, track_data): frames/keyframes/features are set on the handle first
   int match(const double T_cur_from_actkey[7], const double T_actkey_from_w[7], const std::vector<svs_match_point>& ap_map,
@@ -374,10 +391,45 @@ class DeviceMap {
   bool valid() const { return ok_; }
   svs_map* handle() { return h_; }
   const char* last_error() const { return svs_map_last_error(h_); }
+  // vertex_table_ / point_table_ / feature tables as flat arrays (slam_graph.hpp:65-137): poses [V][7], per point its
+  // anchor vertex and xyz_anchor, vis_set + feature_table as CSR over the points (centre (u,v,u_r) and pyramid level)
+  bool set(const std::vector<double>& T_me_from_world, const std::vector<int>& point_anchor, const std::vector<double>& xyz_anchor,
+           const std::vector<int>& vis_ptr, const std::vector<int>& vis_pose, const std::vector<double>& feat_center,
+           const std::vector<int>& feat_level) {
+    V_ = (int)(T_me_from_world.size() / 7); Np_ = (int)point_anchor.size();
+    return ok_ && svs_map_set(h_, V_, T_me_from_world.data(), Np_, point_anchor.data(), xyz_anchor.data(), vis_ptr.data(),
+                              vis_pose.data(), feat_center.data(), feat_level.data()) == SVS_OK;
+  }
+  // copyDataToG2o (slam_graph.cpp:985-1032) into `graph`'s bundle adjuster; returns the number of edges, < 0 on error
+  int copyDataToG2o(svs_ba* ba, const std::vector<int>& window_vertex, const std::vector<int>& active_point, const svs_cam& cam,
+                    const std::vector<int>& c_i = {}, const std::vector<int>& c_j = {}, const std::vector<double>& c_T = {},
+                    const std::vector<double>& c_Lambda = {}) {
+    int E = 0;
+    const int rc = ok_ ? svs_ba_set_problem_from_map(ba, h_, (int)window_vertex.size(), window_vertex.data(), nullptr,
+                                                     (int)active_point.size(), active_point.data(), (int)c_i.size(), c_i.data(),
+                                                     c_j.data(), c_T.data(), c_Lambda.data(), &cam, &E)
+                       : SVS_ERR_NOGPU;
+    return rc == SVS_OK ? E : rc;
+  }
+  // restoreDataFromG2o (slam_graph.cpp:1037-1058), device to device
+  bool restoreDataFromG2o(svs_ba* ba) { return ok_ && svs_map_absorb(h_, ba) == SVS_OK; }
+  bool updatePoses(const std::vector<int>& vertex, const std::vector<double>& T) {
+    return ok_ && svs_map_update_poses(h_, (int)vertex.size(), vertex.data(), T.data()) == SVS_OK;
+  }
+  bool updatePoints(const std::vector<int>& point, const std::vector<double>& xyz_anchor) {
+    return ok_ && svs_map_update_points(h_, (int)point.size(), point.data(), xyz_anchor.data()) == SVS_OK;
+  }
+  bool get(std::vector<double>* T_me_from_world, std::vector<double>* xyz_anchor) {
+    T_me_from_world->resize(7 * (size_t)V_); xyz_anchor->resize(3 * (size_t)(Np_ > 0 ? Np_ : 1));
+    const bool r = ok_ && svs_map_get(h_, T_me_from_world->data(), xyz_anchor->data()) == SVS_OK;
+    xyz_anchor->resize(3 * (size_t)Np_);
+    return r;
+  }
 
  private:
   svs_map* h_ = nullptr;
   bool ok_ = false;
+  int V_ = 0, Np_ = 0;
 };
 
 }  // namespace svs

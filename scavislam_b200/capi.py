@@ -116,7 +116,7 @@ EXPORTS = [
     "svs_dt_set_disparity", "svs_dt_compute_point_cloud", "svs_dt_set_point_cloud", "svs_dt_get_point_cloud",
     "svs_dt_chi2", "svs_dt_jacobian_reduction", "svs_dt_track",
     "svs_matcher_create", "svs_matcher_destroy", "svs_matcher_last_error", "svs_matcher_set_keyframe",
-    "svs_matcher_set_current", "svs_matcher_set_features", "svs_match",
+    "svs_matcher_set_current", "svs_matcher_set_features", "svs_matcher_set_features_from_fast", "svs_match",
     "svs_prep_create", "svs_prep_destroy", "svs_prep_last_error", "svs_prep_process", "svs_prep_level",
     "svs_prep_get_u8", "svs_prep_get_f32", "svs_dt_set_images_device", "svs_dt_swap_prev_cur",
     "svs_matcher_set_pyramid_device",
@@ -127,6 +127,7 @@ EXPORTS = [
     "svs_denseTrackingCpu",
     "svs_constraints_create", "svs_constraints_destroy", "svs_constraints_last_error", "svs_computeConstraint_batch",
     "svs_map_create", "svs_map_destroy", "svs_map_last_error", "svs_map_set", "svs_map_update_poses",
+    "svs_map_update_points", "svs_map_get", "svs_map_absorb",
     "svs_ba_set_problem_from_map", "svs_map_last_edges",
 ]
 
@@ -225,6 +226,9 @@ def lib():
     L.svs_map_last_error.restype = C.c_char_p
     L.svs_map_set.argtypes = [vp, C.c_int, c_dp, C.c_int, c_ip, c_dp, c_ip, c_ip, c_dp, c_ip]
     L.svs_map_update_poses.argtypes = [vp, C.c_int, c_ip, c_dp]
+    L.svs_map_update_points.argtypes = [vp, C.c_int, c_ip, c_dp]
+    L.svs_map_get.argtypes = [vp, c_dp, c_dp]
+    L.svs_map_absorb.argtypes = [vp, vp]
     L.svs_ba_set_problem_from_map.argtypes = [vp, vp, C.c_int, c_ip, c_up, C.c_int, c_ip, C.c_int, c_ip, c_ip, c_dp, c_dp,
                                               C.POINTER(SvsCam), c_ip]
     L.svs_map_last_edges.argtypes = [vp, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp]
@@ -265,6 +269,7 @@ def lib():
     L.svs_matcher_set_keyframe.argtypes = [vp, C.c_int, c_dp, ucpp, c_ip]
     L.svs_matcher_set_current.argtypes = [vp, ucpp, c_ip, c_fp, C.c_int]
     L.svs_matcher_set_features.argtypes = [vp, C.c_int, c_ip, c_ip, C.c_int]
+    L.svs_matcher_set_features_from_fast.argtypes = [vp, C.c_int, vp]
     L.svs_match.argtypes = [vp, c_dp, c_dp, C.POINTER(SvsMatchPoint), C.c_int, C.c_int, C.c_int, C.c_int,
                             C.POINTER(SvsMatchResult)]
     _LIB = L
@@ -669,6 +674,10 @@ class GuidedMatcher:
         content = np.ascontiguousarray(content, np.int32)
         self._ck(lib().svs_matcher_set_features(self._h, level, _ip(xy), _ip(content), len(xy)))
 
+    def set_features_from_fast(self, level, fast_grid):
+        """FAST corners of `fast_grid`'s last detect call, taken where they lie on the device."""
+        self._ck(lib().svs_matcher_set_features_from_fast(self._h, level, fast_grid._h))
+
     def match(self, T_cur_from_actkey, T_actkey_from_w, points, search_radius, thr_mean, thr_std):
         """points: structured array with MATCH_POINT_DTYPE.  Returns a MATCH_RESULT_DTYPE array."""
         pts = np.ascontiguousarray(points, MATCH_POINT_DTYPE)
@@ -934,11 +943,27 @@ class DeviceMap:
         lvl = np.ascontiguousarray(feat_level, np.int32)
         self._ck(lib().svs_map_set(self._h, len(poses), _dp(poses), len(pa), _ip(pa), _dp(xyz), _ip(vp_), _ip(vs), _dp(cen),
                                    _ip(lvl)))
+        self.V, self.Np = len(poses), len(pa)
 
     def update_poses(self, vertex, poses):
         v = np.ascontiguousarray(vertex, np.int32)
         T = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
         self._ck(lib().svs_map_update_poses(self._h, len(v), _ip(v), _dp(T)))
+
+    def update_points(self, point, xyz_anchor):
+        v = np.ascontiguousarray(point, np.int32)
+        x = np.ascontiguousarray(xyz_anchor, np.float64).reshape(-1, 3)
+        self._ck(lib().svs_map_update_points(self._h, len(v), _ip(v), _dp(x)))
+
+    def get(self):
+        """(poses [V,7], xyz_anchor [Np,3]) as they lie on the device."""
+        T, x = np.zeros((self.V, 7)), np.zeros((max(self.Np, 1), 3))
+        self._ck(lib().svs_map_get(self._h, _dp(T), _dp(x)))
+        return T, x[:self.Np]
+
+    def absorb(self, ba):
+        """SlamGraph::restoreDataFromG2o, device to device: the optimised window of `ba` goes back into the map."""
+        self._ck(lib().svs_map_absorb(self._h, ba._h))
 
     def set_problem(self, ba, window_vertex, active_point, cam, fixed=None, c_i=(), c_j=(), c_T=None, c_Lambda=None):
         """Assembles the window on the device and loads it into `ba` (a BundleAdjuster).  Returns E."""

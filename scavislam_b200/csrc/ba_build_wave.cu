@@ -14,6 +14,8 @@
 //
 // Reference semantics: G2oEdgeProjectPSI2UVU::linearizeOplus (anchored_points.cpp:168-189), g2o
 // BaseMultiEdge::constructQuadraticForm, BlockSolver<6,3>::buildSystem / solve (Schur part).
+#include <cstdlib>
+
 #include "ba_dev.cuh"
 #include "ba_kernels.cuh"
 
@@ -30,7 +32,7 @@ constexpr int kWvInts = 8 + 40;   // slot poses, pair table (36) padded
 size_t build_wave_smem_bytes() { return (size_t)kWvWarps * (kWvDoubles * 8 + kWvInts * 4); }
 
 __global__ void __launch_bounds__(kWvWarps * 32)
-k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
+k_build_wave(BaDev d, int robust, double delta, int n_task_blocks, int prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LmCtl* __restrict__ ctl = d.ctl;
@@ -106,6 +108,9 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
   if (nw_max > kWvSlots / K) nw_max = kWvSlots / K;
   if (nw_max > kWvLm) nw_max = kWvLm;
 
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pclk = prof ? clock64() : 0;
+#define PBW(i) do { if (prof) { __syncwarp(); const long long c_ = clock64(); pacc[i] += c_ - pclk; pclk = c_; } } while (0)
+  PBW(0);
   for (int w0 = 0; w0 < nlm; w0 += nw_max) {
     const int nw = min(nw_max, nlm - w0);
     // ---- phase 1: one lane per edge of the wave
@@ -132,6 +137,7 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
     }
     sChi[lane] = chi;
     __syncwarp();
+    PBW(1);
     if (lane < nw) {
       double s = 0.;
       for (int i = 0; i < k; ++i) s += sChi[lane * k + i];
@@ -175,6 +181,7 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
       sLm[j * kWvLmD + 18 + c * 6 + r] = s;
     }
     __syncwarp();
+    PBW(2);
     // ---- phase 3: (Hll + lambda I)^-1 per landmark; Hll / b_l to HBM for the back-substitution
     if (lane < nw) {
       double Di[9];
@@ -204,6 +211,7 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
         for (int sg = lane; sg < nslots_w; sg += 32) d.W[(size_t)c * d.nslots + s0 + sg] = sB[18 * sg + c];
     }
     __syncwarp();
+    PBW(3);
     // ---- phase 5: accumulate the task's contribution to the reduced system in registers.
     //      The Schur product common to every unit runs branch-free (9 16-byte loads of B_n, FMAs straight
     //      into the accumulators); the direct J^T W J terms of the few special pairs follow in their own loops.
@@ -259,6 +267,7 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
         }
       }
     }
+    PBW(4);
     // ---- phase 6: gradients bp = -J^T W e, bc = Y b_l
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -284,6 +293,7 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
       }
     }
     __syncwarp();
+    PBW(5);
   }
   // ---- flush: one RED.F64 per accumulated element for the whole task
 #pragma unroll
@@ -308,6 +318,10 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks) {
       atomicAdd(d.bc + 6 * p + r, accc[q]);
     }
   }
+  PBW(6);
+  if (prof && lane == 0)
+    for (int i = 0; i < 7; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(d.dbg) + 36 + i, (unsigned long long)pacc[i]);
+#undef PBW
 }
 
 void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st) {
@@ -317,7 +331,8 @@ void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st
     cudaFuncSetAttribute(k_build_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_wave_smem_bytes());
   const int task_blocks = (d.ntasks + kWvWarps - 1) / kWvWarps;
   const int c_blocks = (d.C + kWvWarps * 32 - 1) / (kWvWarps * 32);
-  k_build_wave<<<task_blocks + c_blocks, kWvWarps * 32, build_wave_smem_bytes(), st>>>(d, robust, delta, task_blocks);
+  static const int prof = getenv("SVS_BUILD_TIMING") ? 1 : 0;
+  k_build_wave<<<task_blocks + c_blocks, kWvWarps * 32, build_wave_smem_bytes(), st>>>(d, robust, delta, task_blocks, prof);
 }
 
 }  // namespace svs

@@ -13,6 +13,7 @@
 #include <numeric>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/svs_b200.h"
@@ -24,7 +25,8 @@ using namespace svs;
 // Symbolic analysis of the reduced camera system (see analyse() below)
 struct Symbolic {
   std::vector<int> perm, pos, col_ptr, row_idx, upd_ptr, upd_dst, upd_ab, urg_dst, tbl, branch_ptr;
-  int max_col_branch = 0, max_col_sep = 0;
+  std::vector<int> rptr, rowpos, rcol;   // row-major index of the off-diagonal factor blocks (backward pass)
+  int max_col_branch = 0, max_col_sep = 0, max_row = 0;
   int nblk = 0;
 };
 
@@ -50,13 +52,15 @@ struct svs_ba {
   int Kmax_gen = 1;
   int nnzb_S = 0;
   int C_edges = 0;
-  int max_col_blocks = 0, max_col_branch = 0, nbranch = 1, nsep_blk = 0;
+  int max_col_blocks = 0, max_col_branch = 0, nbranch = 1, nsep_blk = 0, max_row_blocks = 0;
   std::vector<int> extra_pairs;   // svs_ba_set_structure: pose pairs added to the block pattern
   // one window sharded by landmarks across ranks: NCCL communicator of this handle
   NcclComm comm = nullptr; int comm_rank = 0, comm_size = 1;
   size_t sys_count = 0;            // doubles of the packed S | bp | bc buffer (one all-reduce per trial)
   int L_full = 0;                  // svs_ba_set_problem_sharded: landmarks of the whole window, 0 = not sharded
   double* d_psi_all = nullptr; size_t psi_all_cap = 0;
+  double* d_out = nullptr; double* h_out = nullptr; size_t out_cap = 0;   // accepted state in the caller's order (one-call API)
+  bool export_next = false;
   // host scratch of set_problem, kept across calls (fresh multi-MB vectors page-fault every time)
   std::vector<int> w_eptr, w_eord, w_fill, w_anchor, w_K, w_order, w_lm_eptr, w_lm_sptr, w_lm_anchor, w_ie_pose, w_bucket;
   std::vector<unsigned char> w_self, w_lm_self, w_adj;
@@ -247,6 +251,24 @@ void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, c
       }
   }
   sy.upd_ptr[P] = (int)sy.upd_dst.size();
+  // row-major index of the off-diagonal blocks, columns descending inside a row: the backward pass walks the
+  // rows from the last to the first and scatters x_i into the columns of row i
+  {
+    sy.rptr.assign(P + 1, 0);
+    for (int j = 0; j < P; ++j)
+      for (int b = sy.col_ptr[j] + 1; b < sy.col_ptr[j + 1]; ++b) sy.rptr[sy.row_idx[b] + 1]++;
+    sy.max_row = 0;
+    for (int i = 0; i < P; ++i) { sy.max_row = std::max(sy.max_row, sy.rptr[i + 1]); sy.rptr[i + 1] += sy.rptr[i]; }
+    std::vector<int> fill(sy.rptr.begin(), sy.rptr.end() - 1);
+    sy.rowpos.assign(sy.nblk, -1);
+    sy.rcol.assign(sy.nblk - P > 0 ? sy.nblk - P : 0, 0);
+    for (int j = P - 1; j >= 0; --j)
+      for (int b = sy.col_ptr[j] + 1; b < sy.col_ptr[j + 1]; ++b) {
+        const int at = fill[sy.row_idx[b]]++;
+        sy.rowpos[b] = at;
+        sy.rcol[at] = j;
+      }
+  }
   // urg_dst[col_ptr[j] + 1 + a] = destination of pair (a, 0) of column j
   sy.urg_dst.assign(sy.nblk, 0);
   for (int j = 0; j < P; ++j) {
@@ -313,6 +335,10 @@ int svs_ba_create(const svs_ba_opts* opts, svs_ba** out) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SVS_ERR_NOGPU;
   svs_ba* h = new svs_ba();
   h->flags = opts ? opts->flags : 0;
+  {   // threads of the per-landmark host loops of set_problem: a few, never more than half the machine
+    const int hw = (int)std::thread::hardware_concurrency();
+    h->host_threads = std::max(1, std::min(8, hw / 2));
+  }
   if (const char* ht = getenv("SVS_HOST_THREADS")) h->host_threads = std::max(1, atoi(ht));
   int dev = opts ? opts->device : -1;
   if (dev < 0) cudaGetDevice(&dev);
@@ -335,6 +361,8 @@ void svs_ba_destroy(svs_ba* h) {
   free_arena(h);
   if (h->comm) { if (const NcclApi* nc = nccl_api()) nc->CommDestroy(h->comm); }
   if (h->d_psi_all) cudaFree(h->d_psi_all);
+  if (h->d_out) cudaFree(h->d_out);
+  if (h->h_out) cudaFreeHost(h->h_out);
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->tev) cudaEventDestroy(e);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -521,7 +549,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   auto& lm_eptr = h->w_lm_eptr; auto& lm_sptr = h->w_lm_sptr; auto& lm_anchor = h->w_lm_anchor; auto& ie_pose = h->w_ie_pose;
   auto& lm_self = h->w_lm_self; auto& edge_src = h->w_edge_src; auto& ipsi = h->w_psi;
   lm_eptr.assign(L + 1, 0); lm_sptr.assign(L + 1, 0); lm_anchor.assign(L, 0); ie_pose.resize(E);
-  lm_self.assign(L, 0); edge_src.assign(E, 0); ipsi.resize(3 * (size_t)L);
+  lm_self.assign(L, 0); edge_src.resize(E); ipsi.resize(3 * (size_t)L);
   for (int li = 0; li < L; ++li) {
     const int l = order[li];
     lm_eptr[li + 1] = lm_eptr[li] + (eptr[l + 1] - eptr[l]);
@@ -660,12 +688,12 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   auto lay = [&]() {
     h->arena_off = 0;
 #define UP(field, vec) dev_upload(h, &d.field, vec)
-    UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self);
+    UP(fixed, fx); UP(lm_eptr, lm_eptr); UP(lm_sptr, lm_sptr); UP(lm_anchor, lm_anchor); UP(lm_self, lm_self); UP(lm_user, h->lm_to_user);
     UP(e_pose, ie_pose); UP(edge_src, edge_src);
     UP(task_lm, task_lm); UP(task_cnt, task_cnt); UP(gen_lm, gen_lm); UP(long_lm, long_lm);
     UP(tbl, sy.tbl); UP(perm, sy.perm); UP(pos, sy.pos); UP(col_ptr, sy.col_ptr); UP(row_idx, sy.row_idx);
     UP(upd_ptr, sy.upd_ptr); UP(upd_dst, sy.upd_dst); UP(upd_ab, sy.upd_ab); UP(urg_dst, sy.urg_dst);
-    UP(branch_ptr, sy.branch_ptr);
+    UP(branch_ptr, sy.branch_ptr); UP(rptr, sy.rptr); UP(rowpos, sy.rowpos); UP(rcol, sy.rcol);
     dev_upload(h, &d.c_i, c_i, (size_t)C); dev_upload(h, &d.c_j, c_j, (size_t)C);
     h->off_num = h->off_cT = h->arena_off;   // the numbers (everything a same-structure call re-sends) lie last
     dev_upload(h, &d.c_T, c_T, 7 * (size_t)C);
@@ -688,10 +716,10 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       if (!h->measuring) { d.S = sys; d.bp = sys + 36 * (size_t)sy.nblk; d.bc = d.bp + 6 * (size_t)P; d.totals = d.bc + 6 * (size_t)P; }
       h->sys_count = 36 * (size_t)sy.nblk + 12 * (size_t)P;
     }
-    AL(x, 6 * (size_t)P);
+    AL(x, 6 * (size_t)P); AL(Nrow, 36 * (size_t)std::max(sy.nblk - P, 1));
     AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
     AL(ctl, 1);
-    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 48);
+    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 64);
 #undef AL
   };
   h->measuring = true;
@@ -707,7 +735,8 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   d.e_obs = d.e_obs_w; d.e_w = d.e_w_w;
   launch_regroup(d, d_obs_info ? d_obs_info : h->d_raw, h->stream);   // [3][E] internal order <- [E][3] user order
   CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
-  h->max_col_blocks = sy.max_col_sep; h->max_col_branch = sy.max_col_branch;
+  CK(cudaMemsetAsync(d.dbg, 0, 64 * sizeof(long long), h->stream));
+  h->max_col_blocks = sy.max_col_sep; h->max_col_branch = sy.max_col_branch; h->max_row_blocks = sy.max_row;
   d.nbranch = h->nbranch;
   CK(cudaMemsetAsync(d.chi_c, 0, std::max(C, 1) * sizeof(double), h->stream));
   CK(cudaMemsetAsync(d.chi_c_new, 0, std::max(C, 1) * sizeof(double), h->stream));
@@ -819,7 +848,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
       // every rank holds the partial reduced system of its landmarks: ONE all-reduce of S | bp | bc
       if (nc) CKN(nc->AllReduce(d.S, d.S, h->sys_count, kNcclFloat64, kNcclSum, h->comm, h->stream));
       CKO(cudaEventRecord(h->tev[kEv * k + 2], h->stream));
-      launch_solve(d, h->max_col_branch, h->max_col_blocks, h->nsep_blk, h->stream);
+      launch_solve(d, h->max_col_branch, std::max(h->max_col_blocks, h->max_row_blocks - 2), h->nsep_blk, h->stream);
       CKO(cudaEventRecord(h->tev[kEv * k + 3], h->stream));
       launch_update(d, robust, huber_delta, nc ? 1 : 0, h->stream);
       CKO(cudaEventRecord(h->tev[kEv * k + 4], h->stream));
@@ -830,6 +859,11 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
       CKO(cudaEventRecord(h->tev[kEv * k + 5], h->stream));
     }
     CKO(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
+    if (h->export_next) {   // one-call API: the accepted state rides back with the control block, in the caller's order
+      const size_t n = 7 * (size_t)d.P + 3 * (size_t)d.L;
+      launch_export(d, h->d_out, h->stream);
+      CKO(cudaMemcpyAsync(h->h_out, h->d_out, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
     CKO(cudaStreamSynchronize(h->stream));
     CKO(cudaGetLastError());
     const int done_trials = h->h_ctl->trials_total - trials_seen;
@@ -847,7 +881,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     if (it >= num_iters || (h->h_ctl->stop && !h->h_ctl->again)) break;
   }
   CKO(cudaEventRecord(h->ev[6], h->stream));
-  CKO(cudaStreamSynchronize(h->stream));
+  CKO(cudaEventSynchronize(h->ev[6]));
   h->cur_known = h->h_ctl->cur;   // read back after the last trial of this call
   if (st) {
     const LmCtl& c = *h->h_ctl;
@@ -867,8 +901,15 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     st->ms_build = ms[0]; st->ms_solve = ms[1]; st->ms_update = ms[2]; st->ms_control = ms[3];
     st->launches = launches;
   }
-  if (getenv("SVS_SOLVE_TIMING")) {
+  if (getenv("SVS_BUILD_TIMING")) {
     long long dbg[48];
+    cudaMemcpy(dbg, d.dbg, sizeof dbg, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "k_build_wave warp-cycles summed over warps and launches: setup %lld linearise %lld landmark-sums %lld inverse+Y+spill %lld "
+            "schur+direct %lld gradients %lld flush %lld\n", dbg[36], dbg[37], dbg[38], dbg[39], dbg[40], dbg[41], dbg[42]);
+    cudaMemset(d.dbg + 36, 0, 8 * sizeof(long long));
+  }
+  if (getenv("SVS_SOLVE_TIMING")) {
+    long long dbg[64];
     cudaMemcpy(dbg, d.dbg, sizeof dbg, cudaMemcpyDeviceToHost);
     fprintf(stderr, "k_solve cycles since setup (branch factored, cluster sync, separators factored, separators solved + sync, "
             "branch solved, end):\n");
@@ -876,8 +917,8 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
       fprintf(stderr, "  CTA %d:", g);
       for (int i = 0; i < 6; ++i) fprintf(stderr, " %lld", dbg[g * 6 + i]);
       const long long* q = dbg + 12 + 12 * g;
-      fprintf(stderr, "\n     chain: hand-over %lld chol %lld wait-updates %lld load+publish %lld | helper 0: wait-factor %lld rows %lld "
-              "barrier %lld updates %lld | last helper: %lld %lld %lld %lld\n", q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8],
+      fprintf(stderr, "\n     chain: hand-over %lld chol %lld wait-urgent+load %lld publish %lld | unit thread 0: wait-factor %lld wait-rows %lld "
+              "units %lld | row thread 0: wait-factor %lld rows %lld wait-rows %lld N+rhs %lld\n", q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[8],
               q[9], q[10], q[11]);
     }
   }
@@ -928,9 +969,28 @@ int svs_optimiseInnerAndOuterWindow(svs_ba* h, int P, double* T_qt, const unsign
   int rc = svs_ba_set_problem(h, P, T_qt, fixed, L, psi, E, e_point, e_pose, e_anchor, e_obs, e_info, C, c_i, c_j,
                               c_T, c_Lambda, cam);
   if (rc) return -100 + rc;
+  // the optimised state comes back in ONE copy behind the last trial (no separate read-out round trips)
+  const size_t n = 7 * (size_t)P + 3 * (size_t)L;
+  if (n > h->out_cap) {
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    h->d_out = h->h_out = nullptr; h->out_cap = 0;
+    if (cudaMalloc((void**)&h->d_out, (n + n / 4) * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_out, (n + n / 4) * sizeof(double)) != cudaSuccess)
+      return -100 + fail(h, SVS_ERR_CUDA, "out of memory for the read-out buffer");
+    h->out_cap = n + n / 4;
+  }
+  h->export_next = n > 0 && h->L_full == 0;
   // lambda0 = 50, 5 trials: slam_graph.cpp:338, :1073
   const int it = svs_ba_optimize(h, num_iters, robust, huber_delta, 50., 5, stats);
+  const bool exported = h->export_next && it >= 0;
+  h->export_next = false;
   if (it <= -100) return it;
+  if (exported) {
+    memcpy(T_qt, h->h_out, 7 * (size_t)P * sizeof(double));
+    memcpy(psi, h->h_out + 7 * (size_t)P, 3 * (size_t)L * sizeof(double));
+    return it;
+  }
   if ((rc = svs_ba_get_poses(h, T_qt))) return -100 + rc;
   if ((rc = svs_ba_get_points(h, psi))) return -100 + rc;
   return it;
@@ -1019,7 +1079,7 @@ int svs_ba_solve_reduced(svs_ba* h, int robust, double huber_delta, double lambd
   if ((rc = set_lambda(h, lambda))) return rc;
   if ((rc = clear_system(h))) return rc;
   launch_build(d, h->Kmax_gen, robust, huber_delta, h->stream);
-  launch_solve(d, h->max_col_branch, h->max_col_blocks, h->nsep_blk, h->stream);
+  launch_solve(d, h->max_col_branch, std::max(h->max_col_blocks, h->max_row_blocks - 2), h->nsep_blk, h->stream);
   if (d.P) CK(cudaMemcpyAsync(x, d.x, 6 * (size_t)d.P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_ctl, d.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1130,6 +1190,8 @@ int svs_ba_get_points_all(svs_ba* h, double* psi) {
   if (!nc) return fail(h, SVS_ERR_STATE, "NCCL library not loadable");
   if (n > h->psi_all_cap) {
     if (h->d_psi_all) cudaFree(h->d_psi_all);
+  if (h->d_out) cudaFree(h->d_out);
+  if (h->h_out) cudaFreeHost(h->h_out);
     h->d_psi_all = nullptr; h->psi_all_cap = 0;
     CK(cudaMalloc((void**)&h->d_psi_all, n * sizeof(double)));
     h->psi_all_cap = n;
@@ -1189,7 +1251,7 @@ int svs_ba_system_buffers(svs_ba* h, double** S, long long* nS, double** bp, dou
 int svs_ba_trial_solve(svs_ba* h, int robust, double huber_delta) {
   if (!h || !h->has_problem) return h ? fail(h, SVS_ERR_STATE, "no problem set") : SVS_ERR_INVALID;
   cudaSetDevice(h->device);
-  launch_solve(h->d, h->max_col_branch, h->max_col_blocks, h->nsep_blk, h->stream);
+  launch_solve(h->d, h->max_col_branch, std::max(h->max_col_blocks, h->max_row_blocks - 2), h->nsep_blk, h->stream);
   launch_update(h->d, robust, huber_delta, 1, h->stream);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
@@ -1237,5 +1299,11 @@ int ba_set_problem_device_obs(svs_ba* h, int P, const double* T_qt, const unsign
   return rc;
 }
 int ba_device(const svs_ba* h) { return h->device; }
+int ba_state_on_device(svs_ba* h, const double* const** pose, const double* const** psi, const int** lm_user, const int** cur,
+                       cudaStream_t* stream, int* P, int* L) {
+  if (!h || !h->has_problem) return SVS_ERR_STATE;
+  *pose = h->d.pose; *psi = h->d.psi; *lm_user = h->d.lm_user; *cur = &h->d.ctl->cur; *stream = h->stream; *P = h->d.P; *L = h->d.L;
+  return SVS_OK;
+}
 }  // namespace svs
 

@@ -17,4 +17,5 @@ int update_grid_blocks(int L, int C);
 void launch_update(const BaDev& d, int robust, double delta, int defer_decision, cudaStream_t st);
 void launch_decide_deferred(const BaDev& d, cudaStream_t st);
 void launch_chi2(const BaDev& d, int robust, double delta, cudaStream_t st);
+void launch_export(const BaDev& d, double* out, cudaStream_t st);
 }  // namespace svs

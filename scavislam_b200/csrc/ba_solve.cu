@@ -39,12 +39,28 @@ namespace cg = cooperative_groups;
 
 namespace svs {
 
-constexpr int kSolveThreads = 512;
-constexpr int kHelperWarps = 12;                 // warps 1-3, 5-7, 9-11, 13-15: never on the chain warp's scheduler
-constexpr int kHelpers = kHelperWarps * 32;
-constexpr int kBarPub = 1;    // chain arrives, helpers sync: column j's diagonal factor is published
-constexpr int kBarDone = 2;   // helpers arrive, chain syncs: column j's updates are applied
-constexpr int kBarH = 3;      // helpers only
+constexpr int kSolveThreads = 256;               // 8 warps; warp w issues from scheduler w % 4
+// Roles (factor_range).  Nothing but the chain warp ever runs on scheduler 0 (warp 4 idles through the
+// factorisation); what bounds the helpers is the number of instructions their schedulers must issue per column
+// (ncu: with sixteen resident warps that all walked the column loop, 3 300 warp-instructions per column on three
+// schedulers), so there are exactly as many helper warps as the work of a SLAM-shaped column fills.
+constexpr int kChainWarp = 0;
+constexpr int kUnitWarps = 3;                    // warps 1, 2, 3 (one per scheduler): quarter-block units of the trailing update
+constexpr int kRowWarps = 2;                     // warps 5, 6: rows of the column, N rows, right-hand side; warp 6 (whose lanes
+                                                 // are idle while warp 5 scales a window column's 31 rows) also takes the units
+                                                 // the unit warps have no lanes left for (a window column has 100, they have 96)
+constexpr int kUrgentWarp = 7;                   // the two pair updates the chain reads next
+__device__ __forceinline__ int unit_warp_index(int w) { return (w >= 1 && w <= 3) ? w - 1 : -1; }
+__device__ __forceinline__ int row_warp_index(int w) { return w == 5 ? 0 : (w == 6 ? 1 : -1); }
+constexpr int kUnitThreads = kUnitWarps * 32, kRowThreads = kRowWarps * 32;
+constexpr int kPubAll = 32 * (1 + kUnitWarps + kRowWarps + 1);   // chain + unit + row + urgent warps
+constexpr int kRowsAll = 32 * (kUnitWarps + kRowWarps + 1);      // unit warps wait, row warps produce and wait, urgent produces
+constexpr int kRefillAll = 32 * (kUnitWarps + kRowWarps);       // the urgent warp only touches the next two columns: resident
+constexpr int kUnitStride = kUnitThreads + 32;                 // the second row warp takes the units beyond the unit warps' lanes
+constexpr int kBarPub = 1;    // chain arrives, helpers + urgent warp sync: column j's diagonal factor is published
+constexpr int kBarUrg = 2;    // urgent warp arrives, chain syncs: the chain's next inputs are up to date
+constexpr int kBarH = 3;      // all rows of the column are scaled (row + urgent warps produce, unit + row warps wait)
+constexpr int kBarH2 = 5;     // unit + row warps (ring refill)
 constexpr int kBarBack = 4;   // backward pass, all threads of the CTA
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -122,20 +138,20 @@ __device__ __forceinline__ void load_row6(const double* __restrict__ p, double v
 
 // One contiguous range of columns factored by one CTA.
 struct Team {
-  double* ring;               // block id -> ring + ((id - org) & mask) * 36
+  int ring_off;               // (doubles into the dynamic shared memory) block id -> ring + ((id - org) & mask) * 36
   int org; unsigned mask;
   int cap;                    // ring capacity in blocks (refills keep [col_ptr[j], col_ptr[j] + cap) resident)
   int prefilled;              // 1: the whole range already lies in `ring` (separator phase)
   int j0, j1;                 // column range [j0, j1)
   int sep_blk0;               // updates of blocks >= sep_blk0 go to `area` (nblk when there is none)
-  double* area;               // separator accumulation area of this CTA: block b at area + (b - sep_blk0) * 36
+  int area_off;               // separator accumulation area of this CTA: block b at area + (b - sep_blk0) * 36
   int slot;                   // index of the team's fail flags / diagonal-factor buffers
   int refill_period;
   long long* prof;            // nullptr or 16 cycle counters (developer knob SVS_SOLVE_TIMING)
 };
 
 struct SolveShared {
-  double* yv;
+  int yv_off;                 // right-hand side / solution, 6 doubles per column (offset into the dynamic shared memory)
   int* col_ptr; int* upd_ptr; int* row_idx;
   unsigned char* sfix;
   int (*fail)[2];
@@ -143,15 +159,95 @@ struct SolveShared {
   double* cdiag;
 };
 
-__device__ __forceinline__ double* ring_blk(const Team& T, int id) {
-  return T.ring + (size_t)((unsigned)(id - T.org) & T.mask) * 36;
+// Every shared-memory operand of the kernel is addressed relative to the one dynamic shared array, so that the
+// compiler sees the address space (a select between pointers it cannot trace becomes a GENERIC load: an order of
+// magnitude slower than LDS on this path).
+extern __shared__ __align__(16) double sm_solve[];
+__device__ __forceinline__ int ring_idx(const Team& T, int id) { return T.ring_off + (int)((unsigned)(id - T.org) & T.mask) * 36; }
+#define ring_blk(T, id) (sm_solve + ring_idx(T, id))
+
+// One quarter-block unit of the trailing update: rows 3h..3h+2, columns 3g..3g+2 of S_ab -= L_a L_b^T
+// (18 16-byte loads, 54 FMAs).  u = 4 * pair + 2 h + g, ab = (a << 16) | b, dst = destination block.
+__device__ __forceinline__ void quarter_unit(const BaDev& d, const Team& T, int base, int hi, int u, int ab, int dst) {
+  const int h = (u >> 1) & 1, g = u & 1;
+  const double2* La = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + (ab >> 16)) + h * 18);
+  const double2* Lb = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + (ab & 0xffff)) + g * 18);
+  double a[18], b[18], o[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { const double2 v = La[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { const double2 v = Lb[q]; b[2 * q] = v.x; b[2 * q + 1] = v.y; }
+  const bool far = dst >= hi && dst < T.sep_blk0;   // not resident: read-modify-write in HBM
+  double* Dg = d.S + (size_t)dst * 36 + h * 18 + g * 3;
+  double* D = sm_solve + (dst < hi ? ring_idx(T, dst) : T.area_off + (dst - T.sep_blk0) * 36) + h * 18 + g * 3;
+  if (far) {
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) o[rr * 3 + cc] = Dg[rr * 6 + cc];
+  } else {
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) o[rr * 3 + cc] = D[rr * 6 + cc];
+  }
+#pragma unroll
+  for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) o[rr * 3 + cc] = fma(-a[rr * 6 + k], b[cc * 6 + k], o[rr * 3 + cc]);
+  if (far) {
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) Dg[rr * 6 + cc] = o[rr * 3 + cc];
+  } else {
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) D[rr * 6 + cc] = o[rr * 3 + cc];
+  }
+}
+
+// Every refill_period columns the helpers (unit, row and urgent warps; `rid` in [0, kRefillAll)) reload the ring slots
+// the finished columns freed.  Copies are never in flight while updates run, so a destination is either resident
+// (< hi) or in HBM.
+__device__ __forceinline__ void ring_refill(const BaDev& d, const Team& T, const int* col_ptr, int blk_end, int j, int rid,
+                                            int& until_refill, int& hi) {
+  if (--until_refill != 0) return;
+  until_refill = T.refill_period;
+  if (!(hi < blk_end && j + 1 < T.j1)) return;
+  __threadfence();   // read-modify-writes of far blocks in HBM before the copies read them
+  bar_sync(kBarH2, kRefillAll);
+  const int hi_new = min(blk_end, col_ptr[j + 1] + T.cap);
+  for (int cc = rid; cc < (hi_new - hi) * 18; cc += kRefillAll) {
+    const int id = hi + cc / 18, w = cc % 18;
+    cp_async16(ring_blk(T, id) + 2 * w, d.S + (size_t)id * 36 + 2 * w);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  bar_sync(kBarH2, kRefillAll);
+  hi = hi_new;
 }
 
 // Right-looking block Cholesky of columns [T.j0, T.j1); the forward solve rides along as an extra row.
+//
+// Three roles, three named barriers:
+//   chain warp (warp 0)    factors D_c and publishes it (kBarPub, arrive); before it loads the inputs of column
+//                          c+1 it waits for the URGENT updates of column c-1 (kBarUrg, sync);
+//   urgent warp (warp 15)  after "column j published": scales the first two blocks of the column, (j+1, j) and
+//                          (j+2, j) in a window, and applies the two pair updates the chain is going to read next
+//                          -- D_{j+2} and S_{j+2,j+1} -- then signals (kBarUrg, arrive);  ~550 cycles, well inside
+//                          the chain's ~960;
+//   general helpers        everything else of column j: the other rows (L_ij), the other pair updates, the
+//                          right-hand side, N_ij for the backward pass.  They re-join the chain only through kBarPub, one
+//                          column later; since every helper must arrive there, "column j published" also means
+//                          "all of column j-1 applied".
 __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S, double lambda) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int* col_ptr = S.col_ptr; const int* upd_ptr = S.upd_ptr; const int* row_idx = S.row_idx;
-  double* yv = S.yv;
+  double* yv = sm_solve + S.yv_off;
   if (T.j0 >= T.j1) return;
   const int blk_end = col_ptr[T.j1];
   int hi = blk_end;
@@ -165,9 +261,8 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
     cp_async_wait_all();
   }
   __syncthreads();
-  constexpr int kBoth = 32 + kHelpers;
 
-  if (warp == 0) {
+  if (warp == kChainWarp) {
     // ------------------------------------------------------------------ the chain warp
     const int lr = (lane >= 1) + (lane >= 3) + (lane >= 6) + (lane >= 10) + (lane >= 15);
     const int r = lane < 21 ? lr : 0, c = lane < 21 ? lane - lr * (lr + 1) / 2 : 0;
@@ -186,6 +281,19 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       }
       if (lane < 21) S.cdiag[lane] = dreg;
       __syncwarp();
+      PCH(0);
+      // the inputs of the NEXT column, while this one is being factored: they are final once the urgent updates of
+      // column j-1 are in (every older column is complete by then), and they must be read before column j is
+      // published, because the helpers then overwrite S_{j+1,j} with L_{j+1,j}
+      bool nlinked = false;
+      const double* pD = nullptr;
+      const double* pB = nullptr;
+      if (j + 1 < T.j1) {
+        const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
+        nlinked = nb > 0 && row_idx[base + 1] == j + 1;
+        pD = ring_blk(T, col_ptr[j + 1]) + r * 6 + c;
+        pB = ring_blk(T, base + 1);
+      }
       double a[22];
       {
         const double2* c2 = reinterpret_cast<const double2*>(S.cdiag);
@@ -193,26 +301,21 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
         for (int q = 0; q < 11; ++q) { const double2 v = c2[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
       }
       __syncwarp();
-      PCH(0);
       // every lane factors the block redundantly in registers: no shuffles or shared-memory round trips
       // between the pivots (scripts/ubench/chol.cu)
       const bool ok = chol6_packed(a, lambda + (S.sfix[j] ? 1. : 0.), l, rinv);
       if (T.prof && l[20] != 0.) PCH(1);
-      bool nlinked = false;
-      // every generation of the "updates applied" barrier is consumed before the next factor is published,
-      // so the helpers can never arrive twice on one generation
-      if (ok && j > T.j0) { bar_sync(kBarDone, kBoth); ++consumed; }   // updates of columns < j applied
-      PCH(2);
-      if (ok && j + 1 < T.j1) {
-        const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-        nlinked = nb > 0 && row_idx[base + 1] == j + 1;
-        dreg = ring_blk(T, col_ptr[j + 1])[r * 6 + c];
+      // the urgent updates of column j-1 (and with them everything older) are in: the next column's inputs are final
+      if (j > T.j0) { bar_sync(kBarUrg, 64); ++consumed; }
+      double dnext = 0.;
+      if (pD) {
+        dnext = *pD;
         if (nlinked) {
-          const double* B = ring_blk(T, base + 1);
-          load_row6(B + r * 6, sr);
-          load_row6(B + c * 6, sc);
+          load_row6(pB + r * 6, sr);
+          load_row6(pB + c * 6, sc);
         }
       }
+      if (T.prof && dnext != 1.2345e-300) PCH(2);
       if (lane == 0) {   // publish l (21) and rinv (6): 14 independent 16-byte stores by one lane (a per-lane
                          // select of "its" element would be a 27-deep dependent chain on the critical warp)
         double2* sl2 = reinterpret_cast<double2*>(S.sL[T.slot][j & 1]);
@@ -224,93 +327,51 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
         sl2[13] = make_double2(rinv[5], 0.);
         if (!ok) S.fail[T.slot][j & 1] = 1;
       }
-      bar_arrive(kBarPub, kBoth);
-      if (T.prof && dreg != 1.2345e-300) PCH(3);
+      bar_arrive(kBarPub, kPubAll);
+      PCH(3);
       if (!ok) { produced = j - T.j0; break; }
       linked = nlinked;
+      dreg = dnext;
     }
+    for (; consumed < produced; ++consumed) bar_sync(kBarUrg, 64);
     if (T.prof && lane == 0)
       for (int i = 0; i < 4; ++i) T.prof[i] = pa[i];
 #undef PCH
-    for (; consumed < produced; ++consumed) bar_sync(kBarDone, kBoth);
-  } else if ((warp & 3) != 0) {
-    // ------------------------------------------------------------------ helper warps
-    const int ht = (warp - 1 - (warp >> 2)) * 32 + lane;
-    int until_refill = T.refill_period;
-    long long ph[5] = {0, 0, 0, 0, 0}, pt = T.prof ? clock64() : 0;
-#define PHL(i) do { if (T.prof) { const long long c_ = clock64(); ph[i] += c_ - pt; pt = c_; } } while (0)
+  } else if (warp == kUrgentWarp) {
+    // ------------------------------------------------------------------ the urgent warp
     for (int j = T.j0; j < T.j1; ++j) {
       const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-      const int link = (j + 1 < T.j1 && nb > 0 && row_idx[base + 1] == j + 1) ? 1 : 0;
-      const int u0 = upd_ptr[j] + link, nunits = (upd_ptr[j + 1] - u0) * 4;
-      // this thread's first unit of the trailing update: fetched under the wait for the diagonal factor
-      int2 e0 = make_int2(0, 0);
-      if (ht < nunits) e0 = make_int2(__ldg(d.upd_ab + u0 + (ht >> 2)), __ldg(d.upd_dst + u0 + (ht >> 2)));
-      // ... and its first row of the column: final since the previous column's updates
-      const int nrows = nb * 6 + 1;
-      double v0[6] = {0, 0, 0, 0, 0, 0};
-      if (ht < nrows) load_row6(ht < nb * 6 ? ring_blk(T, base + 1 + ht / 6) + (ht % 6) * 6 : yv + 6 * j, v0);
-      bar_sync(kBarPub, kBoth);
-      PHL(0);
+      const bool want = j + 2 < T.j1;   // the chain reads D_{j+2} and S_{j+2,j+1} next
+      const int i1 = (j + 1 < T.j1 && nb > 0 && row_idx[base + 1] == j + 1) ? 0 : -1;   // index of row j+1 in the column (same
+                                                                                        // rule as the chain's and the unit warps' `link`)
+      int i2 = i1 + 1;                                                    // index of row j+2, if present
+      if (!(i2 < nb && row_idx[base + 1 + i2] == j + 2)) i2 = -1;
+      bar_sync(kBarPub, kPubAll);
       if (S.fail[T.slot][j & 1]) break;
-      const double* sl = S.sL[T.slot][j & 1];
-      // ---- rows of the column: L_ij = S_ij L_jj^-T (kept in the ring for the trailing update), and
-      //      N_ij = L_ij L_jj^-1 stored transposed for the backward pass; the right-hand side is one more row
-      for (int row = ht; row < nrows; row += kHelpers) {
-        double L_[28];
-        {
-          const double2* l2 = reinterpret_cast<const double2*>(sl);
+      // the first two blocks of the column are scaled here (the general helpers take the others)
+      if (lane < 6 * min(nb, 2)) {
+        const double2* l2 = reinterpret_cast<const double2*>(S.sL[T.slot][j & 1]);
+        double L_[28], v[6], o[6];
 #pragma unroll
-          for (int q = 0; q < 14; ++q) { const double2 t2 = l2[q]; L_[2 * q] = t2.x; L_[2 * q + 1] = t2.y; }
-        }
-        double* src;
-        double* gdst;
-        int gstride;
-        if (row < nb * 6) {
-          const int a = row / 6, rr = row - a * 6;
-          src = ring_blk(T, base + 1 + a) + rr * 6;
-          gdst = d.S + (size_t)(base + 1 + a) * 36 + rr;
-          gstride = 6;
-        } else {
-          src = yv + 6 * j;
-          gdst = d.ywork + 6 * (size_t)j;
-          gstride = 1;
-        }
-        double v[6], o[6], n[6];
-        if (row == ht) {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) v[q] = v0[q];
-        } else {
-          load_row6(src, v);
-        }
+        for (int q = 0; q < 14; ++q) { const double2 t2 = l2[q]; L_[2 * q] = t2.x; L_[2 * q + 1] = t2.y; }
+        double* src = ring_blk(T, base + 1 + lane / 6) + (lane % 6) * 6;
+        load_row6(src, v);
         row_fwd(v, L_, L_ + 21, o);
-        {
-          double2* d2 = reinterpret_cast<double2*>(src);
-          d2[0] = make_double2(o[0], o[1]); d2[1] = make_double2(o[2], o[3]); d2[2] = make_double2(o[4], o[5]);
-        }
-        row_bwd(o, L_, L_ + 21, n);
-#pragma unroll
-        for (int q = 0; q < 6; ++q) gdst[q * gstride] = n[q];
+        double2* d2 = reinterpret_cast<double2*>(src);
+        d2[0] = make_double2(o[0], o[1]); d2[1] = make_double2(o[2], o[3]); d2[2] = make_double2(o[4], o[5]);
       }
-      PHL(1);
-      bar_sync(kBarH, kHelpers);
-      PHL(2);
-      // ---- trailing update in quarter-block units: rows 3h..3h+2, columns 3g..3g+2 of S_ab -= L_a L_b^T
-      //      (18 16-byte loads, 54 FMAs; at most one unit per thread for SLAM-shaped columns)
-      for (int u = ht; u < nunits; u += kHelpers) {
-        const int2 e = (u == ht) ? e0 : make_int2(__ldg(d.upd_ab + u0 + (u >> 2)), __ldg(d.upd_dst + u0 + (u >> 2)));
-        const int h = (u >> 1) & 1, g = u & 1;
-        const double2* La = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + (e.x >> 16)) + h * 18);
-        const double2* Lb = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + (e.x & 0xffff)) + g * 18);
+      bar_arrive(kBarH, kRowsAll);   // (orders the stores above before the trailing update of the unit warps)
+      if (want && i2 >= 0 && lane < 8 && (lane < 4 || i1 >= 0)) {
+        // lanes 0-3: D_{j+2} -= L2 L2^T, lanes 4-7: S_{j+2,j+1} -= L2 L1^T, a quarter block each
+        const int h = (lane >> 1) & 1, g = lane & 1, second = lane >> 2;
+        const double2* La = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + i2) + h * 18);
+        const double2* Lb = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + (second ? i1 : i2)) + g * 18);
         double a[18], b[18], o[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) { const double2 v = La[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
 #pragma unroll
         for (int q = 0; q < 9; ++q) { const double2 v = Lb[q]; b[2 * q] = v.x; b[2 * q + 1] = v.y; }
-        const int dst = e.y;
-        double* D = (dst < hi ? ring_blk(T, dst)
-                              : (dst >= T.sep_blk0 ? T.area + (size_t)(dst - T.sep_blk0) * 36 : d.S + (size_t)dst * 36)) +
-                    h * 18 + g * 3;
+        double* D = ring_blk(T, second ? col_ptr[j + 1] + 1 : col_ptr[j + 2]) + h * 18 + g * 3;
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
@@ -326,120 +387,223 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
 #pragma unroll
           for (int cc = 0; cc < 3; ++cc) D[rr * 6 + cc] = o[rr * 3 + cc];
       }
-      // b_a -= L_aj y_j, dealt from the last helper thread downwards (the first ones hold the update units)
-      for (int w = kHelpers - 1 - ht; w < nb * 6; w += kHelpers) {
+      bar_arrive(kBarUrg, 64);
+    }
+  } else if (unit_warp_index(warp) >= 0) {
+    // ------------------------------------------------------------------ unit warps: the trailing update
+    const int ut = unit_warp_index(warp) * 32 + lane;
+    int until_refill = T.refill_period;
+    long long ph[5] = {0, 0, 0, 0, 0}, pt = T.prof ? clock64() : 0;
+#define PHL(i) do { if (T.prof) { const long long c_ = clock64(); ph[i] += c_ - pt; pt = c_; } } while (0)
+    for (int j = T.j0; j < T.j1; ++j) {
+      const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
+      const int link = (j + 1 < T.j1 && nb > 0 && row_idx[base + 1] == j + 1) ? 1 : 0;
+      const int u0 = upd_ptr[j] + link, nunits = (upd_ptr[j + 1] - u0) * 4;
+      // destinations the urgent warp takes care of (same rule as there)
+      int dU1 = -1, dU2 = -1;
+      if (j + 2 < T.j1 && link < nb && row_idx[base + 1 + link] == j + 2) {   // row j+2 can only sit right after row j+1
+        dU1 = col_ptr[j + 2];
+        if (link) dU2 = col_ptr[j + 1] + 1;
+      }
+      // this thread's first unit: fetched under the wait for the diagonal factor
+      int2 e0 = make_int2(0, 0);
+      if (ut < nunits) e0 = make_int2(__ldg(d.upd_ab + u0 + (ut >> 2)), __ldg(d.upd_dst + u0 + (ut >> 2)));
+      bar_sync(kBarPub, kPubAll);   // (also: every helper is done with the previous column)
+      const int col_failed = S.fail[T.slot][j & 1];   // (first read behind the barrier: the barrier wait ends here)
+      if (T.prof && col_failed >= 0) PHL(0);
+      if (col_failed) break;
+      bar_sync(kBarH, kRowsAll);    // the column's rows are scaled
+      if (T.prof && *reinterpret_cast<volatile int*>(&S.fail[T.slot][j & 1]) >= 0) PHL(1);
+      // quarter-block units, at most one per thread for SLAM-shaped columns (the urgent warp owns lanes 96..127 of the
+      // unit index space)
+      for (int u = ut; u < nunits; u += kUnitStride) {
+        const int2 e = (u == ut) ? e0 : make_int2(__ldg(d.upd_ab + u0 + (u >> 2)), __ldg(d.upd_dst + u0 + (u >> 2)));
+        if (e.y == dU1 || e.y == dU2) continue;   // the urgent warp's urgent ones
+        quarter_unit(d, T, base, hi, u, e.x, e.y);
+      }
+      PHL(2);
+      ring_refill(d, T, col_ptr, blk_end, j, ut, until_refill, hi);
+    }
+    if (T.prof && ut == 0)
+      for (int i = 0; i < 4; ++i) T.prof[4 + i] = ph[i];
+#undef PHL
+  } else if (row_warp_index(warp) >= 0) {
+    // ------------------------------------------------------------------ row warps: L rows, N rows, right-hand side
+    const int rt = row_warp_index(warp) * 32 + lane;
+    int until_refill = T.refill_period;
+    long long ph[5] = {0, 0, 0, 0, 0}, pt = T.prof ? clock64() : 0;
+#define PHL(i) do { if (T.prof) { const long long c_ = clock64(); ph[i] += c_ - pt; pt = c_; } } while (0)
+    for (int j = T.j0; j < T.j1; ++j) {
+      const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
+      const int nrows = nb * 6 + 1;
+      bar_sync(kBarPub, kPubAll);
+      const int col_failed = S.fail[T.slot][j & 1];
+      if (T.prof && col_failed >= 0) PHL(0);
+      if (col_failed) break;
+      const double* sl = S.sL[T.slot][j & 1];
+      double L_[28];
+      {
+        const double2* l2 = reinterpret_cast<const double2*>(sl);
+#pragma unroll
+        for (int q = 0; q < 14; ++q) { const double2 t2 = l2[q]; L_[2 * q] = t2.x; L_[2 * q + 1] = t2.y; }
+      }
+      // ---- rows of the column: L_ij = S_ij L_jj^-T, kept in the ring for the trailing update (the first two blocks
+      //      are the urgent warp's); the right-hand side is one more row (forward solve)
+      for (int row = 6 * min(nb, 2) + rt; row < nrows; row += kRowThreads) {
+        double* src = sm_solve + (row < nb * 6 ? ring_idx(T, base + 1 + row / 6) + (row % 6) * 6 : S.yv_off + 6 * j);
+        double v[6], o[6];
+        load_row6(src, v);
+        row_fwd(v, L_, L_ + 21, o);
+        double2* d2 = reinterpret_cast<double2*>(src);
+        d2[0] = make_double2(o[0], o[1]); d2[1] = make_double2(o[2], o[3]); d2[2] = make_double2(o[4], o[5]);
+      }
+      PHL(1);
+      bar_sync(kBarH, kRowsAll);
+      if (T.prof && *reinterpret_cast<volatile int*>(&S.fail[T.slot][j & 1]) >= 0) PHL(2);
+      if (rt >= 32) {   // second row warp: the units beyond the unit warps' lanes (index space 96..127 mod 128)
+        const int link = (j + 1 < T.j1 && nb > 0 && row_idx[base + 1] == j + 1) ? 1 : 0;
+        const int u0 = upd_ptr[j] + link, nunits = (upd_ptr[j + 1] - u0) * 4;
+        int dU1 = -1, dU2 = -1;
+        if (j + 2 < T.j1 && link < nb && row_idx[base + 1 + link] == j + 2) {
+          dU1 = col_ptr[j + 2];
+          if (link) dU2 = col_ptr[j + 1] + 1;
+        }
+        for (int u = kUnitThreads + (rt - 32); u < nunits; u += kUnitStride) {
+          const int ab = __ldg(d.upd_ab + u0 + (u >> 2)), dst = __ldg(d.upd_dst + u0 + (u >> 2));
+          if (dst == dU1 || dst == dU2) continue;
+          quarter_unit(d, T, base, hi, u, ab, dst);
+        }
+      }
+      // ---- N_ij = L_ij L_jj^-1 (and z_j = y_j L_jj^-1) for the backward pass, stored transposed in row-major order;
+      //      nothing in the forward pass waits for it
+      for (int row = rt; row < nrows; row += kRowThreads) {
+        const double* src;
+        double* gdst;
+        int gstride;
+        if (row < nb * 6) {
+          const int a = row / 6, rr = row - a * 6;
+          src = sm_solve + ring_idx(T, base + 1 + a) + rr * 6;
+          gdst = d.Nrow + (size_t)__ldg(d.rowpos + base + 1 + a) * 36 + rr;   // transposed inside the block
+          gstride = 6;
+        } else {
+          src = sm_solve + S.yv_off + 6 * j;
+          gdst = d.ywork + 6 * (size_t)j;
+          gstride = 1;
+        }
+        double o[6], n[6];
+        load_row6(src, o);
+        row_bwd(o, L_, L_ + 21, n);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) gdst[q * gstride] = n[q];
+      }
+      // ---- b_a -= L_aj y_j
+      for (int w = rt; w < nb * 6; w += kRowThreads) {
         const int a = w / 6, rr = w - a * 6;
         double La[6], yj[6];
         load_row6(ring_blk(T, base + 1 + a) + rr * 6, La);
         load_row6(yv + 6 * j, yj);
-        const double s = (La[0] * yj[0] + La[1] * yj[1] + La[2] * yj[2]) + (La[3] * yj[3] + La[4] * yj[4] + La[5] * yj[5]);
-        yv[6 * row_idx[base + 1 + a] + rr] -= s;
-      }
-      // ---- every refill_period columns: reload the ring slots the finished columns freed.  Copies are
-      //      never in flight while updates run, so a destination is either resident (< hi) or in HBM.
-      if (--until_refill == 0) {
-        until_refill = T.refill_period;
-        if (hi < blk_end && j + 1 < T.j1) {
-          __threadfence();   // read-modify-writes of far blocks in HBM before the copies read them
-          bar_sync(kBarH, kHelpers);
-          const int hi_new = min(blk_end, col_ptr[j + 1] + T.cap);
-          for (int cc = ht; cc < (hi_new - hi) * 18; cc += kHelpers) {
-            const int id = hi + cc / 18, w = cc % 18;
-            cp_async16(ring_blk(T, id) + 2 * w, d.S + (size_t)id * 36 + 2 * w);
-          }
-          cp_async_commit();
-          cp_async_wait_all();
-          bar_sync(kBarH, kHelpers);
-          hi = hi_new;
-        }
+        const double sdot = (La[0] * yj[0] + La[1] * yj[1] + La[2] * yj[2]) + (La[3] * yj[3] + La[4] * yj[4] + La[5] * yj[5]);
+        yv[6 * row_idx[base + 1 + a] + rr] -= sdot;
       }
       PHL(3);
-      bar_arrive(kBarDone, kBoth);
+      ring_refill(d, T, col_ptr, blk_end, j, kUnitThreads + rt, until_refill, hi);
     }
-    if (T.prof && (ht == 0 || ht == kHelpers - 1))
-      for (int i = 0; i < 4; ++i) T.prof[(ht == 0 ? 4 : 8) + i] = ph[i];
+    if (T.prof && rt == 0)
+      for (int i = 0; i < 4; ++i) T.prof[8 + i] = ph[i];
 #undef PHL
   }
   __threadfence();   // N blocks and z (global) before the backward pass streams them back
   __syncthreads();
 }
 
-// Backward solve x_j = z_j - sum_i N_ij^T x_i for columns [j0, j1), descending: the transposed N blocks
-// and z are streamed back through `buf` (2 x half blocks) in chunks, double buffered; warp 0 walks the
-// dependency chain out of shared memory while the other warps fetch the next chunk.
-__device__ void backsolve_range(const BaDev& d, int j0, int j1, double* buf, int half, const SolveShared& S) {
-  if (j0 >= j1) return;
+// Backward solve x_j = z_j - sum_{i > j} N_ij^T x_i, row oriented: the rows are walked from the last to the
+// first; once x_i is final it is scattered into the columns of row i (c_j -= N_ij^T x_i for every block (i, j)).
+// The row-major N blocks of a descending run of rows are ONE contiguous piece of memory; they are streamed through
+// `buf` (2 x half blocks) in chunks of whole rows, double buffered: warp 0 walks the chain while the other warps
+// fetch the next chunk.  Per row the chain is one shared-memory round trip (x_i) and six FMAs; no reduction across
+// lanes, no shuffles.  Only blocks whose column lies in [c0, c1) are applied.
+constexpr int kMaxChunks = 48;
+__device__ void scatter_rows(const BaDev& d, int lo, int hi, int c0, int c1, int buf_off, int half, const SolveShared& S,
+                             int* sChunk) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int* col_ptr = S.col_ptr; const int* row_idx = S.row_idx;
-  double* xv = S.yv;
-  double* bufs[2] = {buf, buf + (size_t)half * 36};
-  auto chunk_lo = [&](int jhi) {   // largest [jlo, jhi) whose blocks + z fit one half
-    int jlo = jhi - 1;
-    while (jlo > j0 && (col_ptr[jhi] - col_ptr[jlo - 1]) + (jhi - (jlo - 1)) <= half) --jlo;
-    return jlo;
-  };
-  auto load_chunk = [&](double* b, int jlo, int jhi, int tid, int nth) {
-    const int nb16 = (col_ptr[jhi] - col_ptr[jlo]) * 18;
-    const double* src = d.S + (size_t)col_ptr[jlo] * 36;
-    for (int c = tid; c < nb16; c += nth) cp_async16(b + 2 * (size_t)c, src + 2 * (size_t)c);
-    double* zb = b + (size_t)(col_ptr[jhi] - col_ptr[jlo]) * 36;
-    const double* zs = d.ywork + 6 * (size_t)jlo;
-    for (int c = tid; c < (jhi - jlo) * 3; c += nth) cp_async16(zb + 2 * (size_t)c, zs + 2 * (size_t)c);
-    cp_async_commit();
-  };
-  int jhi = j1, which = 0;
-  int jlo = chunk_lo(jhi);
-  load_chunk(bufs[0], jlo, jhi, t, kSolveThreads);
-  cp_async_wait_all();
-  bar_sync(kBarBack, kSolveThreads);
-  const int r = lane % 6, g = lane / 6;   // 5 lane groups walk a column's blocks; lanes 30, 31 idle
-  double xreg = 0.;                       // lanes 0..5: x of the column solved last
-  while (jhi > j0) {
-    const int njhi = jlo, njlo = njhi > j0 ? chunk_lo(njhi) : j0;
-    if (njhi > j0 && warp > 0) load_chunk(bufs[which ^ 1], njlo, njhi, t - 32, kSolveThreads - 32);
-    if (warp == 0) {
-      const double* b = bufs[which];
-      const double* zb = b + (size_t)(col_ptr[jhi] - col_ptr[jlo]) * 36;
-      for (int j = jhi - 1; j >= jlo; --j) {
-        const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-        // the block right below the diagonal multiplies the x just solved: it is taken from registers
-        // (shuffle broadcast); everything else reads x from shared memory and does not sit on the chain
-        const int link = (j + 1 < j1 && nb > 0 && row_idx[base + 1] == j + 1) ? 1 : 0;
-        double acc = 0.;
-        if (lane < 30)
-          for (int a = g + link; a < nb; a += 5) {
-            double Lt[6], xa[6];
-            load_row6(b + (size_t)(base + 1 + a - col_ptr[jlo]) * 36 + r * 6, Lt);
-            load_row6(xv + 6 * row_idx[base + 1 + a], xa);
-            acc += (Lt[0] * xa[0] + Lt[1] * xa[1] + Lt[2] * xa[2]) + (Lt[3] * xa[3] + Lt[4] * xa[4] + Lt[5] * xa[5]);
-          }
-        double tot = acc;
-        tot += __shfl_down_sync(0xffffffffu, acc, 6);
-        const double a12 = __shfl_down_sync(0xffffffffu, acc, 12);
-        const double a18 = __shfl_down_sync(0xffffffffu, acc, 18);
-        const double a24 = __shfl_down_sync(0xffffffffu, acc, 24);
-        tot += a12 + a18 + a24;
-        double v = (lane < 6 ? zb[6 * (j - jlo) + lane] : 0.) - tot;
-        if (link) {
-          double Lt[6];
-          load_row6(b + (size_t)(base + 1 - col_ptr[jlo]) * 36 + (lane < 6 ? lane : 0) * 6, Lt);
-          double s0 = 0., s1 = 0.;
-#pragma unroll
-          for (int q = 0; q < 6; q += 2) {
-            s0 = fma(Lt[q], __shfl_sync(0xffffffffu, xreg, q), s0);
-            s1 = fma(Lt[q + 1], __shfl_sync(0xffffffffu, xreg, q + 1), s1);
-          }
-          v -= s0 + s1;
-        }
-        xreg = v;
-        if (lane < 6) xv[6 * j + lane] = v;
-        __syncwarp();
+  const int* rptr = S.upd_ptr;   // the forward pass's index arrays have been replaced by the row-major ones
+  const int* rcol = S.row_idx;
+  double* xv = sm_solve + S.yv_off;
+  const int r = lane % 6, g = lane / 6;   // five lane groups take the blocks of a row; lanes 30, 31 idle
+  for (int top = hi; top > lo;) {
+    // chunk boundaries top = b[0] > b[1] > ... (rows [b[k+1], b[k]) form chunk k), worked out once by one thread
+    if (t == 0) {
+      int n = 0, a = top;
+      sChunk[0] = top;
+      while (a > lo && n < kMaxChunks) {
+        int b = a - 1;
+        while (b > lo && rptr[a] - rptr[b - 1] <= half) --b;
+        sChunk[++n] = b;
+        a = b;
       }
+      sChunk[kMaxChunks + 1] = n;
     }
+    bar_sync(kBarBack, kSolveThreads);
+    const int nchunks = sChunk[kMaxChunks + 1];
+    auto load_chunk = [&](int k, int tid, int nth) {
+      const int b0 = rptr[sChunk[k + 1]], n16 = (rptr[sChunk[k]] - b0) * 18;
+      double* dst = sm_solve + buf_off + (k & 1) * half * 36;
+      const double* src = d.Nrow + (size_t)b0 * 36;
+      for (int c = tid; c < n16; c += nth) cp_async16(dst + 2 * (size_t)c, src + 2 * (size_t)c);
+      cp_async_commit();
+    };
+    load_chunk(0, t, kSolveThreads);
     cp_async_wait_all();
     bar_sync(kBarBack, kSolveThreads);
-    jhi = njhi; jlo = njlo; which ^= 1;
+    for (int k = 0; k < nchunks; ++k) {
+      if (k + 1 < nchunks && warp > 0) load_chunk(k + 1, t - 32, kSolveThreads - 32);
+      if (warp == 0) {
+        const double* b = sm_solve + buf_off + (k & 1) * half * 36;
+        const int rlo = sChunk[k + 1], b0 = rptr[rlo];
+        for (int i = sChunk[k] - 1; i >= rlo; --i) {
+          const int p0 = rptr[i], nb = rptr[i + 1] - p0;
+          double xi[6];
+          load_row6(xv + 6 * i, xi);   // final: every row above has been scattered (and the warp synchronised)
+          if (lane < 30)
+            for (int a = g; a < nb; a += 5) {
+              const int col = rcol[p0 + a];
+              if (col < c0 || col >= c1) continue;   // a separator row also holds blocks of the other branch
+              double Nt[6];
+              load_row6(b + (size_t)(p0 - b0 + a) * 36 + r * 6, Nt);
+              const double sdot = (Nt[0] * xi[0] + Nt[1] * xi[1] + Nt[2] * xi[2]) + (Nt[3] * xi[3] + Nt[4] * xi[4] + Nt[5] * xi[5]);
+              xv[6 * col + r] -= sdot;
+            }
+          __syncwarp();
+        }
+      }
+      cp_async_wait_all();
+      bar_sync(kBarBack, kSolveThreads);
+    }
+    top = sChunk[nchunks];
+    bar_sync(kBarBack, kSolveThreads);   // sChunk is rewritten by the next round
   }
+}
+
+//   rows [k0, k1): x already known (separator rows of a branch), only scattered;  rows [j0, j1): solved here.
+//   S.yv holds c (= z for the columns of the range, x elsewhere).
+__device__ void backsolve_rows(const BaDev& d, int j0, int j1, int k0, int k1, int buf_off, int half, const SolveShared& S,
+                               int* sChunk) {
+  if (j0 >= j1) return;
+  double* xv = sm_solve + S.yv_off;
+  for (int i = 6 * j0 + (int)threadIdx.x; i < 6 * j1; i += kSolveThreads) xv[i] = d.ywork[i];   // c <- z
+  __syncthreads();
+  scatter_rows(d, k0, k1, j0, j1, buf_off, half, S, sChunk);
+  scatter_rows(d, j0, j1, j0, j1, buf_off, half, S, sChunk);
+}
+
+// Between the forward and the backward pass the column-oriented index arrays in shared memory (upd_ptr, row_idx)
+// are replaced by the row-oriented ones (rptr, rcol).
+__device__ void load_row_index(const BaDev& d, const SolveShared& S) {
+  const int t = threadIdx.x;
+  __syncthreads();
+  for (int i = t; i <= d.P; i += kSolveThreads) S.upd_ptr[i] = d.rptr[i];
+  for (int i = t; i < d.nblk - d.P; i += kSolveThreads) S.row_idx[i] = d.rcol[i];
+  __syncthreads();
 }
 
 // smem layout: [ring: cap*36 doubles][area: nsep*36 doubles][y: 6P doubles][meta ints: col_ptr (P+1),
@@ -447,12 +611,12 @@ __device__ void backsolve_range(const BaDev& d, int j0, int j1, double* buf, int
 // cap is a power of two >= 4 * (widest column of a branch + 1).
 __global__ void __launch_bounds__(kSolveThreads)
 k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
-  extern __shared__ __align__(16) double sm_solve[];
   __shared__ int sFail[2][2];
   __shared__ double sRed[kSolveThreads / 32 + 2];
   __shared__ __align__(16) double sLbuf[2][2][28];
   __shared__ __align__(16) double sCdiag[22];
   __shared__ int sXfail;   // written by the other CTA of the cluster
+  __shared__ int sChunk[kMaxChunks + 2];
   LmCtl* ctl = d.ctl;
   if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
   cg::cluster_group cluster = cg::this_cluster();
@@ -464,10 +628,11 @@ k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
   const int G = d.nbranch;                 // 1: a single chain, 2: two ends + separator (cluster of 2 CTAs)
   const int sep0 = d.branch_ptr[G];        // first separator column (= P when G == 1)
   SolveShared S;
-  double* ring = sm_solve;
-  double* area = ring + (size_t)cap * 36;
-  S.yv = area + (size_t)nsep * 36;
-  int* meta = reinterpret_cast<int*>(S.yv + ((6 * (size_t)P + 1) / 2) * 2);
+  const int ring_off = 0, area_off = cap * 36;
+  double* area = sm_solve + area_off;
+  S.yv_off = area_off + nsep * 36;
+  double* const yv_k = sm_solve + S.yv_off;
+  int* meta = reinterpret_cast<int*>(yv_k + ((6 * (size_t)P + 1) / 2) * 2);
   S.col_ptr = meta; S.upd_ptr = S.col_ptr + (P + 1); S.row_idx = S.upd_ptr + (P + 1);
   S.sfix = reinterpret_cast<unsigned char*>(S.row_idx + nblk);
   S.fail = sFail; S.sL = sLbuf; S.cdiag = sCdiag;
@@ -483,7 +648,7 @@ k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
     const bool mine = (j >= my0 && j < my1) || (rank == 0 && j >= sep0);
     double v = 0.;
     if (mine) { const int p = d.perm[j]; v = d.bp[6 * p + rr] - d.bc[6 * p + rr]; }
-    S.yv[i] = v;
+    yv_k[i] = v;
   }
   const int sep_blk0 = G > 1 ? d.col_ptr[sep0] : nblk;
   if (G > 1) {   // separator blocks: CTA 0 starts from S, CTA 1 from zero; both accumulate their branch's updates
@@ -494,9 +659,9 @@ k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
   tk[0] = clock64();
 
   Team br;
-  br.ring = ring; br.org = 0; br.mask = (unsigned)cap - 1u; br.cap = cap; br.prefilled = 0;
-  br.j0 = my0; br.j1 = my1; br.sep_blk0 = sep_blk0; br.area = area; br.slot = 0; br.refill_period = refill_branch;
-  br.prof = (prof && d.dbg) ? d.dbg + 12 + 12 * rank : nullptr;
+  br.ring_off = ring_off; br.org = 0; br.mask = (unsigned)cap - 1u; br.cap = cap; br.prefilled = 0;
+  br.j0 = my0; br.j1 = my1; br.sep_blk0 = sep_blk0; br.area_off = area_off; br.slot = 0; br.refill_period = refill_branch;
+  br.prof = (prof && d.dbg) ? d.dbg + 12 + 12 * rank : nullptr;   // [.. + 32 + 3): unit phases of helper 0 (rank 0: dbg 44..46, rank 1: 56..58)
   factor_range(d, br, S, lambda);
   tk[1] = clock64();
   int failed = sFail[0][0] | sFail[0][1];
@@ -506,7 +671,7 @@ k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
     tk[2] = clock64();
     if (rank == 0) {
       const double* rarea = cluster.map_shared_rank(area, 1);
-      const double* ryv = cluster.map_shared_rank(S.yv, 1);
+      const double* ryv = cluster.map_shared_rank(yv_k, 1);
       const int* rfail = cluster.map_shared_rank(&sXfail, 1);
       for (int i = t; i < nsep * 18; i += nt) {
         const double2 a = reinterpret_cast<const double2*>(rarea)[i];
@@ -514,30 +679,33 @@ k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
         const double2 b = *o;
         *o = make_double2(a.x + b.x, a.y + b.y);
       }
-      for (int i = 6 * sep0 + t; i < 6 * P; i += nt) S.yv[i] += ryv[i];
+      for (int i = 6 * sep0 + t; i < 6 * P; i += nt) yv_k[i] += ryv[i];
       failed |= *rfail;
       __syncthreads();
       if (!failed) {
         Team sp;
-        sp.ring = area; sp.org = sep_blk0; sp.mask = 0xffffffffu; sp.cap = nsep; sp.prefilled = 1;
-        sp.j0 = sep0; sp.j1 = P; sp.sep_blk0 = nblk; sp.area = area; sp.slot = 1; sp.refill_period = 1 << 30; sp.prof = nullptr;
+        sp.ring_off = area_off; sp.org = sep_blk0; sp.mask = 0xffffffffu; sp.cap = nsep; sp.prefilled = 1;
+        sp.j0 = sep0; sp.j1 = P; sp.sep_blk0 = nblk; sp.area_off = area_off; sp.slot = 1; sp.refill_period = 1 << 30; sp.prof = nullptr;
         factor_range(d, sp, S, lambda);
         failed = sFail[1][0] | sFail[1][1];
       }
       tk[3] = clock64();
-      if (!failed) backsolve_range(d, sep0, P, ring, cap / 2, S);
+      load_row_index(d, S);
+      if (!failed) backsolve_rows(d, sep0, P, 0, 0, ring_off, cap / 2, S, sChunk);
       __syncthreads();
       // push the separator solution and the verdict into CTA 1
-      double* rx = cluster.map_shared_rank(S.yv, 1);
+      double* rx = cluster.map_shared_rank(yv_k, 1);
       int* rf = cluster.map_shared_rank(&sXfail, 1);
-      for (int i = 6 * sep0 + t; i < 6 * P; i += nt) rx[i] = S.yv[i];
+      for (int i = 6 * sep0 + t; i < 6 * P; i += nt) rx[i] = yv_k[i];
       if (t == 0) *rf = failed;
     } else {
+      load_row_index(d, S);
       tk[3] = tk[2];
     }
     cluster.sync();   // #2
     if (rank == 1) failed = sXfail;
   } else {
+    load_row_index(d, S);
     tk[2] = tk[3] = tk[1];
   }
   tk[4] = clock64();
@@ -551,10 +719,10 @@ k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
     if (G > 1) cluster.sync();   // keeps the barrier count of the two CTAs equal (#3)
     return;
   }
-  backsolve_range(d, my0, my1, ring, cap / 2, S);
+  backsolve_rows(d, my0, my1, G > 1 ? sep0 : P, P, ring_off, cap / 2, S, sChunk);
   __syncthreads();
   tk[5] = clock64();
-  double* xv = S.yv;
+  double* xv = yv_k;
   // --- pose update (G2oVertexSE3::oplusImpl) into the trial buffer; scale = sum x (lambda x + b)
   double sc = 0;
   for (int p = t; p < P; p += nt) {

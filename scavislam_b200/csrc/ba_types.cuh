@@ -44,6 +44,7 @@ struct BaDev {
   const int* lm_sptr;            // [L+1]
   const int* lm_anchor;          // [L]
   const unsigned char* lm_self;  // [L] first edge is the observation in the anchor frame
+  const int* lm_user;            // [L] internal landmark -> the caller's landmark index
   // fused-kernel work lists: tasks = runs of landmarks with identical slot lists and <= 8 frames
   const int* task_lm;   // [ntasks] first landmark
   const int* task_cnt;  // [ntasks] landmarks in the task
@@ -79,7 +80,11 @@ struct BaDev {
   const int* upd_dst;  // destination block of each (a>=b) pair of a column
   const int* upd_ab;   // (a << 16 | b): indices into the column's sub-diagonal list (b-major order)
   const int* urg_dst;  // [nblk] destination of pair (a, 0) of column j at col_ptr[j] + 1 + a
-  double* Linv;        // [P][36] inverse of the diagonal factor blocks
+  double* Linv;        // [P][36] inverse of the diagonal factor blocks (general solver)
+  const int* rptr;     // [P+1] row-major index of the off-diagonal factor blocks, columns descending inside a row
+  const int* rowpos;   // [nblk] position of a block in that order (-1 for diagonal blocks)
+  const int* rcol;     // [nblk - P] column of the block at a row-major position
+  double* Nrow;        // [nblk - P][36] N_ij^T = (L_ij L_jj^-1)^T in row-major order, written by the forward pass of k_solve
   int nbranch;              // independent branches of the elimination tree (1 = a single chain)
   const int* branch_ptr;    // [nbranch + 1] column ranges of the branches; [nbranch] = first separator column
   double* ywork;       // [6P]

@@ -308,6 +308,23 @@ void launch_regroup(const BaDev& d, const double* raw, cudaStream_t st) {
   if (d.E > 0) k_regroup<<<(d.E + 255) / 256, 256, 0, st>>>(d, raw);
 }
 
+// ------------------------------------------------------------------ k_export: accepted state -> [P][7] poses, [L][3] psi in the CALLER's order
+// (restoreDataFromG2o's read-out, slam_graph.cpp:1037-1058, as one contiguous buffer for a single device-to-host copy)
+__global__ void k_export(BaDev d, double* __restrict__ out) {
+  const int cur = d.ctl->cur;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 7 * d.P) out[i] = d.pose[cur][i];
+  if (i < d.L) {
+    const double* s = d.psi[cur] + 3 * (size_t)i;
+    double* o = out + 7 * (size_t)d.P + 3 * (size_t)d.lm_user[i];
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+  }
+}
+void launch_export(const BaDev& d, double* out, cudaStream_t st) {
+  const int n = d.L > 7 * d.P ? d.L : 7 * d.P;
+  if (n > 0) k_export<<<(n + 255) / 256, 256, 0, st>>>(d, out);
+}
+
 void launch_prep(const BaDev& d, int buf, cudaStream_t st) {
   if (d.P == 0) return;
   k_prep<<<(d.P + 127) / 128, 128, 0, st>>>(d, buf);

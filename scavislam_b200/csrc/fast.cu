@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/svs_b200.h"
+#include "internal.cuh"
 
 namespace {
 
@@ -110,44 +111,74 @@ struct GridParams {
   int grid_w, grid_h, fast_min, fast_max, min_inner, min_outer, max_inner, max_outer;
 };
 
-// The threshold walk of FastGrid::detectAdaptively (fast_grid.cpp:86-152) on histogram suffix
-// sums: one thread per grid row (prev_thr / prev_prev_thr are shared by the cells of a row).
-__global__ void k_fast_select(CellDev* cells, const int* __restrict__ hist, GridParams g, int trials, int* thr_detect) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.grid_h) return;
-  int prev_thr = -1, prev_prev_thr = -2;
-  for (int i = 0; i < g.grid_w; ++i) {
-    const int ci = j * g.grid_w + i;
-    int thr = cells[ci].thr;
-    int tdet = -1;   // threshold of the last detect() call; -1 = none (trials <= 0)
-    for (int trial = 0; trial < trials; ++trial) {
-      tdet = thr;
-      int nd = 0;
-      for (int s = max(thr, 0); s < 256; ++s) nd += hist[ci * 256 + s];
-      if (prev_prev_thr == thr) { thr = (thr + prev_prev_thr) / 2; break; }
-      prev_prev_thr = prev_thr;
-      prev_thr = thr;
-      if (nd < g.min_inner) {
-        if (thr <= g.fast_min) break;
-        --thr;
-        if (nd < g.min_outer) {
-          if (thr <= g.fast_min) break;
-          --thr;
-          continue;
-        }
-      } else if (nd > g.max_inner) {
-        if (thr >= g.fast_max) break;
-        ++thr;
-        if (nd > g.max_outer) {
-          if (thr >= g.fast_max) break;
-          ++thr;
-          continue;
-        }
+// The threshold walk of FastGrid::detectAdaptively (fast_grid.cpp:86-152) on histogram suffix sums.
+// One warp per cell first turns the cell's 256-bin score histogram into suffix sums in shared memory
+// (count of corners at threshold >= s), so that every trial of the walk is one lookup; then one thread per
+// grid row walks its cells (prev_thr / prev_prev_thr are shared by the cells of a row).
+constexpr int kSelCells = 32;   // cells per launch block (kMaxCells is 64: two rounds at most)
+__global__ void __launch_bounds__(kSelCells * 32)
+k_fast_select(CellDev* cells, const int* __restrict__ hist, GridParams g, int trials, int* thr_detect) {
+  __shared__ int ssuf[kSelCells][257];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncells = g.grid_w * g.grid_h;
+  const int per_round = (kSelCells / g.grid_w) * g.grid_w;   // whole grid rows per round (grid_w <= kSelCells, checked by the launcher)
+  for (int c0 = 0; c0 < ncells; c0 += per_round) {
+    const int ci = c0 + warp;
+    if (warp < per_round && ci < ncells) {
+      // lane owns bins [8 lane, 8 lane + 8): local suffix sums, then a warp scan over the lane totals
+      int v[8], tot = 0;
+#pragma unroll
+      for (int q = 7; q >= 0; --q) { tot += hist[ci * 256 + 8 * lane + q]; v[q] = tot; }
+      int above = tot;   // inclusive suffix scan over lanes (higher lanes = higher bins)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_down_sync(0xffffffffu, above, o);
+        if (lane + o < 32) above += up;
       }
-      break;
+      above -= tot;      // corners in the bins of all higher lanes
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ssuf[warp][8 * lane + q] = v[q] + above;
+      if (lane == 0) ssuf[warp][256] = 0;
     }
-    cells[ci].thr = thr;
-    thr_detect[ci] = tdet;
+    __syncthreads();
+    const int rows_here = min(per_round, ncells - c0) / g.grid_w;
+    const int j = threadIdx.x;   // grid row within this round
+    if (j < rows_here) {
+      int prev_thr = -1, prev_prev_thr = -2;
+      for (int i = 0; i < g.grid_w; ++i) {
+        const int cl = j * g.grid_w + i, ci2 = c0 + cl;
+        int thr = cells[ci2].thr;
+        int tdet = -1;   // threshold of the last detect() call; -1 = none (trials <= 0)
+        for (int trial = 0; trial < trials; ++trial) {
+          tdet = thr;
+          const int nd = ssuf[cl][min(max(thr, 0), 256)];
+          if (prev_prev_thr == thr) { thr = (thr + prev_prev_thr) / 2; break; }
+          prev_prev_thr = prev_thr;
+          prev_thr = thr;
+          if (nd < g.min_inner) {
+            if (thr <= g.fast_min) break;
+            --thr;
+            if (nd < g.min_outer) {
+              if (thr <= g.fast_min) break;
+              --thr;
+              continue;
+            }
+          } else if (nd > g.max_inner) {
+            if (thr >= g.fast_max) break;
+            ++thr;
+            if (nd > g.max_outer) {
+              if (thr >= g.fast_max) break;
+              ++thr;
+              continue;
+            }
+          }
+          break;
+        }
+        cells[ci2].thr = thr;
+        thr_detect[ci2] = tdet;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -244,6 +275,7 @@ struct svs_fast {
   int* h_pinned = nullptr;   // cell_off + cells + xy staging
   int h_pinned_ints = 0;
   bool has_image = false;
+  int last_total = 0, last_ncells = 0;   // result of the last detect call, still on the device (d_xy, d_cell_off)
 };
 
 #define FCK(call)                                                       \
@@ -254,6 +286,13 @@ struct svs_fast {
       return SVS_ERR_CUDA;                                              \
     }                                                                   \
   } while (0)
+
+namespace svs {
+// keypoints of the last detect call where they lie on the device: xy [n][2], cell_off [ncells + 1] (internal.cuh)
+void fast_device_results(svs_fast* f, const int** d_xy, const int** d_cell_off, int* ncells, int* n, int* device) {
+  *d_xy = f->d_xy; *d_cell_off = f->d_cell_off; *ncells = f->last_ncells; *n = f->last_total; *device = f->device;
+}
+}  // namespace svs
 
 extern "C" {
 
@@ -338,6 +377,7 @@ static int run_detect(svs_fast* h, svs_fast_cell* cells, int ncells, const svs_f
   }
   if (gp) {
     if (gp->grid_w * gp->grid_h != ncells) { h->err = "grid size does not match the cell count"; return SVS_ERR_INVALID; }
+    if (gp->grid_w < 1 || gp->grid_w > kSelCells) { h->err = "grid wider than 32 cells"; return SVS_ERR_UNSUPPORTED; }
     t0 = std::min(t0, gp->fast_min);
   }
   t0 = std::max(t0, 0);
@@ -356,7 +396,7 @@ static int run_detect(svs_fast* h, svs_fast_cell* cells, int ncells, const svs_f
   }
   if (gp) {
     GridParams g{gp->grid_w, gp->grid_h, gp->fast_min, gp->fast_max, gp->min_inner, gp->min_outer, gp->max_inner, gp->max_outer};
-    k_fast_select<<<1, 64, 0, h->stream>>>(h->d_cells, h->d_hist, g, trials, h->d_thr_detect);
+    k_fast_select<<<1, kSelCells * 32, 0, h->stream>>>(h->d_cells, h->d_hist, g, trials, h->d_thr_detect);
   }
   const int rows = std::max(max_ih, 1);
   const dim3 wgrid((rows * 32 + 255) / 256, ncells);
@@ -370,6 +410,7 @@ static int run_detect(svs_fast* h, svs_fast_cell* cells, int ncells, const svs_f
   if (write_back_thr) FCK(cudaMemcpyAsync(hc, h->d_cells, sizeof(CellDev) * ncells, cudaMemcpyDeviceToHost, h->stream));
   FCK(cudaStreamSynchronize(h->stream));
   const int total = h->h_pinned[ncells];
+  h->last_total = std::min(total, lim); h->last_ncells = ncells;
   memcpy(cell_off, h->h_pinned, sizeof(int) * (ncells + 1));
   if (write_back_thr)
     for (int c = 0; c < ncells; ++c) cells[c].thr = hc[c].thr;

@@ -102,6 +102,32 @@ __global__ void k_gather_poses(MapDev m, const int* __restrict__ window, int P, 
   out[i] = m.pose[7 * (size_t)window[i / 7] + i % 7];
 }
 
+// restoreDataFromG2o (slam_graph.cpp:1037-1058) without leaving the device: vertex and point estimates of the
+// optimised window go back into the map (xyz_anchor = invert_depth(psi), maths_utils.h:66-69)
+__global__ void k_absorb(double* __restrict__ map_pose, double* __restrict__ map_xyz, const double* __restrict__ pose0,
+                         const double* __restrict__ pose1, const double* __restrict__ psi0, const double* __restrict__ psi1,
+                         const int* __restrict__ lm_user, const int* __restrict__ cur, const int* __restrict__ window,
+                         const int* __restrict__ active, int P, int L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = *cur;
+  const double* pose = c ? pose1 : pose0;
+  const double* psi = c ? psi1 : psi0;
+  if (i < 7 * P) map_pose[7 * (size_t)window[i / 7] + i % 7] = pose[i];
+  if (i < L) {
+    const double a = psi[3 * (size_t)i], b = psi[3 * (size_t)i + 1], w = psi[3 * (size_t)i + 2];
+    double* x = map_xyz + 3 * (size_t)active[lm_user[i]];
+    x[0] = a / w; x[1] = b / w; x[2] = 1. / w;
+  }
+}
+
+// scatter of n records of `width` doubles into rows `index[i]` of a table
+__global__ void k_scatter_rows(double* __restrict__ table, const int* __restrict__ index, const double* __restrict__ rows, int n,
+                               int width) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  table[(size_t)width * index[i / width] + i % width] = rows[i];
+}
+
 }  // namespace
 
 struct svs_map {
@@ -116,6 +142,8 @@ struct svs_map {
   std::vector<double> h_pose, h_psi;
   const double* d_oi_last = nullptr;   // [E][3] observations, [E][3] weights of the last assembly
   int last_E = 0;
+  const int* d_win_last = nullptr; const int* d_act_last = nullptr; int last_P = 0, last_L = 0;   // the last assembled window
+  char* d_upd = nullptr; size_t upd_cap = 0;   // staging of svs_map_update_*
 };
 
 #define GCK(call)                                                       \
@@ -151,7 +179,7 @@ void svs_map_destroy(svs_map* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_map); cudaFree(h->d_work);
+  cudaFree(h->d_map); cudaFree(h->d_work); cudaFree(h->d_upd);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -209,15 +237,65 @@ int svs_map_set(svs_map* h, int V, const double* T_me_from_world, int Np, const 
   return SVS_OK;
 }
 
+// n records of `width` doubles go to the device in ONE copy and are scattered there
+static int map_scatter(svs_map* h, double* table, int rows_in_table, int n, const int* index, const double* rows, int width,
+                       const char* what) {
+  for (int i = 0; i < n; ++i)
+    if (index[i] < 0 || index[i] >= rows_in_table) { h->err = std::string(what) + " index out of range"; return SVS_ERR_INVALID; }
+  if (n == 0) return SVS_OK;
+  cudaSetDevice(h->device);
+  const size_t ib = al256(sizeof(int) * (size_t)n), rb = sizeof(double) * (size_t)n * width;
+  if (ib + rb > h->upd_cap) {
+    GCK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_upd); h->d_upd = nullptr; h->upd_cap = 0;
+    GCK(cudaMalloc(&h->d_upd, 2 * (ib + rb)));
+    h->upd_cap = 2 * (ib + rb);
+  }
+  GCK(cudaMemcpyAsync(h->d_upd, index, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  GCK(cudaMemcpyAsync(h->d_upd + ib, rows, rb, cudaMemcpyHostToDevice, h->stream));
+  k_scatter_rows<<<(n * width + 255) / 256, 256, 0, h->stream>>>(table, reinterpret_cast<const int*>(h->d_upd),
+                                                                 reinterpret_cast<const double*>(h->d_upd + ib), n, width);
+  GCK(cudaGetLastError());
+  GCK(cudaStreamSynchronize(h->stream));   // the caller's arrays may go away
+  return SVS_OK;
+}
+
 int svs_map_update_poses(svs_map* h, int n, const int* vertex, const double* T_me_from_world) {
   if (!h || n < 0 || (n && (!vertex || !T_me_from_world)) || !h->d_map) return SVS_ERR_INVALID;
+  return map_scatter(h, const_cast<double*>(h->m.pose), h->V, n, vertex, T_me_from_world, 7, "vertex");
+}
+
+int svs_map_update_points(svs_map* h, int n, const int* point, const double* xyz_anchor) {
+  if (!h || n < 0 || (n && (!point || !xyz_anchor)) || !h->d_map) return SVS_ERR_INVALID;
+  return map_scatter(h, const_cast<double*>(h->m.xyz), h->Np, n, point, xyz_anchor, 3, "point");
+}
+
+int svs_map_get(svs_map* h, double* T_me_from_world, double* xyz_anchor) {
+  if (!h || !h->d_map) return SVS_ERR_INVALID;
   cudaSetDevice(h->device);
-  for (int i = 0; i < n; ++i) {
-    if (vertex[i] < 0 || vertex[i] >= h->V) { h->err = "vertex outside [0, V)"; return SVS_ERR_INVALID; }
-    GCK(cudaMemcpyAsync(const_cast<double*>(h->m.pose) + 7 * (size_t)vertex[i], T_me_from_world + 7 * (size_t)i, sizeof(double) * 7,
-                        cudaMemcpyHostToDevice, h->stream));
-  }
+  if (T_me_from_world) GCK(cudaMemcpyAsync(T_me_from_world, h->m.pose, sizeof(double) * 7 * (size_t)h->V, cudaMemcpyDeviceToHost, h->stream));
+  if (xyz_anchor && h->Np) GCK(cudaMemcpyAsync(xyz_anchor, h->m.xyz, sizeof(double) * 3 * (size_t)h->Np, cudaMemcpyDeviceToHost, h->stream));
   GCK(cudaStreamSynchronize(h->stream));
+  return SVS_OK;
+}
+
+// SlamGraph::restoreDataFromG2o (slam_graph.cpp:1037-1058): the optimised window of `ba` (loaded with
+// svs_ba_set_problem_from_map from THIS map) goes back into the map, device to device
+int svs_map_absorb(svs_map* h, svs_ba* ba) {
+  if (!h || !ba || !h->d_map || !h->d_win_last) return SVS_ERR_INVALID;
+  if (svs::ba_device(ba) != h->device) { h->err = "map and bundle adjuster live on different devices"; return SVS_ERR_INVALID; }
+  const double* const* pose; const double* const* psi; const int* lm_user; const int* cur; cudaStream_t st; int P, L;
+  if (svs::ba_state_on_device(ba, &pose, &psi, &lm_user, &cur, &st, &P, &L) != SVS_OK || P != h->last_P || L != h->last_L) {
+    h->err = "the bundle adjuster does not hold the window this map assembled last";
+    return SVS_ERR_STATE;
+  }
+  cudaSetDevice(h->device);
+  GCK(cudaStreamSynchronize(h->stream));
+  const int n = std::max(7 * P, L);
+  k_absorb<<<(n + 255) / 256, 256, 0, st>>>(const_cast<double*>(h->m.pose), const_cast<double*>(h->m.xyz), pose[0], pose[1], psi[0], psi[1],
+                                            lm_user, cur, h->d_win_last, h->d_act_last, P, L);
+  GCK(cudaGetLastError());
+  GCK(cudaStreamSynchronize(st));
   return SVS_OK;
 }
 
@@ -294,6 +372,7 @@ int svs_ba_set_problem_from_map(svs_ba* ba, svs_map* h, int P, const int* window
   GCK(cudaStreamSynchronize(h->stream));
   if (num_edges) *num_edges = E;
   h->d_oi_last = d_oi; h->last_E = E;
+  h->d_win_last = d_win; h->d_act_last = d_act; h->last_P = P; h->last_L = L;
   const int rc = svs::ba_set_problem_device_obs(ba, P, h->h_pose.data(), fixed, L, h->h_psi.data(), E, h->h_ep.data(), h->h_es.data(),
                                                 h->h_ea.data(), d_oi, C, c_i, c_j, c_T, c_Lambda, cam);
   if (rc != SVS_OK) h->err = std::string("svs_ba_set_problem: ") + svs_last_error(ba);

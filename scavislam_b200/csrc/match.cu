@@ -422,6 +422,42 @@ int svs_matcher_set_features(svs_matcher * h, int level, const int* xy, const in
   return SVS_OK;
 }
 
+// FAST corners handed over on the device (FastGrid::detect fills the quadtree the matcher queries,
+// fast_grid.cpp:75-80: content = index of the corner inside its cell): no trip through host memory.
+__global__ void k_kp_from_fast(const int* __restrict__ xy, const int* __restrict__ cell_off, int ncells, int n,
+                               int* __restrict__ kp_xy, int* __restrict__ kp_content) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = 0;
+  while (c + 1 < ncells && cell_off[c + 1] <= i) ++c;
+  kp_xy[2 * i] = xy[2 * i]; kp_xy[2 * i + 1] = xy[2 * i + 1];
+  kp_content[i] = i - cell_off[c];
+}
+
+int svs_matcher_set_features_from_fast(svs_matcher * h, int level, svs_fast* fast) {
+  if (!h || !fast || level < 0 || level >= h->nlevels) return SVS_ERR_INVALID;
+  const int* d_xy; const int* d_off; int ncells, n, dev;
+  svs::fast_device_results(fast, &d_xy, &d_off, &ncells, &n, &dev);
+  if (dev != h->device) { h->err = "FAST handle lives on another device"; return SVS_ERR_INVALID; }
+  if (n < 0 || n > h->max_kp) { h->err = "more keypoints than the matcher was created for"; return SVS_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  const int nb = h->bw[level] * h->bh[level];
+  h->nkp[level] = n;
+  MCK(cudaMemsetAsync(h->d_bucket_tmp[level], 0, sizeof(int) * 2 * nb, h->stream));
+  if (n) {
+    // the detect call synchronised the FAST handle's stream before it returned: its results are complete
+    k_kp_from_fast<<<(n + 255) / 256, 256, 0, h->stream>>>(d_xy, d_off, ncells, n, h->d_kp_xy[level], h->d_kp_content[level]);
+    k_bucket_count<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_kp_xy[level], n, h->bw[level], h->d_bucket_tmp[level]);
+  }
+  k_bucket_scan<<<1, 32, 0, h->stream>>>(h->d_bucket_tmp[level], nb, h->d_bucket_ptr[level], h->d_bucket_tmp[level] + nb);
+  if (n)
+    k_bucket_fill<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_kp_xy[level], n, h->bw[level], h->d_bucket_tmp[level] + nb,
+                                                          h->d_bucket_item[level]);
+  MCK(cudaGetLastError());
+  MCK(cudaStreamSynchronize(h->stream));   // the FAST handle may detect again
+  return SVS_OK;
+}
+
 int svs_match(svs_matcher * h, const double T_cur_from_actkey[7], const double T_actkey_from_w[7],
               const svs_match_point* pts, int n, int search_radius, int thr_mean, int thr_std, svs_match_result* out) {
   if (!h || !T_cur_from_actkey || !T_actkey_from_w || n < 0 || n > h->max_pts || (n && (!pts || !out)) || search_radius < 0)

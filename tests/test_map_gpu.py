@@ -62,3 +62,36 @@ def test_pose_updates_and_invalid_windows(svs, oracle):
     with pytest.raises(svs.SvsError):                             # the same vertex twice
         dm.set_problem(ba, np.concatenate([win, win[:1]]), act, pb.cam)
     dm.close(); ba.close()
+
+
+def test_optimised_window_is_absorbed_on_the_device(svs, oracle):
+    """restoreDataFromG2o (slam_graph.cpp:1037-1058) device to device: after optimize() the window's vertex poses and
+    xyz_anchor = invert_depth(psi) of its points are in the map, everything outside the window is untouched; the
+    next assembly starts from the optimised state.  svs_map_update_points is the host-side way in."""
+    pb = synth.make_window(30, 3000, seed=6)
+    m, win, act = synth_graph.make_map(pb, seed=6)
+    dm, ba = svs.DeviceMap(), svs.BundleAdjuster()
+    dm.set(m["poses"], m["point_anchor"], m["xyz_anchor"], m["vis_ptr"], m["vis_pose"], m["feat_center"], m["feat_level"])
+    T0, x0 = dm.get()
+    np.testing.assert_array_equal(T0, m["poses"]); np.testing.assert_array_equal(x0, m["xyz_anchor"])
+    dm.set_problem(ba, win, act, pb.cam, c_i=pb.c_i, c_j=pb.c_j, c_T=pb.c_T, c_Lambda=pb.c_Lambda)
+    ba.optimize(3)
+    poses, psi = ba.poses(), ba.points()
+    dm.absorb(ba)
+    T1, x1 = dm.get()
+    np.testing.assert_array_equal(T1[win], poses)
+    xyz = np.stack([psi[:, 0] / psi[:, 2], psi[:, 1] / psi[:, 2], 1.0 / psi[:, 2]], -1)
+    np.testing.assert_array_equal(x1[act], xyz)
+    out_v = np.setdiff1d(np.arange(len(T0)), win)
+    out_p = np.setdiff1d(np.arange(len(x0)), act)
+    np.testing.assert_array_equal(T1[out_v], T0[out_v]); np.testing.assert_array_equal(x1[out_p], x0[out_p])
+    assert np.abs(T1[win] - T0[win]).max() > 0
+    # the next assembly of the same window starts where the optimiser stopped
+    dm.set_problem(ba, win, act, pb.cam, c_i=pb.c_i, c_j=pb.c_j, c_T=pb.c_T, c_Lambda=pb.c_Lambda)
+    np.testing.assert_array_equal(ba.poses(), poses)
+    np.testing.assert_allclose(ba.points(), psi, rtol=1e-14)
+    # host-side point write-back
+    some = np.asarray(act[:5])
+    dm.update_points(some, m["xyz_anchor"][some] + 0.25)
+    np.testing.assert_array_equal(dm.get()[1][some], m["xyz_anchor"][some] + 0.25)
+    dm.close(); ba.close()

@@ -161,3 +161,32 @@ def test_empty_inputs(svs, oracle):
     with pytest.raises(svs.SvsError):
         m.set_features(0, np.array([[700, 10]], np.int32), np.array([0], np.int32))
     m.close()
+
+
+def test_features_handed_over_on_the_device(svs, oracle):
+    """FAST corners taken from the detector's device buffers (svs_matcher_set_features_from_fast) give the same
+    matches, bit for bit, as the corners copied through the host with their per-cell ordinals."""
+    seq = si.sequence(2)
+    levels, cams = _levels()
+    kf_pyr = fi.uint8_pyramid(seq[0]["img"], NLV)
+    cur_pyr = fi.uint8_pyramid(seq[1]["img"], NLV)
+    pts = _points(oracle, kf_pyr, seq[0]["disp"], cams)
+    T_cur = oracle.se3_exp(np.array([0.001, 0.0, -0.02, 0.0, -0.0035, 0.0]))
+    res = []
+    for on_device in (False, True):
+        m = svs.GuidedMatcher(levels)
+        m.set_keyframe(0, I7, kf_pyr)
+        m.set_current(cur_pyr, seq[1]["disp"])
+        for l in range(NLV):
+            g = svs.FastGrid(640 >> l, 480 >> l, 222 if l == 0 else 55, 74 if l == 0 else 18, 25, 3, 3)
+            g.set_image(cur_pyr[l])
+            xy, off = g.detect_adaptively(5)
+            if on_device:
+                m.set_features_from_fast(l, g)
+            else:
+                m.set_features(l, xy, np.concatenate([np.arange(off[c + 1] - off[c]) for c in range(9)]).astype(np.int32))
+            g.close()
+        res.append(m.match(T_cur, I7, pts, 4, 22, 10))
+        m.close()
+    assert res[0]["matched"].sum() > 0.5 * len(pts)
+    _assert_same(res[1], res[0])
