@@ -39,24 +39,25 @@ namespace cg = cooperative_groups;
 
 namespace svs {
 
-constexpr int kSolveThreads = 256;               // 8 warps; warp w issues from scheduler w % 4
-// Roles (factor_range).  Nothing but the chain warp ever runs on scheduler 0 (warp 4 idles through the
+constexpr int kSolveThreads = 384;               // 12 warps; warp w issues from scheduler w % 4
+// Roles (factor_range).  Nothing but the chain warp ever runs on scheduler 0 (warps 4 and 8 idle through the
 // factorisation); what bounds the helpers is the number of instructions their schedulers must issue per column
 // (ncu: with sixteen resident warps that all walked the column loop, 3 300 warp-instructions per column on three
-// schedulers), so there are exactly as many helper warps as the work of a SLAM-shaped column fills.
+// schedulers), so there are exactly as many helper warps as the work of a SLAM-shaped column fills.  Measured
+// alternatives (C2 / C5 solve time per 10 iterations): this layout 1.64 / 7.76 ms; three unit warps with the four
+// left-over units of a window column on the urgent warp 1.65 / 7.88 ms; with the left-over units on the second row
+// warp 1.93 / 9.19 ms (its N rows and right-hand side then finish too late for the next column).
 constexpr int kChainWarp = 0;
-constexpr int kUnitWarps = 3;                    // warps 1, 2, 3 (one per scheduler): quarter-block units of the trailing update
-constexpr int kRowWarps = 2;                     // warps 5, 6: rows of the column, N rows, right-hand side; warp 6 (whose lanes
-                                                 // are idle while warp 5 scales a window column's 31 rows) also takes the units
-                                                 // the unit warps have no lanes left for (a window column has 100, they have 96)
+constexpr int kUnitWarps = 4;                    // warps 1, 2, 3, 5: quarter-block units of the trailing update
+constexpr int kRowWarps = 2;                     // warps 6, 9: rows of the column, N rows, right-hand side
 constexpr int kUrgentWarp = 7;                   // the two pair updates the chain reads next
-__device__ __forceinline__ int unit_warp_index(int w) { return (w >= 1 && w <= 3) ? w - 1 : -1; }
-__device__ __forceinline__ int row_warp_index(int w) { return w == 5 ? 0 : (w == 6 ? 1 : -1); }
+__device__ __forceinline__ int unit_warp_index(int w) { return w == 1 ? 0 : (w == 2 ? 1 : (w == 3 ? 2 : (w == 5 ? 3 : -1))); }
+__device__ __forceinline__ int row_warp_index(int w) { return w == 6 ? 0 : (w == 9 ? 1 : -1); }
 constexpr int kUnitThreads = kUnitWarps * 32, kRowThreads = kRowWarps * 32;
 constexpr int kPubAll = 32 * (1 + kUnitWarps + kRowWarps + 1);   // chain + unit + row + urgent warps
 constexpr int kRowsAll = 32 * (kUnitWarps + kRowWarps + 1);      // unit warps wait, row warps produce and wait, urgent produces
 constexpr int kRefillAll = 32 * (kUnitWarps + kRowWarps);       // the urgent warp only touches the next two columns: resident
-constexpr int kUnitStride = kUnitThreads + 32;                 // the second row warp takes the units beyond the unit warps' lanes
+constexpr int kUnitStride = kUnitThreads;
 constexpr int kBarPub = 1;    // chain arrives, helpers + urgent warp sync: column j's diagonal factor is published
 constexpr int kBarUrg = 2;    // urgent warp arrives, chain syncs: the chain's next inputs are up to date
 constexpr int kBarH = 3;      // all rows of the column are scaled (row + urgent warps produce, unit + row warps wait)
@@ -460,20 +461,6 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       PHL(1);
       bar_sync(kBarH, kRowsAll);
       if (T.prof && *reinterpret_cast<volatile int*>(&S.fail[T.slot][j & 1]) >= 0) PHL(2);
-      if (rt >= 32) {   // second row warp: the units beyond the unit warps' lanes (index space 96..127 mod 128)
-        const int link = (j + 1 < T.j1 && nb > 0 && row_idx[base + 1] == j + 1) ? 1 : 0;
-        const int u0 = upd_ptr[j] + link, nunits = (upd_ptr[j + 1] - u0) * 4;
-        int dU1 = -1, dU2 = -1;
-        if (j + 2 < T.j1 && link < nb && row_idx[base + 1 + link] == j + 2) {
-          dU1 = col_ptr[j + 2];
-          if (link) dU2 = col_ptr[j + 1] + 1;
-        }
-        for (int u = kUnitThreads + (rt - 32); u < nunits; u += kUnitStride) {
-          const int ab = __ldg(d.upd_ab + u0 + (u >> 2)), dst = __ldg(d.upd_dst + u0 + (u >> 2));
-          if (dst == dU1 || dst == dU2) continue;
-          quarter_unit(d, T, base, hi, u, ab, dst);
-        }
-      }
       // ---- N_ij = L_ij L_jj^-1 (and z_j = y_j L_jj^-1) for the backward pass, stored transposed in row-major order;
       //      nothing in the forward pass waits for it
       for (int row = rt; row < nrows; row += kRowThreads) {
@@ -560,18 +547,40 @@ __device__ void scatter_rows(const BaDev& d, int lo, int hi, int c0, int c1, int
       if (warp == 0) {
         const double* b = sm_solve + buf_off + (k & 1) * half * 36;
         const int rlo = sChunk[k + 1], b0 = rptr[rlo];
-        for (int i = sChunk[k] - 1; i >= rlo; --i) {
-          const int p0 = rptr[i], nb = rptr[i + 1] - p0;
+        // Software pipeline: everything of a row that does not depend on x -- its block range, this lane's first
+        // block (column and the N row) -- is fetched while the previous row is being scattered; what is left on the
+        // chain per row is the read of x_i, six FMAs and the read-modify-write of the target column.
+        int i = sChunk[k] - 1;
+        int p0 = 0, nb = 0, col = -1;
+        double Nt[6] = {0, 0, 0, 0, 0, 0};
+        auto prefetch = [&](int row) {
+          p0 = rptr[row]; nb = rptr[row + 1] - p0; col = -1;
+          if (lane < 30 && g < nb) {
+            col = rcol[p0 + g];
+            load_row6(b + (size_t)(p0 - b0 + g) * 36 + r * 6, Nt);
+          }
+        };
+        if (i >= rlo) prefetch(i);
+        for (; i >= rlo; --i) {
+          const int cp0 = p0, cnb = nb, ccol = col;
+          double cN[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) cN[q] = Nt[q];
           double xi[6];
           load_row6(xv + 6 * i, xi);   // final: every row above has been scattered (and the warp synchronised)
-          if (lane < 30)
-            for (int a = g; a < nb; a += 5) {
-              const int col = rcol[p0 + a];
-              if (col < c0 || col >= c1) continue;   // a separator row also holds blocks of the other branch
-              double Nt[6];
-              load_row6(b + (size_t)(p0 - b0 + a) * 36 + r * 6, Nt);
-              const double sdot = (Nt[0] * xi[0] + Nt[1] * xi[1] + Nt[2] * xi[2]) + (Nt[3] * xi[3] + Nt[4] * xi[4] + Nt[5] * xi[5]);
-              xv[6 * col + r] -= sdot;
+          if (i > rlo) prefetch(i - 1);
+          if (ccol >= c0 && ccol < c1) {   // (a separator row also holds blocks of the other branch)
+            const double sdot = (cN[0] * xi[0] + cN[1] * xi[1] + cN[2] * xi[2]) + (cN[3] * xi[3] + cN[4] * xi[4] + cN[5] * xi[5]);
+            xv[6 * ccol + r] -= sdot;
+          }
+          if (lane < 30)   // rows with more than five blocks: the farther columns, not needed by the next rows
+            for (int a = g + 5; a < cnb; a += 5) {
+              const int col2 = rcol[cp0 + a];
+              if (col2 < c0 || col2 >= c1) continue;
+              double N2[6];
+              load_row6(b + (size_t)(cp0 - b0 + a) * 36 + r * 6, N2);
+              const double sdot = (N2[0] * xi[0] + N2[1] * xi[1] + N2[2] * xi[2]) + (N2[3] * xi[3] + N2[4] * xi[4] + N2[5] * xi[5]);
+              xv[6 * col2 + r] -= sdot;
             }
           __syncwarp();
         }
