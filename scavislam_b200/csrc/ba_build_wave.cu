@@ -320,7 +320,7 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks, int prof) {
   }
   PBW(6);
   if (prof && lane == 0)
-    for (int i = 0; i < 7; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(d.dbg) + 36 + i, (unsigned long long)pacc[i]);
+    for (int i = 0; i < 7; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(d.dbg) + 48 + i, (unsigned long long)pacc[i]);
 #undef PBW
 }
 
@@ -620,7 +620,7 @@ k_build_wave2(BaDev d, int robust, double delta, int n_task_blocks, int prof) {
   }
   PBW(6);
   if (prof && lane == 0)
-    for (int i = 0; i < 7; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(d.dbg) + 36 + i, (unsigned long long)pacc[i]);
+    for (int i = 0; i < 7; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(d.dbg) + 48 + i, (unsigned long long)pacc[i]);
 #undef PBW
 }
 

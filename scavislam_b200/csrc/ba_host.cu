@@ -288,18 +288,35 @@ void analyse(int P, const std::vector<std::vector<int>>& adj_in, bool natural, c
 // Returns the number of branches (1 when the graph is not banded enough).
 int choose_branches(int P, const std::vector<std::vector<int>>& adj, std::vector<int>& order,
                     std::vector<int>& branch_ptr) {
-  int w = 0;
-  for (int i = 0; i < P; ++i)
-    for (int j : adj[i]) w = std::max(w, std::abs(i - j));
   order.clear();
   branch_ptr.clear();
+  if (P < 8) return 1;
+  // band width of the window WITHOUT its few long-range edges (loop closures, prepareForOptimization(root, loop_id)):
+  // the smallest w that leaves at most kMaxLong edges longer than w
+  constexpr int kMaxLong = 24;
+  std::vector<int> hist(P, 0);
+  for (int i = 0; i < P; ++i)
+    for (int j : adj[i])
+      if (j > i) hist[j - i]++;
+  int w = P - 1, longer = 0;
+  while (w > 0 && longer + hist[w] <= kMaxLong) { longer += hist[w]; --w; }
   if (w == 0 || (P - w) / 2 < 3 * w) return 1;
   const int left = (P - w) / 2;             // poses [0, left) | separator [left, left + w) | [left + w, P)
+  auto side = [&](int p) { return p < left ? 0 : (p >= left + w ? 1 : 2); };
+  // a long edge between the two ends would couple the concurrent eliminations: one of its poses joins the separator
+  std::vector<char> in_sep(P, 0);
+  for (int i = 0; i < P; ++i)
+    for (int j : adj[i])
+      if (j - i > w && side(i) + side(j) == 1 && !in_sep[i] && !in_sep[j]) in_sep[j] = 1;
   branch_ptr.push_back(0);
-  for (int i = 0; i < left; ++i) order.push_back(i);
+  for (int i = 0; i < left; ++i)
+    if (!in_sep[i]) order.push_back(i);
   branch_ptr.push_back((int)order.size());
-  for (int i = P - 1; i >= left + w; --i) order.push_back(i);
+  for (int i = P - 1; i >= left + w; --i)
+    if (!in_sep[i]) order.push_back(i);
   branch_ptr.push_back((int)order.size());
+  for (int i = 0; i < P; ++i)
+    if (in_sep[i]) order.push_back(i);
   for (int i = left; i < left + w; ++i) order.push_back(i);
   return 2;
 }
@@ -337,7 +354,7 @@ int svs_ba_create(const svs_ba_opts* opts, svs_ba** out) {
   h->flags = opts ? opts->flags : 0;
   {   // threads of the per-landmark host loops of set_problem: a few, never more than half the machine
     const int hw = (int)std::thread::hardware_concurrency();
-    h->host_threads = std::max(1, std::min(8, hw / 2));
+    h->host_threads = std::max(1, std::min(4, hw / 2));
   }
   if (const char* ht = getenv("SVS_HOST_THREADS")) h->host_threads = std::max(1, atoi(ht));
   int dev = opts ? opts->device : -1;
@@ -606,21 +623,20 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   {
     auto& A = h->w_adj;
     A.assign((size_t)P * P, 0);
-    // (concurrent writers only ever store 1 into a byte: benign)
-#pragma omp parallel num_threads(nthr) if (L > 4096)
-    {
-      std::vector<int> ps;   // a track has no length limit (slam_graph.cpp:1001-1027)
-#pragma omp for schedule(static)
-      for (int l = 0; l < L; ++l) {
-        if (l_anchor[l] < 0) continue;
-        ps.clear();
-        ps.push_back(l_anchor[l]);
-        for (int k = eptr[l] + l_self[l]; k < eptr[l + 1]; ++k) ps.push_back(e_pose[eord[k]]);
-        const int n = (int)ps.size();
-        for (int x = 0; x < n; ++x)
-          for (int y = x + 1; y < n; ++y) { A[(size_t)ps[x] * P + ps[y]] = 1; A[(size_t)ps[y] * P + ps[x]] = 1; }
+    // one representative per task (its landmarks share one slot list) + the landmarks outside the task lists; a
+    // track has no length limit (slam_graph.cpp:1001-1027)
+    auto mark = [&](int li) {   // internal landmark index
+      const int b = lm_eptr[li] + lm_self[li], en = lm_eptr[li + 1], a = lm_anchor[li];
+      for (int x = b; x < en; ++x) {
+        const int px = ie_pose[x];
+        A[(size_t)a * P + px] = 1; A[(size_t)px * P + a] = 1;
+        for (int y = x + 1; y < en; ++y) { const int py = ie_pose[y]; A[(size_t)px * P + py] = 1; A[(size_t)py * P + px] = 1; }
       }
-    }
+    };
+    for (int li : task_lm) mark(li);
+    for (int li : gen_lm)
+      if (lm_eptr[li + 1] > lm_eptr[li]) mark(li);
+    for (int li : long_lm) mark(li);
     for (int c = 0; c < C; ++c) { A[(size_t)c_i[c] * P + c_j[c]] = 1; A[(size_t)c_j[c] * P + c_i[c]] = 1; }
     for (size_t q = 0; q + 1 < h->extra_pairs.size(); q += 2) {   // svs_ba_set_structure
       const int a = h->extra_pairs[q], b = h->extra_pairs[q + 1];
@@ -902,11 +918,11 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     st->launches = launches;
   }
   if (getenv("SVS_BUILD_TIMING")) {
-    long long dbg[48];
+    long long dbg[64];
     cudaMemcpy(dbg, d.dbg, sizeof dbg, cudaMemcpyDeviceToHost);
     fprintf(stderr, "k_build_wave warp-cycles summed over warps and launches: setup %lld linearise %lld landmark-sums %lld inverse+Y+spill %lld "
-            "schur+direct %lld gradients %lld flush %lld\n", dbg[36], dbg[37], dbg[38], dbg[39], dbg[40], dbg[41], dbg[42]);
-    cudaMemset(d.dbg + 36, 0, 8 * sizeof(long long));
+            "schur+direct %lld gradients %lld flush %lld\n", dbg[48], dbg[49], dbg[50], dbg[51], dbg[52], dbg[53], dbg[54]);
+    cudaMemset(d.dbg + 48, 0, 8 * sizeof(long long));
   }
   if (getenv("SVS_SOLVE_TIMING")) {
     long long dbg[64];
@@ -916,10 +932,10 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     for (int g = 0; g < 2; ++g) {
       fprintf(stderr, "  CTA %d:", g);
       for (int i = 0; i < 6; ++i) fprintf(stderr, " %lld", dbg[g * 6 + i]);
-      const long long* q = dbg + 12 + 12 * g;
+      const long long* q = dbg + 12 + 16 * g;
       fprintf(stderr, "\n     chain: hand-over %lld chol %lld wait-urgent+load %lld publish %lld | unit thread 0: wait-factor %lld wait-rows %lld "
-              "units %lld | row thread 0: wait-factor %lld rows %lld wait-rows %lld N+rhs %lld\n", q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[8],
-              q[9], q[10], q[11]);
+              "units %lld | row thread 0: wait-factor %lld rows %lld wait-rows %lld N+rhs %lld | urgent: wait-factor %lld rows %lld units %lld\n",
+              q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[8], q[9], q[10], q[11], q[12], q[13], q[14]);
     }
   }
   return h->h_ctl->iter;

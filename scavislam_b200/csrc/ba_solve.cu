@@ -340,6 +340,8 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
 #undef PCH
   } else if (warp == kUrgentWarp) {
     // ------------------------------------------------------------------ the urgent warp
+    long long pu[4] = {0, 0, 0, 0}, ptu = T.prof ? clock64() : 0;
+#define PUR(i) do { if (T.prof) { const long long c_ = clock64(); pu[i] += c_ - ptu; ptu = c_; } } while (0)
     for (int j = T.j0; j < T.j1; ++j) {
       const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
       const bool want = j + 2 < T.j1;   // the chain reads D_{j+2} and S_{j+2,j+1} next
@@ -348,7 +350,9 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       int i2 = i1 + 1;                                                    // index of row j+2, if present
       if (!(i2 < nb && row_idx[base + 1 + i2] == j + 2)) i2 = -1;
       bar_sync(kBarPub, kPubAll);
-      if (S.fail[T.slot][j & 1]) break;
+      const int ufail = S.fail[T.slot][j & 1];
+      if (T.prof && ufail >= 0) PUR(0);
+      if (ufail) break;
       // the first two blocks of the column are scaled here (the general helpers take the others)
       if (lane < 6 * min(nb, 2)) {
         const double2* l2 = reinterpret_cast<const double2*>(S.sL[T.slot][j & 1]);
@@ -361,6 +365,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
         double2* d2 = reinterpret_cast<double2*>(src);
         d2[0] = make_double2(o[0], o[1]); d2[1] = make_double2(o[2], o[3]); d2[2] = make_double2(o[4], o[5]);
       }
+      PUR(1);
       bar_arrive(kBarH, kRowsAll);   // (orders the stores above before the trailing update of the unit warps)
       if (want && i2 >= 0 && lane < 8 && (lane < 4 || i1 >= 0)) {
         // lanes 0-3: D_{j+2} -= L2 L2^T, lanes 4-7: S_{j+2,j+1} -= L2 L1^T, a quarter block each
@@ -388,8 +393,12 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
 #pragma unroll
           for (int cc = 0; cc < 3; ++cc) D[rr * 6 + cc] = o[rr * 3 + cc];
       }
+      PUR(2);
       bar_arrive(kBarUrg, 64);
     }
+    if (T.prof && lane == 0)
+      for (int i = 0; i < 3; ++i) T.prof[12 + i] = pu[i];
+#undef PUR
   } else if (unit_warp_index(warp) >= 0) {
     // ------------------------------------------------------------------ unit warps: the trailing update
     const int ut = unit_warp_index(warp) * 32 + lane;
@@ -670,7 +679,7 @@ k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
   Team br;
   br.ring_off = ring_off; br.org = 0; br.mask = (unsigned)cap - 1u; br.cap = cap; br.prefilled = 0;
   br.j0 = my0; br.j1 = my1; br.sep_blk0 = sep_blk0; br.area_off = area_off; br.slot = 0; br.refill_period = refill_branch;
-  br.prof = (prof && d.dbg) ? d.dbg + 12 + 12 * rank : nullptr;   // [.. + 32 + 3): unit phases of helper 0 (rank 0: dbg 44..46, rank 1: 56..58)
+  br.prof = (prof && d.dbg) ? d.dbg + 12 + 16 * rank : nullptr;   // [.. + 32 + 3): unit phases of helper 0 (rank 0: dbg 44..46, rank 1: 56..58)
   factor_range(d, br, S, lambda);
   tk[1] = clock64();
   int failed = sFail[0][0] | sFail[0][1];
