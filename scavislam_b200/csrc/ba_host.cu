@@ -735,7 +735,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     AL(x, 6 * (size_t)P); AL(Nrow, 36 * (size_t)std::max(sy.nblk - P, 1));
     AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
     AL(ctl, 1);
-    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 64);
+    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 160);
 #undef AL
   };
   h->measuring = true;
@@ -751,7 +751,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   d.e_obs = d.e_obs_w; d.e_w = d.e_w_w;
   launch_regroup(d, d_obs_info ? d_obs_info : h->d_raw, h->stream);   // [3][E] internal order <- [E][3] user order
   CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
-  CK(cudaMemsetAsync(d.dbg, 0, 64 * sizeof(long long), h->stream));
+  CK(cudaMemsetAsync(d.dbg, 0, 160 * sizeof(long long), h->stream));
   h->max_col_blocks = sy.max_col_sep; h->max_col_branch = sy.max_col_branch; h->max_row_blocks = sy.max_row;
   d.nbranch = h->nbranch;
   CK(cudaMemsetAsync(d.chi_c, 0, std::max(C, 1) * sizeof(double), h->stream));
@@ -925,6 +925,18 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     cudaMemset(d.dbg + 48, 0, 8 * sizeof(long long));
   }
   if (getenv("SVS_SOLVE_TIMING")) {
+    {
+      long long tr[160];
+      cudaMemcpy(tr, d.dbg, sizeof tr, cudaMemcpyDeviceToHost);
+      const long long* t0 = tr + 12 + 52;
+      fprintf(stderr, "trace (CTA 0, columns 10..25 of its branch; cycles relative to the chain's publish of column 10):\n");
+      const char* nm[5] = {"chain published  ", "chain has U(j-1)  ", "urgent past Pub   ", "urgent arrives U  ", "unit 0 past Pub   "};
+      for (int k = 0; k < 5; ++k) {
+        fprintf(stderr, "  %s", nm[k]);
+        for (int c = 0; c < 16; ++c) fprintf(stderr, " %6lld", t0[k * 16 + c] - t0[0]);
+        fprintf(stderr, "\n");
+      }
+    }
     long long dbg[64];
     cudaMemcpy(dbg, d.dbg, sizeof dbg, cudaMemcpyDeviceToHost);
     fprintf(stderr, "k_solve cycles since setup (branch factored, cluster sync, separators factored, separators solved + sync, "

@@ -151,6 +151,7 @@ struct Team {
   long long* prof;            // nullptr or 16 cycle counters (developer knob SVS_SOLVE_TIMING)
 };
 
+#define TRACE(k, j) do { if (T.prof && T.slot == 0 && (j) - T.j0 >= 10 && (j) - T.j0 < 26 && (threadIdx.x & 31) == 0) T.prof[52 + (k) * 16 + ((j) - T.j0 - 10)] = clock64(); } while (0)
 struct SolveShared {
   int yv_off;                 // right-hand side / solution, 6 doubles per column (offset into the dynamic shared memory)
   int* col_ptr; int* upd_ptr; int* row_idx;
@@ -316,7 +317,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
           load_row6(pB + c * 6, sc);
         }
       }
-      if (T.prof && dnext != 1.2345e-300) PCH(2);
+      if (T.prof && dnext != 1.2345e-300) { PCH(2); TRACE(1, j); }
       if (lane == 0) {   // publish l (21) and rinv (6): 14 independent 16-byte stores by one lane (a per-lane
                          // select of "its" element would be a 27-deep dependent chain on the critical warp)
         double2* sl2 = reinterpret_cast<double2*>(S.sL[T.slot][j & 1]);
@@ -329,6 +330,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
         if (!ok) S.fail[T.slot][j & 1] = 1;
       }
       bar_arrive(kBarPub, kPubAll);
+      TRACE(0, j);
       PCH(3);
       if (!ok) { produced = j - T.j0; break; }
       linked = nlinked;
@@ -351,7 +353,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       if (!(i2 < nb && row_idx[base + 1 + i2] == j + 2)) i2 = -1;
       bar_sync(kBarPub, kPubAll);
       const int ufail = S.fail[T.slot][j & 1];
-      if (T.prof && ufail >= 0) PUR(0);
+      if (T.prof && ufail >= 0) { PUR(0); TRACE(2, j); }
       if (ufail) break;
       // the first two blocks of the column are scaled here (the general helpers take the others)
       if (lane < 6 * min(nb, 2)) {
@@ -394,6 +396,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
           for (int cc = 0; cc < 3; ++cc) D[rr * 6 + cc] = o[rr * 3 + cc];
       }
       PUR(2);
+      TRACE(3, j);
       bar_arrive(kBarUrg, 64);
     }
     if (T.prof && lane == 0)
@@ -420,7 +423,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       if (ut < nunits) e0 = make_int2(__ldg(d.upd_ab + u0 + (ut >> 2)), __ldg(d.upd_dst + u0 + (ut >> 2)));
       bar_sync(kBarPub, kPubAll);   // (also: every helper is done with the previous column)
       const int col_failed = S.fail[T.slot][j & 1];   // (first read behind the barrier: the barrier wait ends here)
-      if (T.prof && col_failed >= 0) PHL(0);
+      if (T.prof && col_failed >= 0) { PHL(0); if (ut == 0) TRACE(4, j); }
       if (col_failed) break;
       bar_sync(kBarH, kRowsAll);    // the column's rows are scaled
       if (T.prof && *reinterpret_cast<volatile int*>(&S.fail[T.slot][j & 1]) >= 0) PHL(1);
