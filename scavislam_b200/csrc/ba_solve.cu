@@ -51,8 +51,8 @@ constexpr int kChainWarp = 0;
 constexpr int kUnitWarps = 4;                    // warps 1, 2, 3, 5: quarter-block units of the trailing update
 constexpr int kRowWarps = 2;                     // warps 6, 9: rows of the column, N rows, right-hand side
 constexpr int kUrgentWarp = 7;                   // the two pair updates the chain reads next
-__device__ __forceinline__ int unit_warp_index(int w) { return w == 1 ? 0 : (w == 2 ? 1 : (w == 3 ? 2 : (w == 5 ? 3 : -1))); }
-__device__ __forceinline__ int row_warp_index(int w) { return w == 6 ? 0 : (w == 9 ? 1 : -1); }
+__device__ __forceinline__ int unit_warp_index(int w) { return (w >= 1 && w <= 4) ? w - 1 : -1; }   // one per scheduler (warp 4 shares the chain's)
+__device__ __forceinline__ int row_warp_index(int w) { return w == 5 ? 0 : (w == 6 ? 1 : -1); }
 constexpr int kUnitThreads = kUnitWarps * 32, kRowThreads = kRowWarps * 32;
 constexpr int kPubAll = 32 * (1 + kUnitWarps + kRowWarps + 1);   // chain + unit + row + urgent warps
 constexpr int kRowsAll = 32 * (kUnitWarps + kRowWarps + 1);      // unit warps wait, row warps produce and wait, urgent produces
@@ -170,19 +170,33 @@ __device__ __forceinline__ int ring_idx(const Team& T, int id) { return T.ring_o
 
 // One quarter-block unit of the trailing update: rows 3h..3h+2, columns 3g..3g+2 of S_ab -= L_a L_b^T
 // (18 16-byte loads, 54 FMAs).  u = 4 * pair + 2 h + g, ab = (a << 16) | b, dst = destination block.
-__device__ __forceinline__ void quarter_unit(const BaDev& d, const Team& T, int base, int hi, int u, int ab, int dst) {
+// The address decode (indices only) is separate from the arithmetic so that the unit warps can do it while the
+// column's rows are still being scaled.
+struct UnitAddr {
+  int la, lb, dd;        // offsets in sm_solve (doubles): 3 rows of L_a, 3 rows of L_b, the 3x3 destination
+  double* dg;            // destination in HBM when the block is not resident (else nullptr)
+};
+__device__ __forceinline__ UnitAddr unit_addr(const BaDev& d, const Team& T, int base, int hi, int u, int ab, int dst) {
   const int h = (u >> 1) & 1, g = u & 1;
-  const double2* La = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + (ab >> 16)) + h * 18);
-  const double2* Lb = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + (ab & 0xffff)) + g * 18);
+  UnitAddr A;
+  A.la = ring_idx(T, base + 1 + (ab >> 16)) + h * 18;
+  A.lb = ring_idx(T, base + 1 + (ab & 0xffff)) + g * 18;
+  const bool far = dst >= hi && dst < T.sep_blk0;   // not resident: read-modify-write in HBM
+  A.dg = far ? d.S + (size_t)dst * 36 + h * 18 + g * 3 : nullptr;
+  A.dd = (dst < hi ? ring_idx(T, dst) : T.area_off + (dst - T.sep_blk0) * 36) + h * 18 + g * 3;
+  return A;
+}
+__device__ __forceinline__ void unit_run(const UnitAddr& A) {
+  const double2* La = reinterpret_cast<const double2*>(sm_solve + A.la);
+  const double2* Lb = reinterpret_cast<const double2*>(sm_solve + A.lb);
   double a[18], b[18], o[9];
 #pragma unroll
   for (int q = 0; q < 9; ++q) { const double2 v = La[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
 #pragma unroll
   for (int q = 0; q < 9; ++q) { const double2 v = Lb[q]; b[2 * q] = v.x; b[2 * q + 1] = v.y; }
-  const bool far = dst >= hi && dst < T.sep_blk0;   // not resident: read-modify-write in HBM
-  double* Dg = d.S + (size_t)dst * 36 + h * 18 + g * 3;
-  double* D = sm_solve + (dst < hi ? ring_idx(T, dst) : T.area_off + (dst - T.sep_blk0) * 36) + h * 18 + g * 3;
-  if (far) {
+  double* Dg = A.dg;
+  double* D = sm_solve + A.dd;
+  if (Dg) {
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
@@ -199,7 +213,7 @@ __device__ __forceinline__ void quarter_unit(const BaDev& d, const Team& T, int 
     for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
       for (int k = 0; k < 6; ++k) o[rr * 3 + cc] = fma(-a[rr * 6 + k], b[cc * 6 + k], o[rr * 3 + cc]);
-  if (far) {
+  if (Dg) {
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
@@ -210,6 +224,9 @@ __device__ __forceinline__ void quarter_unit(const BaDev& d, const Team& T, int 
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) D[rr * 6 + cc] = o[rr * 3 + cc];
   }
+}
+__device__ __forceinline__ void quarter_unit(const BaDev& d, const Team& T, int base, int hi, int u, int ab, int dst) {
+  unit_run(unit_addr(d, T, base, hi, u, ab, dst));
 }
 
 // Every refill_period columns the helpers (unit, row and urgent warps; `rid` in [0, kRefillAll)) reload the ring slots
@@ -408,36 +425,52 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
     int until_refill = T.refill_period;
     long long ph[5] = {0, 0, 0, 0, 0}, pt = T.prof ? clock64() : 0;
 #define PHL(i) do { if (T.prof) { const long long c_ = clock64(); ph[i] += c_ - pt; pt = c_; } } while (0)
-    for (int j = T.j0; j < T.j1; ++j) {
-      const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
-      const int link = (j + 1 < T.j1 && nb > 0 && row_idx[base + 1] == j + 1) ? 1 : 0;
-      const int u0 = upd_ptr[j] + link, nunits = (upd_ptr[j + 1] - u0) * 4;
-      // destinations the urgent warp takes care of (same rule as there)
-      int dU1 = -1, dU2 = -1;
-      if (j + 2 < T.j1 && link < nb && row_idx[base + 1 + link] == j + 2) {   // row j+2 can only sit right after row j+1
-        dU1 = col_ptr[j + 2];
-        if (link) dU2 = col_ptr[j + 1] + 1;
+    // Per column: indices (base, first update, number of units, the urgent warp's destinations) and this thread's
+    // first (ab, dst) pair.  They depend on the structure only, so column j+1's are fetched while column j's rows are
+    // being scaled (the unit warps have nothing else to do between the two barriers), and the first unit's addresses
+    // are decoded there too: behind kBarH only loads, FMAs and stores remain.
+    struct ColIdx { int base, u0, nunits, dU1, dU2; int2 e; };
+    auto column_indices = [&](int j) {
+      ColIdx c;
+      const int nb = col_ptr[j + 1] - col_ptr[j] - 1;
+      c.base = col_ptr[j];
+      const int link = (j + 1 < T.j1 && nb > 0 && row_idx[c.base + 1] == j + 1) ? 1 : 0;
+      c.u0 = upd_ptr[j] + link;
+      c.nunits = (upd_ptr[j + 1] - c.u0) * 4;
+      c.dU1 = c.dU2 = -1;   // destinations the urgent warp takes care of (same rule as there)
+      if (j + 2 < T.j1 && link < nb && row_idx[c.base + 1 + link] == j + 2) {   // row j+2 can only sit right after row j+1
+        c.dU1 = col_ptr[j + 2];
+        if (link) c.dU2 = col_ptr[j + 1] + 1;
       }
-      // this thread's first unit: fetched under the wait for the diagonal factor
-      int2 e0 = make_int2(0, 0);
-      if (ut < nunits) e0 = make_int2(__ldg(d.upd_ab + u0 + (ut >> 2)), __ldg(d.upd_dst + u0 + (ut >> 2)));
+      c.e = make_int2(0, 0);
+      if (ut < c.nunits) c.e = make_int2(__ldg(d.upd_ab + c.u0 + (ut >> 2)), __ldg(d.upd_dst + c.u0 + (ut >> 2)));
+      return c;
+    };
+    ColIdx cur = column_indices(T.j0 < T.j1 ? T.j0 : 0);
+    for (int j = T.j0; j < T.j1; ++j) {
       bar_sync(kBarPub, kPubAll);   // (also: every helper is done with the previous column)
       const int col_failed = S.fail[T.slot][j & 1];   // (first read behind the barrier: the barrier wait ends here)
       if (T.prof && col_failed >= 0) { PHL(0); if (ut == 0) TRACE(4, j); }
       if (col_failed) break;
+      const bool first = ut < cur.nunits && cur.e.y != cur.dU1 && cur.e.y != cur.dU2;
+      UnitAddr A0 = {0, 0, 0, nullptr};
+      if (first) A0 = unit_addr(d, T, cur.base, hi, ut, cur.e.x, cur.e.y);
+      ColIdx nxt = cur;
+      if (j + 1 < T.j1) nxt = column_indices(j + 1);
       bar_sync(kBarH, kRowsAll);    // the column's rows are scaled
       if (T.prof && *reinterpret_cast<volatile int*>(&S.fail[T.slot][j & 1]) >= 0) PHL(1);
-      // quarter-block units, at most one per thread for SLAM-shaped columns (the urgent warp owns lanes 96..127 of the
-      // unit index space)
-      for (int u = ut; u < nunits; u += kUnitStride) {
-        const int2 e = (u == ut) ? e0 : make_int2(__ldg(d.upd_ab + u0 + (u >> 2)), __ldg(d.upd_dst + u0 + (u >> 2)));
-        if (e.y == dU1 || e.y == dU2) continue;   // the urgent warp's urgent ones
-        quarter_unit(d, T, base, hi, u, e.x, e.y);
+      // quarter-block units, at most one per thread for SLAM-shaped columns
+      if (first) unit_run(A0);
+      for (int u = ut + kUnitStride; u < cur.nunits; u += kUnitStride) {
+        const int2 e = make_int2(__ldg(d.upd_ab + cur.u0 + (u >> 2)), __ldg(d.upd_dst + cur.u0 + (u >> 2)));
+        if (e.y == cur.dU1 || e.y == cur.dU2) continue;   // the urgent warp's
+        quarter_unit(d, T, cur.base, hi, u, e.x, e.y);
       }
       PHL(2);
       ring_refill(d, T, col_ptr, blk_end, j, ut, until_refill, hi);
+      cur = nxt;
     }
-    if (T.prof && ut == 0)
+    if (T.prof && ut == 8)
       for (int i = 0; i < 4; ++i) T.prof[4 + i] = ph[i];
 #undef PHL
   } else if (row_warp_index(warp) >= 0) {
@@ -563,30 +596,41 @@ __device__ void scatter_rows(const BaDev& d, int lo, int hi, int c0, int c1, int
         // block (column and the N row) -- is fetched while the previous row is being scattered; what is left on the
         // chain per row is the read of x_i, six FMAs and the read-modify-write of the target column.
         int i = sChunk[k] - 1;
-        int p0 = 0, nb = 0, col = -1;
-        double Nt[6] = {0, 0, 0, 0, 0, 0};
-        auto prefetch = [&](int row) {
-          p0 = rptr[row]; nb = rptr[row + 1] - p0; col = -1;
-          if (lane < 30 && g < nb) {
-            col = rcol[p0 + g];
-            load_row6(b + (size_t)(p0 - b0 + g) * 36 + r * 6, Nt);
+        int p0 = 0, nb = 0, col = -1, colB = -1;
+        double Nt[6] = {0, 0, 0, 0, 0, 0}, NtB[6] = {0, 0, 0, 0, 0, 0};
+        auto prefetch = [&](int row) {   // two blocks per lane group (g and g + 5): a window row has 7-8 blocks
+          p0 = rptr[row]; nb = rptr[row + 1] - p0; col = -1; colB = -1;
+          if (lane < 30) {
+            if (g < nb) {
+              col = rcol[p0 + g];
+              load_row6(b + (size_t)(p0 - b0 + g) * 36 + r * 6, Nt);
+            }
+            if (g + 5 < nb) {
+              colB = rcol[p0 + g + 5];
+              load_row6(b + (size_t)(p0 - b0 + g + 5) * 36 + r * 6, NtB);
+            }
           }
         };
         if (i >= rlo) prefetch(i);
         for (; i >= rlo; --i) {
-          const int cp0 = p0, cnb = nb, ccol = col;
-          double cN[6];
+          const int cp0 = p0, cnb = nb, ccol = col, ccolB = colB;
+          double cN[6], cNB[6];
 #pragma unroll
-          for (int q = 0; q < 6; ++q) cN[q] = Nt[q];
+          for (int q = 0; q < 6; ++q) { cN[q] = Nt[q]; cNB[q] = NtB[q]; }
           double xi[6];
           load_row6(xv + 6 * i, xi);   // final: every row above has been scattered (and the warp synchronised)
           if (i > rlo) prefetch(i - 1);
-          if (ccol >= c0 && ccol < c1) {   // (a separator row also holds blocks of the other branch)
-            const double sdot = (cN[0] * xi[0] + cN[1] * xi[1] + cN[2] * xi[2]) + (cN[3] * xi[3] + cN[4] * xi[4] + cN[5] * xi[5]);
-            xv[6 * ccol + r] -= sdot;
-          }
-          if (lane < 30)   // rows with more than five blocks: the farther columns, not needed by the next rows
-            for (int a = g + 5; a < cnb; a += 5) {
+          // (a separator row also holds blocks of the other branch: columns outside [c0, c1) are skipped)
+          const bool okA = ccol >= c0 && ccol < c1, okB = ccolB >= c0 && ccolB < c1;
+          const double sdotA = (cN[0] * xi[0] + cN[1] * xi[1] + cN[2] * xi[2]) + (cN[3] * xi[3] + cN[4] * xi[4] + cN[5] * xi[5]);
+          const double sdotB = (cNB[0] * xi[0] + cNB[1] * xi[1] + cNB[2] * xi[2]) + (cNB[3] * xi[3] + cNB[4] * xi[4] + cNB[5] * xi[5]);
+          double* tA = xv + 6 * (okA ? ccol : 0) + r;
+          double* tB = xv + 6 * (okB ? ccolB : 0) + r;
+          const double vA = okA ? *tA : 0., vB = okB ? *tB : 0.;
+          if (okA) *tA = vA - sdotA;
+          if (okB) *tB = vB - sdotB;
+          if (lane < 30)   // rows with more than ten blocks
+            for (int a = g + 10; a < cnb; a += 5) {
               const int col2 = rcol[cp0 + a];
               if (col2 < c0 || col2 >= c1) continue;
               double N2[6];
