@@ -40,18 +40,21 @@ namespace cg = cooperative_groups;
 namespace svs {
 
 constexpr int kSolveThreads = 384;               // 12 warps; warp w issues from scheduler w % 4
-// Roles (factor_range).  Nothing but the chain warp ever runs on scheduler 0 (warps 4 and 8 idle through the
-// factorisation); what bounds the helpers is the number of instructions their schedulers must issue per column
-// (ncu: with sixteen resident warps that all walked the column loop, 3 300 warp-instructions per column on three
-// schedulers), so there are exactly as many helper warps as the work of a SLAM-shaped column fills.  Measured
-// alternatives (C2 / C5 solve time per 10 iterations): this layout 1.64 / 7.76 ms; three unit warps with the four
-// left-over units of a window column on the urgent warp 1.65 / 7.88 ms; with the left-over units on the second row
-// warp 1.93 / 9.19 ms (its N rows and right-hand side then finish too late for the next column).
+// Roles (factor_range).  Eight working warps, two per scheduler (warps 8-11 idle through the factorisation): what bounds
+// the helpers is the number of instructions their schedulers must issue per column (ncu: with sixteen resident warps
+// that all walked the column loop, 3 300 warp-instructions per column on three schedulers) and the FP64 pipe of a
+// scheduler (54 DFMAs of a quarter unit take 2 cycles each: two unit warps on one scheduler doubled the FMA phase).
+// Measured alternatives (C2 / C5 solve time per 10 iterations):
+//   this layout (unit warps 1-4, one per scheduler, warp 4 next to the chain)            1.40 / 6.6 ms
+//   fourth unit warp on warp 11 (scheduler 3, next to a unit warp and the urgent warp)   1.46 / 6.8 ms
+//   round-2 first layout (unit warps 1, 2, 3, 5; row warps 6, 9; chain alone)            1.64 / 7.8 ms
+//   three unit warps, left-over units on the urgent warp                                 1.65 / 7.9 ms
+//   three unit warps, left-over units on the second row warp                             1.93 / 9.2 ms
 constexpr int kChainWarp = 0;
-constexpr int kUnitWarps = 4;                    // warps 1, 2, 3, 5: quarter-block units of the trailing update
-constexpr int kRowWarps = 2;                     // warps 6, 9: rows of the column, N rows, right-hand side
+constexpr int kUnitWarps = 4;                    // warps 1-4: quarter-block units of the trailing update
+constexpr int kRowWarps = 2;                     // warps 5, 6: rows of the column, N rows, right-hand side
 constexpr int kUrgentWarp = 7;                   // the two pair updates the chain reads next
-__device__ __forceinline__ int unit_warp_index(int w) { return (w >= 1 && w <= 4) ? w - 1 : -1; }   // one per scheduler (warp 4 shares the chain's)
+__device__ __forceinline__ int unit_warp_index(int w) { return (w >= 1 && w <= 4) ? w - 1 : -1; }
 __device__ __forceinline__ int row_warp_index(int w) { return w == 5 ? 0 : (w == 6 ? 1 : -1); }
 constexpr int kUnitThreads = kUnitWarps * 32, kRowThreads = kRowWarps * 32;
 constexpr int kPubAll = 32 * (1 + kUnitWarps + kRowWarps + 1);   // chain + unit + row + urgent warps
@@ -335,8 +338,9 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
         }
       }
       if (T.prof && dnext != 1.2345e-300) { PCH(2); TRACE(1, j); }
-      if (lane == 0) {   // publish l (21) and rinv (6): 14 independent 16-byte stores by one lane (a per-lane
-                         // select of "its" element would be a 27-deep dependent chain on the critical warp)
+      {   // publish l (21) and rinv (6): 14 independent 16-byte stores.  Every lane holds the same values and stores
+          // them to the same addresses (one wavefront each): no divergent branch in front of the barrier arrival, and
+          // no per-lane select of "its" element (a 27-deep dependent chain on the critical warp)
         double2* sl2 = reinterpret_cast<double2*>(S.sL[T.slot][j & 1]);
 #pragma unroll
         for (int q = 0; q < 10; ++q) sl2[q] = make_double2(l[2 * q], l[2 * q + 1]);
