@@ -925,7 +925,8 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
     cudaMemset(d.dbg + 48, 0, 8 * sizeof(long long));
   }
   if (getenv("SVS_SOLVE_TIMING")) {
-    {
+    const bool roles = atoi(getenv("SVS_SOLVE_TIMING")) > 1;
+    if (roles) {
       long long tr[160];
       cudaMemcpy(tr, d.dbg, sizeof tr, cudaMemcpyDeviceToHost);
       const long long* t0 = tr + 12 + 52;
@@ -945,6 +946,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
       fprintf(stderr, "  CTA %d:", g);
       for (int i = 0; i < 6; ++i) fprintf(stderr, " %lld", dbg[g * 6 + i]);
       const long long* q = dbg + 12 + 16 * g;
+      if (!roles) { fprintf(stderr, "\n"); continue; }
       fprintf(stderr, "\n     chain: hand-over %lld chol %lld wait-urgent+load %lld publish %lld | unit thread 8: loop-top+factor %lld wait-rows %lld "
               "units %lld | row thread 0: wait-factor %lld rows %lld wait-rows %lld N+rhs %lld | urgent: wait-factor %lld rows %lld units %lld\n",
               q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[8], q[9], q[10], q[11], q[12], q[13], q[14]);

@@ -29,6 +29,7 @@
 // Graphs that are not banded enough for two ends run the same code as a single CTA (one chain).
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 
@@ -77,15 +78,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// 1/sqrt(a): hardware approximation + two Newton steps (the library rsqrt() carries special-case
-// handling that would sit on the pivot chain)
+// 1/sqrt(a): hardware approximation (about 23 bits) + ONE third-order step, y1 = y0 (1 + e/2 + 3 e^2/8) with
+// e = 1 - a y0^2 (error ~ 5/16 e^3 < 2^-64).  Dependent chain: approximation, 4 FP64 operations -- two Newton steps
+// are 6, and the library rsqrt() carries special-case handling; this sits six times on the pivot chain of every column.
 __device__ __forceinline__ double fast_rsqrt(double a) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  const double h = 0.5 * a;
-  y = fma(y, fma(-h * y, y, 0.5), y);
-  y = fma(y, fma(-h * y, y, 0.5), y);
-  return y;
+  const double t = a * y;
+  const double e = fma(-t, y, 1.0);
+  const double ye = y * e;
+  const double p = fma(0.375, e, 0.5);
+  return fma(ye, p, y);
 }
 
 // Lower Cholesky of a 6x6 block given as its packed lower triangle a[r(r+1)/2 + c] (dlam added to the
@@ -176,29 +179,31 @@ __device__ __forceinline__ int ring_idx(const Team& T, int id) { return T.ring_o
 // The address decode (indices only) is separate from the arithmetic so that the unit warps can do it while the
 // column's rows are still being scaled.
 struct UnitAddr {
-  int la, lb, dd;        // offsets in sm_solve (doubles): 3 rows of L_a, 3 rows of L_b, the 3x3 destination
+  const double* la;      // 3 rows of L_a, 3 rows of L_b, the 3x3 destination (shared memory)
+  const double* lb;
+  double* dd;
   double* dg;            // destination in HBM when the block is not resident (else nullptr)
 };
 __device__ __forceinline__ UnitAddr unit_addr(const BaDev& d, const Team& T, int base, int hi, int u, int ab, int dst) {
   const int h = (u >> 1) & 1, g = u & 1;
   UnitAddr A;
-  A.la = ring_idx(T, base + 1 + (ab >> 16)) + h * 18;
-  A.lb = ring_idx(T, base + 1 + (ab & 0xffff)) + g * 18;
+  A.la = ring_blk(T, base + 1 + (ab >> 16)) + h * 18;
+  A.lb = ring_blk(T, base + 1 + (ab & 0xffff)) + g * 18;
   const bool far = dst >= hi && dst < T.sep_blk0;   // not resident: read-modify-write in HBM
   A.dg = far ? d.S + (size_t)dst * 36 + h * 18 + g * 3 : nullptr;
-  A.dd = (dst < hi ? ring_idx(T, dst) : T.area_off + (dst - T.sep_blk0) * 36) + h * 18 + g * 3;
+  A.dd = sm_solve + (dst < hi ? ring_idx(T, dst) : T.area_off + (dst - T.sep_blk0) * 36) + h * 18 + g * 3;
   return A;
 }
 __device__ __forceinline__ void unit_run(const UnitAddr& A) {
-  const double2* La = reinterpret_cast<const double2*>(sm_solve + A.la);
-  const double2* Lb = reinterpret_cast<const double2*>(sm_solve + A.lb);
+  const double2* La = reinterpret_cast<const double2*>(A.la);
+  const double2* Lb = reinterpret_cast<const double2*>(A.lb);
   double a[18], b[18], o[9];
 #pragma unroll
   for (int q = 0; q < 9; ++q) { const double2 v = La[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
 #pragma unroll
   for (int q = 0; q < 9; ++q) { const double2 v = Lb[q]; b[2 * q] = v.x; b[2 * q + 1] = v.y; }
   double* Dg = A.dg;
-  double* D = sm_solve + A.dd;
+  double* D = A.dd;
   if (Dg) {
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr)
@@ -316,6 +321,8 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
         pD = ring_blk(T, col_ptr[j + 1]) + r * 6 + c;
         pB = ring_blk(T, base + 1);
       }
+      double2* sl2 = reinterpret_cast<double2*>(S.sL[T.slot][j & 1]);   // (addresses of the publish: formed before the
+      int* pfail = &S.fail[T.slot][j & 1];                              //  factorisation, not behind the urgent barrier)
       double a[22];
       {
         const double2* c2 = reinterpret_cast<const double2*>(S.cdiag);
@@ -341,14 +348,13 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       {   // publish l (21) and rinv (6): 14 independent 16-byte stores.  Every lane holds the same values and stores
           // them to the same addresses (one wavefront each): no divergent branch in front of the barrier arrival, and
           // no per-lane select of "its" element (a 27-deep dependent chain on the critical warp)
-        double2* sl2 = reinterpret_cast<double2*>(S.sL[T.slot][j & 1]);
 #pragma unroll
         for (int q = 0; q < 10; ++q) sl2[q] = make_double2(l[2 * q], l[2 * q + 1]);
         sl2[10] = make_double2(l[20], rinv[0]);
         sl2[11] = make_double2(rinv[1], rinv[2]);
         sl2[12] = make_double2(rinv[3], rinv[4]);
         sl2[13] = make_double2(rinv[5], 0.);
-        if (!ok) S.fail[T.slot][j & 1] = 1;
+        if (!ok) *pfail = 1;
       }
       bar_arrive(kBarPub, kPubAll);
       TRACE(0, j);
@@ -363,6 +369,17 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
 #undef PCH
   } else if (warp == kUrgentWarp) {
     // ------------------------------------------------------------------ the urgent warp
+    // this lane's two output elements of the urgent updates: t < 21 -> packed lower element of D_{j+2}, else element
+    // t - 21 of S_{j+2,j+1}
+    auto decode = [](int t, int& r, int& c, bool& isS) {
+      isS = t >= 21;
+      if (isS) { r = (t - 21) / 6; c = (t - 21) - r * 6; }
+      else { r = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15); c = t - r * (r + 1) / 2; }
+    };
+    int u0r, u0c, u1r, u1c;
+    bool u0S, u1S;
+    decode(lane, u0r, u0c, u0S);
+    decode(min(lane + 32, 56), u1r, u1c, u1S);
     long long pu[4] = {0, 0, 0, 0}, ptu = T.prof ? clock64() : 0;
 #define PUR(i) do { if (T.prof) { const long long c_ = clock64(); pu[i] += c_ - ptu; ptu = c_; } } while (0)
     for (int j = T.j0; j < T.j1; ++j) {
@@ -372,17 +389,37 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
                                                                                         // rule as the chain's and the unit warps' `link`)
       int i2 = i1 + 1;                                                    // index of row j+2, if present
       if (!(i2 < nb && row_idx[base + 1 + i2] == j + 2)) i2 = -1;
+      // every address below depends on the structure only: formed here, in the shadow of the wait for the diagonal
+      // factor -- behind the barrier this warp is on the loop chain -> urgent -> chain, where only loads, FMAs and
+      // stores remain
+      const bool scale = lane < 6 * min(nb, 2);
+      double* src = ring_blk(T, base + 1 + (scale ? lane / 6 : 0)) + (lane % 6) * 6;
+      const double2* l2 = reinterpret_cast<const double2*>(S.sL[T.slot][j & 1]);
+      const int* pfail = &S.fail[T.slot][j & 1];
+      const bool urgent = want && i2 >= 0;
+      const int nout = urgent ? (i1 >= 0 ? 57 : 21) : 0;
+      const bool on0 = lane < nout, on1 = lane + 32 < nout;
+      const double *pa0 = nullptr, *pb0 = nullptr, *pa1 = nullptr, *pb1 = nullptr;
+      double *t0 = nullptr, *t1 = nullptr;
+      if (urgent) {
+        // D_{j+2} -= L2 L2^T (its 21 lower elements: the chain reads no others) and S_{j+2,j+1} -= L2 L1^T (36), ONE
+        // element per lane and round: 6 loads, 6 dependent FMAs, one store
+        const double* B2 = ring_blk(T, base + 1 + i2);
+        const double* B1 = ring_blk(T, base + 1 + (i1 >= 0 ? i1 : i2));
+        double* Dd = ring_blk(T, col_ptr[j + 2]);
+        double* Sd = ring_blk(T, col_ptr[j + 1] + 1);
+        pa0 = B2 + u0r * 6; pb0 = (u0S ? B1 : B2) + u0c * 6; t0 = (u0S ? Sd : Dd) + u0r * 6 + u0c;
+        pa1 = B2 + u1r * 6; pb1 = (u1S ? B1 : B2) + u1c * 6; t1 = (u1S ? Sd : Dd) + u1r * 6 + u1c;
+      }
       bar_sync(kBarPub, kPubAll);
-      const int ufail = S.fail[T.slot][j & 1];
+      const int ufail = *pfail;
       if (T.prof && ufail >= 0) { PUR(0); TRACE(2, j); }
       if (ufail) break;
-      // the first two blocks of the column are scaled here (the general helpers take the others)
-      if (lane < 6 * min(nb, 2)) {
-        const double2* l2 = reinterpret_cast<const double2*>(S.sL[T.slot][j & 1]);
+      // the first two blocks of the column are scaled here (the row warps take the others)
+      if (scale) {
         double L_[28], v[6], o[6];
 #pragma unroll
         for (int q = 0; q < 14; ++q) { const double2 t2 = l2[q]; L_[2 * q] = t2.x; L_[2 * q + 1] = t2.y; }
-        double* src = ring_blk(T, base + 1 + lane / 6) + (lane % 6) * 6;
         load_row6(src, v);
         row_fwd(v, L_, L_ + 21, o);
         double2* d2 = reinterpret_cast<double2*>(src);
@@ -390,31 +427,22 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       }
       PUR(1);
       bar_arrive(kBarH, kRowsAll);   // (orders the stores above before the trailing update of the unit warps)
-      if (want && i2 >= 0 && lane < 8 && (lane < 4 || i1 >= 0)) {
-        // lanes 0-3: D_{j+2} -= L2 L2^T, lanes 4-7: S_{j+2,j+1} -= L2 L1^T, a quarter block each
-        const int h = (lane >> 1) & 1, g = lane & 1, second = lane >> 2;
-        const double2* La = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + i2) + h * 18);
-        const double2* Lb = reinterpret_cast<const double2*>(ring_blk(T, base + 1 + (second ? i1 : i2)) + g * 18);
-        double a[18], b[18], o[9];
+      if (urgent) {
+        __syncwarp();   // the rows scaled above (other lanes) are visible
+        double a0[6], b0[6], a1[6], b1[6];
+        double o0 = 0., o1 = 0.;
+        if (on0) { load_row6(pa0, a0); load_row6(pb0, b0); o0 = *t0; }
+        if (on1) { load_row6(pa1, a1); load_row6(pb1, b1); o1 = *t1; }
+        if (on0) {
 #pragma unroll
-        for (int q = 0; q < 9; ++q) { const double2 v = La[q]; a[2 * q] = v.x; a[2 * q + 1] = v.y; }
+          for (int k = 0; k < 6; ++k) o0 = fma(-a0[k], b0[k], o0);
+          *t0 = o0;
+        }
+        if (on1) {
 #pragma unroll
-        for (int q = 0; q < 9; ++q) { const double2 v = Lb[q]; b[2 * q] = v.x; b[2 * q + 1] = v.y; }
-        double* D = ring_blk(T, second ? col_ptr[j + 1] + 1 : col_ptr[j + 2]) + h * 18 + g * 3;
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) o[rr * 3 + cc] = D[rr * 6 + cc];
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc)
-#pragma unroll
-            for (int k = 0; k < 6; ++k) o[rr * 3 + cc] = fma(-a[rr * 6 + k], b[cc * 6 + k], o[rr * 3 + cc]);
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) D[rr * 6 + cc] = o[rr * 3 + cc];
+          for (int k = 0; k < 6; ++k) o1 = fma(-a1[k], b1[k], o1);
+          *t1 = o1;
+        }
       }
       PUR(2);
       TRACE(3, j);
@@ -457,7 +485,7 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       if (T.prof && col_failed >= 0) { PHL(0); if (ut == 0) TRACE(4, j); }
       if (col_failed) break;
       const bool first = ut < cur.nunits && cur.e.y != cur.dU1 && cur.e.y != cur.dU2;
-      UnitAddr A0 = {0, 0, 0, nullptr};
+      UnitAddr A0 = {nullptr, nullptr, nullptr, nullptr};
       if (first) A0 = unit_addr(d, T, cur.base, hi, ut, cur.e.x, cur.e.y);
       ColIdx nxt = cur;
       if (j + 1 < T.j1) nxt = column_indices(j + 1);
@@ -486,11 +514,15 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
     for (int j = T.j0; j < T.j1; ++j) {
       const int base = col_ptr[j], nb = col_ptr[j + 1] - base - 1;
       const int nrows = nb * 6 + 1;
+      // addresses first (structure only), in the shadow of the wait for the diagonal factor
+      const int row0 = 6 * min(nb, 2) + rt;
+      double* src0 = sm_solve + (row0 < nb * 6 ? ring_idx(T, base + 1 + row0 / 6) + (row0 % 6) * 6 : S.yv_off + 6 * j);
+      const double* sl = S.sL[T.slot][j & 1];
+      const int* pfail = &S.fail[T.slot][j & 1];
       bar_sync(kBarPub, kPubAll);
-      const int col_failed = S.fail[T.slot][j & 1];
+      const int col_failed = *pfail;
       if (T.prof && col_failed >= 0) PHL(0);
       if (col_failed) break;
-      const double* sl = S.sL[T.slot][j & 1];
       double L_[28];
       {
         const double2* l2 = reinterpret_cast<const double2*>(sl);
@@ -499,8 +531,8 @@ __device__ void factor_range(const BaDev& d, const Team& T, const SolveShared& S
       }
       // ---- rows of the column: L_ij = S_ij L_jj^-T, kept in the ring for the trailing update (the first two blocks
       //      are the urgent warp's); the right-hand side is one more row (forward solve)
-      for (int row = 6 * min(nb, 2) + rt; row < nrows; row += kRowThreads) {
-        double* src = sm_solve + (row < nb * 6 ? ring_idx(T, base + 1 + row / 6) + (row % 6) * 6 : S.yv_off + 6 * j);
+      for (int row = row0; row < nrows; row += kRowThreads) {
+        double* src = row == row0 ? src0 : sm_solve + (row < nb * 6 ? ring_idx(T, base + 1 + row / 6) + (row % 6) * 6 : S.yv_off + 6 * j);
         double v[6], o[6];
         load_row6(src, v);
         row_fwd(v, L_, L_ + 21, o);
@@ -730,7 +762,7 @@ k_solve(BaDev d, int cap, int nsep, int refill_branch, int prof) {
   Team br;
   br.ring_off = ring_off; br.org = 0; br.mask = (unsigned)cap - 1u; br.cap = cap; br.prefilled = 0;
   br.j0 = my0; br.j1 = my1; br.sep_blk0 = sep_blk0; br.area_off = area_off; br.slot = 0; br.refill_period = refill_branch;
-  br.prof = (prof && d.dbg) ? d.dbg + 12 + 16 * rank : nullptr;   // [.. + 32 + 3): unit phases of helper 0 (rank 0: dbg 44..46, rank 1: 56..58)
+  br.prof = (prof > 1 && d.dbg) ? d.dbg + 12 + 16 * rank : nullptr;   // [.. + 32 + 3): unit phases of helper 0 (rank 0: dbg 44..46, rank 1: 56..58)
   factor_range(d, br, S, lambda);
   tk[1] = clock64();
   int failed = sFail[0][0] | sFail[0][1];
@@ -911,7 +943,7 @@ void launch_solve(const BaDev& d, int max_col_branch, int max_col_sep, int nsep,
   attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static const int prof = getenv("SVS_SOLVE_TIMING") ? 1 : 0;
+  static const int prof = getenv("SVS_SOLVE_TIMING") ? std::max(1, atoi(getenv("SVS_SOLVE_TIMING"))) : 0;   // 1: phase boundaries, 2: + per-role counters
   cudaLaunchKernelEx(&cfg, k_solve, d, cap, G > 1 ? nsep : 0, period, prof);
 }
 

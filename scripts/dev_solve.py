@@ -5,7 +5,7 @@ import numpy as np
 from scavislam_b200 import synth, capi
 from oracle import pyoracle as po
 
-os.environ["SVS_SOLVE_TIMING"] = "1"
+os.environ.setdefault("SVS_SOLVE_TIMING", "1")
 ba = capi.BundleAdjuster()
 print(capi.device_info())
 def rel(a, b): return np.abs(a - b).max() / np.abs(b).max()
