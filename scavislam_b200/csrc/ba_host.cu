@@ -6,21 +6,72 @@
 // There is no CPU fallback: every entry point fails with SVS_ERR_NOGPU / SVS_ERR_CUDA
 // when the device path is unavailable.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <chrono>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <numeric>
 #include <set>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/svs_b200.h"
 #include "ba_kernels.cuh"
 #include "nccl_dyn.cuh"
+#include "host_pool.hpp"
 
 using namespace svs;
+
+// One helper thread per handle (started on first use, parked on a condition variable in between): stages the
+// observation arrays in pinned memory and enqueues their DMA while the calling thread analyses the structure.
+struct Worker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool busy = false, quit = false;
+  void run() {
+    std::unique_lock<std::mutex> lk(m);
+    for (;;) {
+      cv.wait(lk, [&] { return quit || job; });
+      if (quit) return;
+      std::function<void()> f = std::move(job);
+      job = nullptr;
+      lk.unlock();
+      f();
+      lk.lock();
+      busy = false;
+      cv.notify_all();
+    }
+  }
+  void post(std::function<void()> f) {
+    std::unique_lock<std::mutex> lk(m);
+    if (!th.joinable()) th = std::thread([this] { run(); });
+    cv.wait(lk, [&] { return !busy; });
+    busy = true;
+    job = std::move(f);
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return !busy; });
+  }
+  ~Worker() {
+    {
+      std::unique_lock<std::mutex> lk(m);
+      cv.wait(lk, [&] { return !busy; });
+      quit = true;
+      cv.notify_all();
+    }
+    if (th.joinable()) th.join();
+  }
+};
 
 // Symbolic analysis of the reduced camera system (see analyse() below)
 struct Symbolic {
@@ -37,7 +88,9 @@ struct svs_ba {
   std::string err;
   bool has_problem = false;
   double* d_raw = nullptr; double* h_raw = nullptr; size_t raw_cap = 0;   // user-order observations + weights (6 doubles per edge)
-  int host_threads = 4;  // OpenMP threads of the per-landmark host loops (SVS_HOST_THREADS)
+  Worker worker;
+  SpinPool pool;   // the per-landmark / per-edge host loops of set_problem
+  int host_threads = 8;  // threads of the per-landmark / per-edge host loops of set_problem (SVS_HOST_THREADS)
   int cur_known = -1;   // host mirror of LmCtl::cur (index of the accepted state buffers), -1 = ask the device
   BaDev d{};
   // one device arena + one pinned staging arena, grown on demand and reused across set_problem calls
@@ -62,7 +115,8 @@ struct svs_ba {
   double* d_out = nullptr; double* h_out = nullptr; size_t out_cap = 0;   // accepted state in the caller's order (one-call API)
   bool export_next = false;
   // host scratch of set_problem, kept across calls (fresh multi-MB vectors page-fault every time)
-  std::vector<int> w_eptr, w_eord, w_fill, w_anchor, w_K, w_order, w_lm_eptr, w_lm_sptr, w_lm_anchor, w_ie_pose, w_bucket;
+  std::vector<std::pair<unsigned long long, int>> w_ko;
+  std::vector<int> w_cnt, w_eptr, w_eord, w_fill, w_anchor, w_K, w_order, w_lm_eptr, w_lm_sptr, w_lm_anchor, w_ie_pose, w_bucket;
   std::vector<unsigned char> w_self, w_lm_self, w_adj;
   std::vector<unsigned long long> w_key;
   std::vector<double> w_psi;
@@ -122,11 +176,10 @@ int dev_upload(svs_ba* h, const T** p, const T* src, size_t n) {
       const size_t bytes = n * sizeof(T);
       if (bytes >= (1u << 20)) {   // multi-MB arrays (observations, weights): split the copy over a few threads
         const int parts = 4;
-#pragma omp parallel for num_threads(4)
-        for (int q = 0; q < parts; ++q) {
+        h->pool.parallel_for(parts, [&](int q) {
           const size_t b0 = bytes * q / parts, b1 = bytes * (q + 1) / parts;
           memcpy(h->stage + off + b0, reinterpret_cast<const char*>(src) + b0, b1 - b0);
-        }
+        });
       } else {
         memcpy(h->stage + off, src, bytes);
       }
@@ -354,9 +407,10 @@ int svs_ba_create(const svs_ba_opts* opts, svs_ba** out) {
   h->flags = opts ? opts->flags : 0;
   {   // threads of the per-landmark host loops of set_problem: a few, never more than half the machine
     const int hw = (int)std::thread::hardware_concurrency();
-    h->host_threads = std::max(1, std::min(4, hw / 2));
+    h->host_threads = std::max(1, std::min(8, hw / 2));
   }
   if (const char* ht = getenv("SVS_HOST_THREADS")) h->host_threads = std::max(1, atoi(ht));
+  h->pool.set_threads(h->host_threads);
   int dev = opts ? opts->device : -1;
   if (dev < 0) cudaGetDevice(&dev);
   h->device = dev;
@@ -400,13 +454,14 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   if ((P && !T_qt) || (L && !psi) || (E && (!e_point || !e_pose || !e_anchor || (!d_obs_info && (!e_obs || !e_info)))) ||
       (C && (!c_i || !c_j || !c_T || !c_Lambda)))
     return fail(h, SVS_ERR_INVALID, "null array");
-  for (int e = 0; e < E; ++e)
-    if (e_point[e] < 0 || e_point[e] >= L || e_pose[e] < 0 || e_pose[e] >= P || e_anchor[e] < 0 || e_anchor[e] >= P)
-      return fail(h, SVS_ERR_INVALID, "observation edge index out of range");
+  // (the observation edges are range-checked inside the grouping pass below, which reads them anyway; the
+  //  same-structure path compares them with an already validated list)
   for (int c = 0; c < C; ++c)
     if (c_i[c] < 0 || c_i[c] >= P || c_j[c] < 0 || c_j[c] >= P || c_i[c] == c_j[c])
       return fail(h, SVS_ERR_INVALID, "pose-pose edge index out of range");
   cudaSetDevice(h->device);
+  h->pool.begin();   // the host loops below run on a few spinning threads until this call returns
+  struct PoolEnd { SpinPool* p; ~PoolEnd() { p->end(); } } pool_end{&h->pool};
   CK(cudaStreamSynchronize(h->stream));   // the arena and the staging buffer are about to be reused
   const bool host_timing = getenv("SVS_HOST_TIMING") != nullptr;
   // ---- same structure as the problem on the device: only the numbers travel
@@ -421,17 +476,18 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       BaDev& d = h->d;
       d.f = cam->f; d.px = cam->px; d.py = cam->py; d.b = cam->b;
       if (E > 0 && !d_obs_info) {
+        // staged in pinned memory and sent in two pieces, so that the first DMA runs under the second copy
         const size_t bytes = 3 * (size_t)E * sizeof(double);
         const int parts = 4;
-#pragma omp parallel for num_threads(4)
-        for (int q = 0; q < 2 * parts; ++q) {
-          const char* src = reinterpret_cast<const char*>(q < parts ? e_obs : e_info);
-          char* dst = reinterpret_cast<char*>(h->h_raw) + (q < parts ? 0 : bytes);
-          const int qq = q % parts;
-          const size_t b0 = bytes * qq / parts, b1 = bytes * (qq + 1) / parts;
-          memcpy(dst + b0, src + b0, b1 - b0);
+        for (int half = 0; half < 2; ++half) {
+          const char* src = reinterpret_cast<const char*>(half ? e_info : e_obs);
+          char* dst = reinterpret_cast<char*>(h->h_raw) + (half ? bytes : 0);
+          h->pool.parallel_for(parts, [&](int q) {
+            const size_t b0 = bytes * q / parts, b1 = bytes * (q + 1) / parts;
+            memcpy(dst + b0, src + b0, b1 - b0);
+          });
+          CK(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_raw) + (half ? bytes : 0), dst, bytes, cudaMemcpyHostToDevice, h->stream));
         }
-        CK(cudaMemcpyAsync(h->d_raw, h->h_raw, 2 * bytes, cudaMemcpyHostToDevice, h->stream));
       }
       if (C) {
         memcpy(h->stage + h->off_cT, c_T, 7 * (size_t)C * sizeof(double));
@@ -465,8 +521,10 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     tp0 = now;
   };
 
-  // ---- observations and weights go to the device in the caller's edge order NOW: the DMA runs under the
-  //      structure analysis below, and a gather kernel brings them into the internal order afterwards
+  // ---- observations and weights go to the device in the caller's edge order NOW: a helper thread stages them in
+  //      pinned memory and enqueues the DMA (observations, then weights) while this thread analyses the structure; a
+  //      gather kernel brings them into the internal order afterwards.  The helper also keeps the copy of the index
+  //      arrays that the same-structure test of the next call compares against.
   if (E > 0 && !d_obs_info) {
     const size_t need = 6 * (size_t)E;
     if (need > h->raw_cap) {
@@ -478,18 +536,28 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       CK(cudaMallocHost((void**)&h->h_raw, want * sizeof(double)));
       h->raw_cap = want;
     }
-    const size_t bytes = 3 * (size_t)E * sizeof(double);
-    const int parts = 4;
-#pragma omp parallel for num_threads(4)
-    for (int q = 0; q < 2 * parts; ++q) {
-      const char* src = reinterpret_cast<const char*>(q < parts ? e_obs : e_info);
-      char* dst = reinterpret_cast<char*>(h->h_raw) + (q < parts ? 0 : bytes);
-      const int qq = q % parts;
-      const size_t b0 = bytes * qq / parts, b1 = bytes * (qq + 1) / parts;
-      memcpy(dst + b0, src + b0, b1 - b0);
-    }
-    lap("raw memcpy");
-    CK(cudaMemcpyAsync(h->d_raw, h->h_raw, 2 * bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  struct Side {   // (every return below waits for the helper: it reads the caller's arrays)
+    Worker* w;
+    cudaError_t err = cudaSuccess;
+    ~Side() { w->wait(); }
+  } side{&h->worker};
+  {
+    cudaError_t* perr = &side.err;
+    h->worker.post([=]() {
+      cudaSetDevice(h->device);
+      if (E > 0 && !d_obs_info) {
+        const size_t bytes = 3 * (size_t)E * sizeof(double);
+        char* hr = reinterpret_cast<char*>(h->h_raw);
+        char* dr = reinterpret_cast<char*>(h->d_raw);
+        memcpy(hr, e_obs, bytes);
+        const cudaError_t e1 = cudaMemcpyAsync(dr, hr, bytes, cudaMemcpyHostToDevice, h->stream);
+        memcpy(hr + bytes, e_info, bytes);
+        const cudaError_t e2 = cudaMemcpyAsync(dr + bytes, hr + bytes, bytes, cudaMemcpyHostToDevice, h->stream);
+        *perr = e1 != cudaSuccess ? e1 : e2;
+      }
+      h->k_epoint.assign(e_point, e_point + E); h->k_epose.assign(e_pose, e_pose + E); h->k_eanchor.assign(e_anchor, e_anchor + E);
+    });
   }
   lap("raw enqueue");
   // ---- group edges per landmark (counting sort), flat arrays only: this runs on the caller's
@@ -497,53 +565,84 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   //      Scratch lives in the handle; the per-landmark and per-edge loops use a few host threads.
   auto& eptr = h->w_eptr; auto& eord = h->w_eord; auto& fillp = h->w_fill;
   eptr.assign(L + 1, 0);
-  for (int e = 0; e < E; ++e) eptr[e_point[e] + 1]++;
-  for (int l = 0; l < L; ++l) eptr[l + 1] += eptr[l];
   eord.resize(E);
-  fillp.assign(eptr.begin(), eptr.end() - 1);
-  for (int e = 0; e < E; ++e) eord[fillp[e_point[e]]++] = e;
+  {
+    // stable counting sort by landmark on `nt` threads: per-thread histograms over contiguous edge ranges, one
+    // prefix over (landmark, thread), per-thread scatter.  The index ranges are checked in the counting pass.
+    const int nt = (E > 32768 && L > 0) ? nthr : 1;
+    auto& cnt = h->w_cnt;
+    cnt.assign((size_t)nt * (L + 1), 0);
+    std::atomic<int> out_of_range{0};
+    h->pool.parallel_for(nt, [&](int t) {
+      int* c = cnt.data() + (size_t)t * (L + 1);
+      const int e0 = (int)((long long)E * t / nt), e1 = (int)((long long)E * (t + 1) / nt);
+      for (int e = e0; e < e1; ++e) {
+        const int l = e_point[e];
+        if (l < 0 || l >= L || e_pose[e] < 0 || e_pose[e] >= P || e_anchor[e] < 0 || e_anchor[e] >= P) { out_of_range.store(1); continue; }
+        c[l]++;
+      }
+    });
+    if (out_of_range.load()) return fail(h, SVS_ERR_INVALID, "observation edge index out of range");
+    int run = 0;
+    for (int l = 0; l < L; ++l) {
+      eptr[l] = run;
+      for (int t = 0; t < nt; ++t) { int& c = cnt[(size_t)t * (L + 1) + l]; const int n = c; c = run; run += n; }
+    }
+    eptr[L] = run;
+    h->pool.parallel_for(nt, [&](int t) {
+      int* c = cnt.data() + (size_t)t * (L + 1);
+      const int e0 = (int)((long long)E * t / nt), e1 = (int)((long long)E * (t + 1) / nt);
+      for (int e = e0; e < e1; ++e) eord[c[e_point[e]]++] = e;
+    });
+  }
   // per landmark: anchor, self-observation flag, observer edges sorted by pose index (in place in eord)
   auto& l_anchor = h->w_anchor; auto& l_K = h->w_K; auto& l_self = h->w_self; auto& key = h->w_key;
   l_anchor.assign(L, -1); l_K.assign(L, 0); l_self.assign(L, 0); key.resize(L);
   int Kmax = 1;
   int bad = 0;
-#pragma omp parallel for schedule(static) reduction(max : Kmax) reduction(max : bad) num_threads(nthr) if (L > 4096)
-  for (int l = 0; l < L; ++l) {
-    const int b = eptr[l], en = eptr[l + 1];
-    key[l] = ~0ull;   // landmarks without observations go last
-    if (b == en) continue;
-    const int anchor = e_anchor[eord[b]];
-    int nself = 0;
-    for (int k = b; k < en; ++k) {
-      const int e = eord[k];
-      if (e_anchor[e] != anchor) bad = std::max(bad, 1);
-      if (e_pose[e] == anchor) ++nself;
-    }
-    // insertion sort by (is-not-self, pose): the self edge first, then ascending pose index
-    for (int k = b + 1; k < en; ++k) {
-      const int e = eord[k];
-      const int ke = e_pose[e] == anchor ? -1 : e_pose[e];
-      int q = k - 1;
-      while (q >= b) {
-        const int f = eord[q];
-        const int kf = e_pose[f] == anchor ? -1 : e_pose[f];
-        if (kf <= ke) break;
-        eord[q + 1] = f;
-        --q;
+  const int nchunk = L > 4096 ? 4 * nthr : 1;   // contiguous landmark ranges, handed out dynamically
+  std::vector<int> c_kmax(nchunk, 1), c_bad(nchunk, 0);
+  h->pool.parallel_for(nchunk, [&](int ck) {
+    int Kmax = 1, bad = 0;
+    for (int l = (int)((long long)L * ck / nchunk), l_end = (int)((long long)L * (ck + 1) / nchunk); l < l_end; ++l) {
+      const int b = eptr[l], en = eptr[l + 1];
+      key[l] = ~0ull;   // landmarks without observations go last
+      if (b == en) continue;
+      const int anchor = e_anchor[eord[b]];
+      int nself = 0;
+      for (int k = b; k < en; ++k) {
+        const int e = eord[k];
+        if (e_anchor[e] != anchor) bad = std::max(bad, 1);
+        if (e_pose[e] == anchor) ++nself;
       }
-      eord[q + 1] = e;
+      // insertion sort by (is-not-self, pose): the self edge first, then ascending pose index
+      for (int k = b + 1; k < en; ++k) {
+        const int e = eord[k];
+        const int ke = e_pose[e] == anchor ? -1 : e_pose[e];
+        int q = k - 1;
+        while (q >= b) {
+          const int f = eord[q];
+          const int kf = e_pose[f] == anchor ? -1 : e_pose[f];
+          if (kf <= ke) break;
+          eord[q + 1] = f;
+          --q;
+        }
+        eord[q + 1] = e;
+      }
+      for (int k = b + 1; k < en; ++k)
+        if (e_pose[eord[k]] == e_pose[eord[k - 1]]) bad = std::max(bad, 2);
+      const int K = 1 + (en - b) - nself;
+      l_anchor[l] = anchor; l_self[l] = (unsigned char)nself; l_K[l] = K;
+      Kmax = std::max(Kmax, K);
+      // locality key: track shape (self flag, length, first and last observer) inside an anchor, so that
+      // neighbouring warps of the fused kernel scatter into the same blocks of the reduced system
+      const unsigned long long first = (unsigned long long)(e_pose[eord[b + (nself ? 1 : 0) < en ? b + (nself ? 1 : 0) : b]] & 0xfffff);
+      const unsigned long long last = (unsigned long long)(e_pose[eord[en - 1]] & 0xfffff);
+      key[l] = ((unsigned long long)(nself ? 0 : 1) << 61) | ((unsigned long long)(K & 0xfffff) << 40) | (first << 20) | last;
     }
-    for (int k = b + 1; k < en; ++k)
-      if (e_pose[eord[k]] == e_pose[eord[k - 1]]) bad = std::max(bad, 2);
-    const int K = 1 + (en - b) - nself;
-    l_anchor[l] = anchor; l_self[l] = (unsigned char)nself; l_K[l] = K;
-    Kmax = std::max(Kmax, K);
-    // locality key: track shape (self flag, length, first and last observer) inside an anchor, so that
-    // neighbouring warps of the fused kernel scatter into the same blocks of the reduced system
-    const unsigned long long first = (unsigned long long)(e_pose[eord[b + (nself ? 1 : 0) < en ? b + (nself ? 1 : 0) : b]] & 0xfffff);
-    const unsigned long long last = (unsigned long long)(e_pose[eord[en - 1]] & 0xfffff);
-    key[l] = ((unsigned long long)(nself ? 0 : 1) << 61) | ((unsigned long long)(K & 0xfffff) << 40) | (first << 20) | last;
-  }
+    c_kmax[ck] = Kmax; c_bad[ck] = bad;
+  });
+  for (int ck = 0; ck < nchunk; ++ck) { Kmax = std::max(Kmax, c_kmax[ck]); bad = std::max(bad, c_bad[ck]); }
   if (bad == 1) return fail(h, SVS_ERR_UNSUPPORTED, "edges of one point name different anchor frames");
   if (bad == 2) return fail(h, SVS_ERR_UNSUPPORTED, "a point is observed twice by the same frame");
   lap("group");
@@ -554,15 +653,21 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   for (int l = 0; l < L; ++l) bucket[(l_anchor[l] < 0 ? P : l_anchor[l]) + 1]++;
   for (int a = 0; a <= P; ++a) bucket[a + 1] += bucket[a];
   {
+    // (key, landmark) pairs side by side: the comparisons of the per-anchor sorts touch no other array
     auto& cur = fillp;
     cur.assign(bucket.begin(), bucket.end() - 1);
-    for (int l = 0; l < L; ++l) order[cur[l_anchor[l] < 0 ? P : l_anchor[l]]++] = l;
+    auto& ko = h->w_ko;
+    ko.resize(L);
+    for (int l = 0; l < L; ++l) ko[cur[l_anchor[l] < 0 ? P : l_anchor[l]]++] = std::make_pair(key[l], l);
+    h->pool.parallel_for((P + 1 + 7) / 8, [&](int ck) {
+      for (int a = 8 * ck; a <= P && a < 8 * ck + 8; ++a) {
+        std::sort(ko.begin() + bucket[a], ko.begin() + bucket[a + 1]);
+        for (int i = bucket[a]; i < bucket[a + 1]; ++i) order[i] = ko[i].second;
+      }
+    });
   }
-#pragma omp parallel for schedule(dynamic, 16) num_threads(nthr) if (L > 4096)
-  for (int a = 0; a <= P; ++a)
-    std::sort(order.begin() + bucket[a], order.begin() + bucket[a + 1],
-              [&](int x, int y) { return key[x] != key[y] ? key[x] < key[y] : x < y; });
   h->lm_to_user = order;
+  lap("order");
   auto& lm_eptr = h->w_lm_eptr; auto& lm_sptr = h->w_lm_sptr; auto& lm_anchor = h->w_lm_anchor; auto& ie_pose = h->w_ie_pose;
   auto& lm_self = h->w_lm_self; auto& edge_src = h->w_edge_src; auto& ipsi = h->w_psi;
   lm_eptr.assign(L + 1, 0); lm_sptr.assign(L + 1, 0); lm_anchor.assign(L, 0); ie_pose.resize(E);
@@ -574,19 +679,21 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   }
   const int ne = lm_eptr[L], ns = lm_sptr[L];
   (void)ne;
-#pragma omp parallel for schedule(static) num_threads(nthr) if (L > 4096)
-  for (int li = 0; li < L; ++li) {
-    const int l = order[li];
-    for (int q = 0; q < 3; ++q) ipsi[3 * (size_t)li + q] = psi[3 * (size_t)l + q];
-    if (l_anchor[l] < 0) continue;
-    lm_anchor[li] = l_anchor[l]; lm_self[li] = l_self[l];
-    int at = lm_eptr[li];
-    for (int k = eptr[l]; k < eptr[l + 1]; ++k, ++at) {
-      const int e = eord[k];
-      ie_pose[at] = e_pose[e];
-      edge_src[at] = e;   // the doubles follow on the device (k_regroup)
+  h->pool.parallel_for(nchunk, [&](int ck) {
+    for (int li = (int)((long long)L * ck / nchunk), li_end = (int)((long long)L * (ck + 1) / nchunk); li < li_end; ++li) {
+      const int l = order[li];
+      for (int q = 0; q < 3; ++q) ipsi[3 * (size_t)li + q] = psi[3 * (size_t)l + q];
+      if (l_anchor[l] < 0) continue;
+      lm_anchor[li] = l_anchor[l]; lm_self[li] = l_self[l];
+      int at = lm_eptr[li];
+      for (int k = eptr[l]; k < eptr[l + 1]; ++k, ++at) {
+        const int e = eord[k];
+        ie_pose[at] = e_pose[e];
+        edge_src[at] = e;   // the doubles follow on the device (k_regroup)
+      }
     }
-  }
+  });
+  lap("fill");
   // ---- work lists of the fused kernel: runs of landmarks with identical slot lists (<= 8 frames)
   std::vector<int> task_lm, task_cnt, gen_lm, long_lm;   // long_lm: more than kMaxTrack slots (streaming kernel, any length)
   int Kmax_gen = 1;
@@ -602,18 +709,32 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
         if (ie_pose[lm_eptr[la] + i] != ie_pose[lm_eptr[lb] + i]) return false;
       return true;
     };
-    for (int li = 0; li < L; ++li) {
-      const int kk = lm_eptr[li + 1] - lm_eptr[li], KK = lm_sptr[li + 1] - lm_sptr[li];
-      if (kk > 0 && KK > kMaxTrack) { long_lm.push_back(li); continue; }
-      if (chunk == 0 || kk == 0 || KK > 8) {
-        gen_lm.push_back(li);
-        Kmax_gen = std::max(Kmax_gen, KK);
-        continue;
+    // built on `nt` threads over contiguous landmark ranges (a run never spans two ranges), concatenated in order
+    const int nt = L > 4096 ? nthr : 1;
+    std::vector<std::vector<int>> t_lm(nt), t_cnt(nt), t_gen(nt), t_long(nt);
+    std::vector<int> t_kmax(nt, 1);
+    h->pool.parallel_for(nt, [&](int t) {
+      auto& tl = t_lm[t]; auto& tc = t_cnt[t];
+      const int l0 = (int)((long long)L * t / nt), l1 = (int)((long long)L * (t + 1) / nt);
+      for (int li = l0; li < l1; ++li) {
+        const int kk = lm_eptr[li + 1] - lm_eptr[li], KK = lm_sptr[li + 1] - lm_sptr[li];
+        if (kk > 0 && KK > kMaxTrack) { t_long[t].push_back(li); continue; }
+        if (chunk == 0 || kk == 0 || KK > 8) {
+          t_gen[t].push_back(li);
+          t_kmax[t] = std::max(t_kmax[t], KK);
+          continue;
+        }
+        if (!tl.empty() && tl.back() + tc.back() == li && tc.back() < chunk && same_slots(tl.back(), li))
+          tc.back()++;
+        else { tl.push_back(li); tc.push_back(1); }
       }
-      if (!task_lm.empty() && task_lm.back() + task_cnt.back() == li && task_cnt.back() < chunk &&
-          same_slots(task_lm.back(), li))
-        task_cnt.back()++;
-      else { task_lm.push_back(li); task_cnt.push_back(1); }
+    });
+    for (int t = 0; t < nt; ++t) {
+      task_lm.insert(task_lm.end(), t_lm[t].begin(), t_lm[t].end());
+      task_cnt.insert(task_cnt.end(), t_cnt[t].begin(), t_cnt[t].end());
+      gen_lm.insert(gen_lm.end(), t_gen[t].begin(), t_gen[t].end());
+      long_lm.insert(long_lm.end(), t_long[t].begin(), t_long[t].end());
+      Kmax_gen = std::max(Kmax_gen, t_kmax[t]);
     }
   }
 
@@ -745,6 +866,8 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   if ((rc = arena_reserve(h, h->arena_off, upload_bytes))) return rc;
   lay();
   lap("stage");
+  h->worker.wait();   // its DMA is in the stream ahead of everything enqueued below
+  if (side.err != cudaSuccess) return fail(h, SVS_ERR_CUDA, cudaGetErrorString(side.err));
   h->d_pose0 = const_cast<double*>(d_pose0c);
   h->d_psi0 = const_cast<double*>(d_psi0c);
   CK(cudaMemcpyAsync(h->arena, h->stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -762,7 +885,6 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   h->C_edges = C;
   h->has_problem = true;
   h->k_P = P; h->k_L = L; h->k_E = E; h->k_C = C; h->k_flags = h->flags; h->k_extra = h->extra_pairs;
-  h->k_epoint.assign(e_point, e_point + E); h->k_epose.assign(e_pose, e_pose + E); h->k_eanchor.assign(e_anchor, e_anchor + E);
   h->k_ci.assign(c_i, c_i + C); h->k_cj.assign(c_j, c_j + C);
   h->k_fixed = fx;
   return svs_ba_reset_state(h);

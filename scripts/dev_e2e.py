@@ -9,8 +9,13 @@ ba = capi.BundleAdjuster()
 pb = synth.make_config("C2")
 pb2 = synth.with_dropouts(pb, 0.02, seed=5)
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+cold = len(sys.argv) > 2 and sys.argv[2] == "cold"   # pause between calls, like a back-end tick (helper threads asleep)
+if cold:
+    import torch   # (bench.py runs with torch and its OpenMP runtime loaded)
 for rep in range(8):
     w = (pb, pb2)[rep & 1] if rep < 6 else pb
+    if cold:
+        time.sleep(0.02)
     t = time.perf_counter()
     it, _, _, st = ba.optimise_inner_and_outer_window(w, iters)
     dt = time.perf_counter() - t
