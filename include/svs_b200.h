@@ -459,6 +459,33 @@ int svs_map_absorb(svs_map *h, svs_ba *ba);
 int svs_ba_set_problem_from_map(svs_ba *ba, svs_map *map, int P, const int *window_vertex, const unsigned char *fixed,
                                 int L, const int *active_point, int C, const int *c_i, const int *c_j,
                                 const double *c_T_ji, const double *c_Lambda, const svs_cam *cam, int *num_edges);
+/* The pose graph of the map: for every vertex its neighbours in the order SlamGraph::computeInitialDoubleWin pushes them
+ * (Vertex::neighbor_ids_ordered_by_strength from the strongest, slam_graph.cpp:584-590; an entry in either direction is a
+ * direct edge of edge_table_), and per directed entry the marginalised constraint copyContraintsToG2o reads
+ * (T_nbr_from_me as qx qy qz qw tx ty tz, Lambda 6x6 row-major; both NULL when the caller brings its own constraints).
+ * To be called again after svs_map_set / svs_map_add_keyframe. */
+int svs_map_set_graph(svs_map *h, const int *nbr_ptr, const int *nbr_id, const double *nbr_T, const double *nbr_Lambda);
+/* SlamGraph::computeInitialDoubleWin + computeActivePointsAndExtendOuterWindow (slam_graph.cpp:556-663) and the pair
+ * selection of copyContraintsToG2o (:938-981) on the device tables.  Returns the double window in ascending vertex order
+ * (the order of the reference's std::map; inner[i] = 1 for INNER frames; frames added by the outer-window extension are
+ * OUTER), the active points in ascending order, and -- when c_i is not NULL -- the constraints between window frames of
+ * which at least one is OUTER, as (c_i, c_j, T_j_from_i, Lambda) with c_i / c_j positions in window_vertex, ordered by
+ * (vertex i, vertex j).  The outputs feed svs_ba_set_problem_from_map unchanged.  SVS_ERR_INVALID if a capacity is too
+ * small (*P, *L, *C then hold the required sizes). */
+int svs_map_select_window(svs_map *h, int root, int inner_window_size, int double_window_size, int cap_P, int *P,
+                          int *window_vertex, unsigned char *inner, int cap_L, int *L, int *active_point, int cap_C, int *C,
+                          int *c_i, int *c_j, double *c_T_ji, double *c_Lambda);
+/* SlamGraph::addKeyframe (slam_graph.cpp:144-186) with addNewPointsToMap / addNewObsToOldPoints (:359-421) on the device
+ * tables: one new vertex with T_me_from_world = T_newkey_from_oldkey * T_oldkey_from_world (composed where the map lies,
+ * so a pose absorbed from the optimiser never visits the host); n_new points, each anchored in an EXISTING frame and seen
+ * by that frame (new_anchor_center at level 0, new_anchor_level) and by the new keyframe (new_center, new_level); n_track
+ * existing points gain an observation by the new keyframe.  The observation lists are rebuilt by kernels (count, scan,
+ * move); the strength bookkeeping of computeStrength / addNewEdges stays with the caller, who passes the new pose graph
+ * with svs_map_set_graph.  *vertex_index = index of the new vertex, *first_new_point = index of the first new point. */
+int svs_map_add_keyframe(svs_map *h, int oldkey, const double *T_newkey_from_oldkey, int n_new, const int *new_anchor,
+                         const double *new_xyz_anchor, const double *new_anchor_center, const int *new_anchor_level,
+                         const double *new_center, const int *new_level, int n_track, const int *track_point,
+                         const double *track_center, const int *track_level, int *vertex_index, int *first_new_point);
 /* the edge list of the last assembly (any output may be NULL); E must equal *num_edges */
 int svs_map_last_edges(svs_map *h, int E, int *e_point, int *e_pose, int *e_anchor, double *e_obs, double *e_info);
 

@@ -419,6 +419,50 @@ class DeviceMap {
   bool updatePoints(const std::vector<int>& point, const std::vector<double>& xyz_anchor) {
     return ok_ && svs_map_update_points(h_, (int)point.size(), point.data(), xyz_anchor.data()) == SVS_OK;
   }
+  // the pose graph: per vertex its neighbours, strongest first (Vertex::neighbor_ids_ordered_by_strength), and per
+  // directed entry the marginalised constraint of the edge table (both payload vectors may be empty)
+  bool setGraph(const std::vector<int>& nbr_ptr, const std::vector<int>& nbr_id, const std::vector<double>& nbr_T = {},
+                const std::vector<double>& nbr_Lambda = {}) {
+    nn_ = (int)nbr_id.size();
+    return ok_ && svs_map_set_graph(h_, nbr_ptr.data(), nbr_id.data(), nbr_T.empty() ? nullptr : nbr_T.data(),
+                                    nbr_Lambda.empty() ? nullptr : nbr_Lambda.data()) == SVS_OK;
+  }
+  // computeInitialDoubleWin + computeActivePointsAndExtendOuterWindow + the pair loop of copyContraintsToG2o
+  // (slam_graph.cpp:556-663, 938-981): what prepareForOptimization (:290-311) hands to copyDataToG2o
+  struct DoubleWindow {
+    std::vector<int> window_vertex, active_point, c_i, c_j;
+    std::vector<unsigned char> inner;
+    std::vector<double> c_T, c_Lambda;
+  };
+  bool computeDoubleWindow(int root_id, int inner_window_size, int double_window_size, DoubleWindow* w) {
+    if (!ok_) return false;
+    const int capC = nn_ > 0 ? nn_ : 1;
+    w->window_vertex.resize(V_); w->inner.resize(V_); w->active_point.resize(Np_ > 0 ? Np_ : 1);
+    w->c_i.resize(capC); w->c_j.resize(capC); w->c_T.resize(7 * (size_t)capC); w->c_Lambda.resize(36 * (size_t)capC);
+    int P = 0, L = 0, C = 0;
+    if (svs_map_select_window(h_, root_id, inner_window_size, double_window_size, V_, &P, w->window_vertex.data(), w->inner.data(),
+                              (int)w->active_point.size(), &L, w->active_point.data(), capC, &C, w->c_i.data(), w->c_j.data(),
+                              w->c_T.data(), w->c_Lambda.data()) != SVS_OK)
+      return false;
+    w->window_vertex.resize(P); w->inner.resize(P); w->active_point.resize(L);
+    w->c_i.resize(C); w->c_j.resize(C); w->c_T.resize(7 * (size_t)C); w->c_Lambda.resize(36 * (size_t)C);
+    return true;
+  }
+  // addKeyframe (slam_graph.cpp:144-186): returns the index of the new vertex, < 0 on error
+  int addKeyframe(int oldkey_id, const double T_newkey_from_oldkey[7], const std::vector<int>& new_anchor,
+                  const std::vector<double>& new_xyz_anchor, const std::vector<double>& new_anchor_center,
+                  const std::vector<int>& new_anchor_level, const std::vector<double>& new_center, const std::vector<int>& new_level,
+                  const std::vector<int>& track_point, const std::vector<double>& track_center, const std::vector<int>& track_level) {
+    if (!ok_) return SVS_ERR_NOGPU;
+    int v = -1, q = -1;
+    const int rc = svs_map_add_keyframe(h_, oldkey_id, T_newkey_from_oldkey, (int)new_anchor.size(), new_anchor.data(),
+                                        new_xyz_anchor.data(), new_anchor_center.data(), new_anchor_level.data(), new_center.data(),
+                                        new_level.data(), (int)track_point.size(), track_point.data(), track_center.data(),
+                                        track_level.data(), &v, &q);
+    if (rc != SVS_OK) return rc;
+    V_ += 1; Np_ += (int)new_anchor.size(); nn_ = 0;
+    return v;
+  }
   bool get(std::vector<double>* T_me_from_world, std::vector<double>* xyz_anchor) {
     T_me_from_world->resize(7 * (size_t)V_); xyz_anchor->resize(3 * (size_t)(Np_ > 0 ? Np_ : 1));
     const bool r = ok_ && svs_map_get(h_, T_me_from_world->data(), xyz_anchor->data()) == SVS_OK;
@@ -429,7 +473,7 @@ class DeviceMap {
  private:
   svs_map* h_ = nullptr;
   bool ok_ = false;
-  int V_ = 0, Np_ = 0;
+  int V_ = 0, Np_ = 0, nn_ = 0;
 };
 
 }  // namespace svs

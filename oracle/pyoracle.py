@@ -561,3 +561,100 @@ def copy_data_to_g2o(m, window_vertex, active_point):
     return dict(pose_qt=pose_qt, psi=np.array(psi, np.float64).reshape(-1, 3), e_point=np.array(ep, np.int32),
                 e_pose=np.array(es, np.int32), e_anchor=np.array(ea, np.int32),
                 e_obs=np.array(obs, np.float64).reshape(-1, 3), e_info=np.array(info, np.float64).reshape(-1, 3))
+
+
+# ---------------------------------------------------------------- window selection and map growth (plain Python)
+def compute_double_window(nbr_ptr, nbr_id, root, inner_window_size, double_window_size):
+    """SlamGraph::computeInitialDoubleWin (reference slam_graph.cpp:556-598): breadth-first from `root`; a vertex that
+    is popped and not yet in the window joins it (INNER while fewer than inner_window_size vertices are in, OUTER
+    afterwards) and pushes its neighbours, strongest first (nbr_id[nbr_ptr[v]:nbr_ptr[v+1]] is that order).
+    Returns {vertex: 1 (INNER) | 2 (OUTER)}.  TEST INFRASTRUCTURE ONLY."""
+    from collections import deque
+    win = {}
+    q = deque([int(root)])
+    while len(win) < double_window_size and q:
+        v = q.popleft()
+        if v in win:                                              # "Avoid cycles!"
+            continue
+        win[v] = 1 if len(win) < inner_window_size else 2
+        for i in range(nbr_ptr[v], nbr_ptr[v + 1]):
+            q.append(int(nbr_id[i]))
+    return win
+
+
+def compute_active_points(m, nbr_ptr, nbr_id, win):
+    """SlamGraph::computeActivePointsAndExtendOuterWindow (slam_graph.cpp:600-663) on the tables of synth_graph:
+    a point seen by an INNER frame is active when its anchor frame is in the window, or when that inner frame has a
+    direct edge to the anchor frame -- the anchor then joins the outer window.  Returns (sorted active point ids,
+    window dict including the extension)."""
+    edges = set()
+    for v in range(len(nbr_ptr) - 1):
+        for i in range(nbr_ptr[v], nbr_ptr[v + 1]):
+            edges.add((v, int(nbr_id[i]))); edges.add((int(nbr_id[i]), v))
+    feature_table = {}
+    for p in range(len(m["point_anchor"])):
+        for i in range(m["vis_ptr"][p], m["vis_ptr"][p + 1]):
+            feature_table.setdefault(int(m["vis_pose"][i]), []).append(p)
+    active, extend = set(), {}
+    for f in sorted(win):                                        # WindowTable is a std::map: ascending frame ids
+        if win[f] != 1:
+            continue
+        for p in feature_table.get(f, []):
+            if p in active:
+                continue
+            a = int(m["point_anchor"][p])
+            if a in win:
+                active.add(p)
+            elif (f, a) in edges:
+                active.add(p)
+                extend[a] = 2
+    out = dict(win)
+    out.update(extend)
+    return sorted(active), out
+
+
+def select_constraints(nbr_ptr, nbr_id, nbr_T, nbr_Lambda, win):
+    """The pair loop of SlamGraph::copyContraintsToG2o (slam_graph.cpp:938-981): every ordered pair (id1, id2) of window
+    frames with an edge and at least one OUTER frame gives a constraint T_2_from_1; pairs in ascending (id1, id2) order.
+    nbr_T[e] / nbr_Lambda[e] belong to the directed entry e = (v -> nbr_id[e]).  Returns (c_i, c_j, c_T, c_Lambda) with
+    c_i / c_j as positions in the ascending window list."""
+    order = sorted(win)
+    pos = {v: i for i, v in enumerate(order)}
+    ci, cj, cT, cL = [], [], [], []
+    for a in order:
+        ents = sorted((int(nbr_id[e]), e) for e in range(nbr_ptr[a], nbr_ptr[a + 1]))
+        for b, e in ents:
+            if b == a or b not in win:
+                continue
+            if win[a] == 2 or win[b] == 2:
+                ci.append(pos[a]); cj.append(pos[b]); cT.append(nbr_T[e]); cL.append(nbr_Lambda[e])
+    return (np.array(ci, np.int32), np.array(cj, np.int32), np.array(cT, np.float64).reshape(-1, 7),
+            np.array(cL, np.float64).reshape(-1, 36))
+
+
+def add_keyframe(m, oldkey, T_newkey_from_oldkey, new_anchor, new_xyz, new_anchor_center, new_anchor_level, new_center,
+                 new_level, track_point, track_center, track_level):
+    """SlamGraph::addKeyframe without the strength bookkeeping (slam_graph.cpp:144-186, 359-421): the new vertex gets
+    T_newkey_from_oldkey * T_oldkey_from_world; every new point is anchored in an existing frame and is seen by that
+    frame and by the new keyframe; tracked points gain an observation by the new keyframe.  Returns the grown tables
+    (observations of a point by ascending vertex id, as synth_graph.make_map lists them)."""
+    V, Np = len(m["poses"]), len(m["point_anchor"])
+    poses = np.vstack([m["poses"], se3_mul(T_newkey_from_oldkey, m["poses"][oldkey])[None]])
+    rows = []
+    for p in range(Np):
+        for i in range(m["vis_ptr"][p], m["vis_ptr"][p + 1]):
+            rows.append((p, int(m["vis_pose"][i]), np.asarray(m["feat_center"][i], np.float64), int(m["feat_level"][i])))
+    for t, p in enumerate(track_point):
+        rows.append((int(p), V, np.asarray(track_center[t], np.float64), int(track_level[t])))
+    for q in range(len(new_anchor)):
+        rows.append((Np + q, int(new_anchor[q]), np.asarray(new_anchor_center[q], np.float64), int(new_anchor_level[q])))
+        rows.append((Np + q, V, np.asarray(new_center[q], np.float64), int(new_level[q])))
+    rows.sort(key=lambda r: (r[0], r[1]))
+    vis_point = np.array([r[0] for r in rows])
+    Np2 = Np + len(new_anchor)
+    return dict(poses=poses, point_anchor=np.concatenate([m["point_anchor"], np.asarray(new_anchor, np.int32)]).astype(np.int32),
+                xyz_anchor=np.vstack([m["xyz_anchor"], np.asarray(new_xyz, np.float64).reshape(-1, 3)]),
+                vis_ptr=np.searchsorted(vis_point, np.arange(Np2 + 1)).astype(np.int32),
+                vis_pose=np.array([r[1] for r in rows], np.int32),
+                feat_center=np.array([r[2] for r in rows], np.float64).reshape(-1, 3),
+                feat_level=np.array([r[3] for r in rows], np.int32))

@@ -127,7 +127,8 @@ EXPORTS = [
     "svs_denseTrackingCpu",
     "svs_constraints_create", "svs_constraints_destroy", "svs_constraints_last_error", "svs_computeConstraint_batch",
     "svs_map_create", "svs_map_destroy", "svs_map_last_error", "svs_map_set", "svs_map_update_poses",
-    "svs_map_update_points", "svs_map_get", "svs_map_absorb",
+    "svs_map_update_points", "svs_map_get", "svs_map_absorb", "svs_map_set_graph", "svs_map_select_window",
+    "svs_map_add_keyframe",
     "svs_ba_set_problem_from_map", "svs_map_last_edges",
 ]
 
@@ -229,6 +230,11 @@ def lib():
     L.svs_map_update_points.argtypes = [vp, C.c_int, c_ip, c_dp]
     L.svs_map_get.argtypes = [vp, c_dp, c_dp]
     L.svs_map_absorb.argtypes = [vp, vp]
+    L.svs_map_set_graph.argtypes = [vp, c_ip, c_ip, c_dp, c_dp]
+    L.svs_map_select_window.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_up, C.c_int, c_ip, c_ip, C.c_int, c_ip,
+                                        c_ip, c_ip, c_dp, c_dp]
+    L.svs_map_add_keyframe.argtypes = [vp, C.c_int, c_dp, C.c_int, c_ip, c_dp, c_dp, c_ip, c_dp, c_ip, C.c_int, c_ip, c_dp, c_ip,
+                                       c_ip, c_ip]
     L.svs_ba_set_problem_from_map.argtypes = [vp, vp, C.c_int, c_ip, c_up, C.c_int, c_ip, C.c_int, c_ip, c_ip, c_dp, c_dp,
                                               C.POINTER(SvsCam), c_ip]
     L.svs_map_last_edges.argtypes = [vp, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp]
@@ -964,6 +970,46 @@ class DeviceMap:
     def absorb(self, ba):
         """SlamGraph::restoreDataFromG2o, device to device: the optimised window of `ba` goes back into the map."""
         self._ck(lib().svs_map_absorb(self._h, ba._h))
+
+    def set_graph(self, nbr_ptr, nbr_id, nbr_T=None, nbr_Lambda=None):
+        """The pose graph: per vertex its neighbours, strongest first; optionally the marginalised constraint of every
+        directed entry (T_nbr_from_me [7], Lambda [36])."""
+        ptr, ids = np.ascontiguousarray(nbr_ptr, np.int32), np.ascontiguousarray(nbr_id, np.int32)
+        T = None if nbr_T is None else np.ascontiguousarray(nbr_T, np.float64).reshape(-1, 7)
+        Lm = None if nbr_Lambda is None else np.ascontiguousarray(nbr_Lambda, np.float64).reshape(-1, 36)
+        self._nn = len(ids)
+        self._ck(lib().svs_map_set_graph(self._h, _ip(ptr), _ip(ids), None if T is None else _dp(T), None if Lm is None else _dp(Lm)))
+
+    def select_window(self, root, inner_window_size, double_window_size):
+        """computeInitialDoubleWin + computeActivePointsAndExtendOuterWindow + the pair selection of copyContraintsToG2o
+        on the device.  Returns dict(window_vertex, inner, active_point, c_i, c_j, c_T, c_Lambda)."""
+        capP, capL, capC = self.V, max(self.Np, 1), max(getattr(self, "_nn", 0), 1)
+        win, inner, act = np.zeros(capP, np.int32), np.zeros(capP, np.uint8), np.zeros(capL, np.int32)
+        ci, cj, cT, cL = np.zeros(capC, np.int32), np.zeros(capC, np.int32), np.zeros((capC, 7)), np.zeros((capC, 36))
+        P, L, Cn = C.c_int(), C.c_int(), C.c_int()
+        self._ck(lib().svs_map_select_window(self._h, int(root), int(inner_window_size), int(double_window_size), capP, C.byref(P),
+                                             _ip(win), inner.ctypes.data_as(c_up), capL, C.byref(L), _ip(act), capC, C.byref(Cn),
+                                             _ip(ci), _ip(cj), _dp(cT), _dp(cL)))
+        P, L, Cn = P.value, L.value, Cn.value
+        return dict(window_vertex=win[:P].copy(), inner=inner[:P].copy(), active_point=act[:L].copy(), c_i=ci[:Cn].copy(),
+                    c_j=cj[:Cn].copy(), c_T=cT[:Cn].copy(), c_Lambda=cL[:Cn].copy())
+
+    def add_keyframe(self, oldkey, T_newkey_from_oldkey, new_anchor=(), new_xyz=None, new_anchor_center=None,
+                     new_anchor_level=(), new_center=None, new_level=(), track_point=(), track_center=None, track_level=()):
+        """SlamGraph::addKeyframe on the device tables.  Returns (index of the new vertex, index of the first new point)."""
+        T = np.ascontiguousarray(T_newkey_from_oldkey, np.float64).reshape(7)
+        na = np.ascontiguousarray(new_anchor, np.int32)
+        d3 = lambda a, n: np.zeros((n, 3)) if a is None else np.ascontiguousarray(a, np.float64).reshape(n, 3)
+        nx, nac, nc = d3(new_xyz, len(na)), d3(new_anchor_center, len(na)), d3(new_center, len(na))
+        nal, nl = np.ascontiguousarray(new_anchor_level, np.int32), np.ascontiguousarray(new_level, np.int32)
+        tp = np.ascontiguousarray(track_point, np.int32)
+        tc, tl = d3(track_center, len(tp)), np.ascontiguousarray(track_level, np.int32)
+        v, q = C.c_int(), C.c_int()
+        self._ck(lib().svs_map_add_keyframe(self._h, int(oldkey), _dp(T), len(na), _ip(na), _dp(nx), _dp(nac), _ip(nal), _dp(nc),
+                                            _ip(nl), len(tp), _ip(tp), _dp(tc), _ip(tl), C.byref(v), C.byref(q)))
+        self.V += 1
+        self.Np += len(na)
+        return v.value, q.value
 
     def set_problem(self, ba, window_vertex, active_point, cam, fixed=None, c_i=(), c_j=(), c_T=None, c_Lambda=None):
         """Assembles the window on the device and loads it into `ba` (a BundleAdjuster).  Returns E."""

@@ -7,6 +7,11 @@
 // exclusive scan, emit the edges in the reference's order: active points in list order, vis_set order inside)
 // and handed to the bundle adjuster where it lies -- only the edge index triples come back to the host,
 // for the structure analysis of svs_ba_set_problem.
+//
+// Round 2 adds what surrounds the assembly: the choice of the double window from the pose graph
+// (computeInitialDoubleWin + computeActivePointsAndExtendOuterWindow, slam_graph.cpp:556-663, and the pair selection
+// of copyContraintsToG2o, :938-981) and the growth of the map by one keyframe (addKeyframe, :144-186, 359-421), both
+// on the tables where they lie.
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -16,6 +21,7 @@
 
 #include "../../include/svs_b200.h"
 #include "internal.cuh"
+#include "se3_dev.cuh"
 
 namespace {
 
@@ -128,6 +134,146 @@ __global__ void k_scatter_rows(double* __restrict__ table, const int* __restrict
   table[(size_t)width * index[i / width] + i % width] = rows[i];
 }
 
+
+// ------------------------------------------------------------------ window selection
+struct GraphDev {
+  const int* nbr_ptr;       // [V+1]
+  const int* nbr_id;        // [nnzN] neighbours of a vertex, strongest first (the order computeInitialDoubleWin pushes them)
+  const double* nbr_T;      // [nnzN][7]  T_nbr_from_me of the directed entry (or nullptr)
+  const double* nbr_Lam;    // [nnzN][36]
+};
+
+// computeInitialDoubleWin (slam_graph.cpp:556-598).  The queue discipline IS the algorithm (a vertex joins when it
+// is popped, not when it is pushed), so one thread walks it; a window is a few hundred vertices.
+__global__ void k_bfs(int V, GraphDev g, int root, int inner, int dbl, int* __restrict__ type, int* __restrict__ queue, int qcap) {
+  if (blockIdx.x || threadIdx.x) return;
+  int head = 0, tail = 0, count = 0;
+  queue[tail++] = root;
+  while (count < dbl && head < tail) {
+    const int v = queue[head++];
+    if (type[v]) continue;                       // "Avoid cycles!"
+    type[v] = count < inner ? 1 : 2;
+    ++count;
+    for (int i = g.nbr_ptr[v]; i < g.nbr_ptr[v + 1] && tail < qcap; ++i) queue[tail++] = g.nbr_id[i];
+  }
+}
+
+__device__ __forceinline__ bool has_edge(const GraphDev& g, int a, int b) {
+  for (int i = g.nbr_ptr[a]; i < g.nbr_ptr[a + 1]; ++i)
+    if (g.nbr_id[i] == b) return true;
+  for (int i = g.nbr_ptr[b]; i < g.nbr_ptr[b + 1]; ++i)
+    if (g.nbr_id[i] == a) return true;
+  return false;
+}
+
+// computeActivePointsAndExtendOuterWindow (slam_graph.cpp:600-663), one thread per map point: active when an INNER
+// frame sees it and its anchor frame is in the window, or that inner frame has an edge to the anchor frame (which then
+// joins the outer window: ext[anchor] = 1)
+__global__ void k_active(MapDev m, GraphDev g, const int* __restrict__ type, int* __restrict__ ext, int* __restrict__ active) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m.Np) return;
+  const int a = m.anchor[p];
+  const bool inwin = type[a] != 0;
+  int act = 0;
+  for (int i = m.vis_ptr[p]; i < m.vis_ptr[p + 1] && !act; ++i) {
+    const int f = m.vis_pose[i];
+    if (type[f] != 1) continue;
+    if (inwin) act = 1;
+    else if (has_edge(g, f, a)) { act = 1; ext[a] = 1; }
+  }
+  active[p] = act;
+}
+
+__global__ void k_window_flags(int V, const int* __restrict__ type, const int* __restrict__ ext, int* __restrict__ wtype,
+                               int* __restrict__ flag) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int t = type[v] ? type[v] : (ext[v] ? 2 : 0);
+  wtype[v] = t;
+  flag[v] = t != 0;
+}
+
+// out[ptr[i]] = i for flagged i (ascending: the order of a std::map / of the sorted point ids); pos[i] = ptr[i] or -1
+__global__ void k_compact(int n, const int* __restrict__ flag, const int* __restrict__ ptr, int* __restrict__ out, int* __restrict__ pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flag[i]) out[ptr[i]] = i;
+  if (pos) pos[i] = flag[i] ? ptr[i] : -1;
+}
+
+// the pair loop of copyContraintsToG2o (slam_graph.cpp:938-981) over the directed neighbour entries
+__device__ __forceinline__ bool pair_selected(const int* wtype, int a, int b) {
+  return b != a && wtype[a] && wtype[b] && (wtype[a] == 2 || wtype[b] == 2);
+}
+__global__ void k_pair_count(int V, GraphDev g, const int* __restrict__ wtype, int* __restrict__ cnt) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= V) return;
+  int c = 0;
+  for (int i = g.nbr_ptr[a]; i < g.nbr_ptr[a + 1]; ++i) c += pair_selected(wtype, a, g.nbr_id[i]);
+  cnt[a] = c;
+}
+__global__ void k_pair_emit(int V, GraphDev g, const int* __restrict__ wtype, const int* __restrict__ win_pos,
+                            const int* __restrict__ ptr, int* __restrict__ c_i, int* __restrict__ c_j, double* __restrict__ c_T,
+                            double* __restrict__ c_Lam) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= V) return;
+  for (int i = g.nbr_ptr[a]; i < g.nbr_ptr[a + 1]; ++i) {
+    const int b = g.nbr_id[i];
+    if (!pair_selected(wtype, a, b)) continue;
+    int rank = 0;   // ascending id2 inside id1 (the inner loop of the reference runs over a std::map)
+    for (int k = g.nbr_ptr[a]; k < g.nbr_ptr[a + 1]; ++k) rank += pair_selected(wtype, a, g.nbr_id[k]) && g.nbr_id[k] < b;
+    const int at = ptr[a] + rank;
+    c_i[at] = win_pos[a]; c_j[at] = win_pos[b];
+    for (int q = 0; q < 7; ++q) c_T[7 * (size_t)at + q] = g.nbr_T ? g.nbr_T[7 * (size_t)i + q] : (q == 3 ? 1. : 0.);
+    for (int q = 0; q < 36; ++q) c_Lam[36 * (size_t)at + q] = g.nbr_Lam ? g.nbr_Lam[36 * (size_t)i + q] : 0.;
+  }
+}
+
+// ------------------------------------------------------------------ growth by one keyframe
+// T_new = T_newkey_from_oldkey * T_oldkey_from_world (slam_graph.cpp:153-156)
+__global__ void k_new_pose(const double* __restrict__ old_pose, int oldkey, const double* __restrict__ T_rel, double* __restrict__ out) {
+  if (blockIdx.x || threadIdx.x) return;
+  double A[7], B[7], AB[7];
+  for (int q = 0; q < 7; ++q) { A[q] = T_rel[q]; B[q] = old_pose[7 * (size_t)oldkey + q]; }
+  svs::se3_mul(A, B, AB);
+  for (int q = 0; q < 7; ++q) out[q] = AB[q];
+}
+__global__ void k_grow_count(int Np_old, int Np_new, const int* __restrict__ old_ptr, const int* __restrict__ add_idx, int* __restrict__ cnt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Np_new) return;
+  cnt[p] = p < Np_old ? old_ptr[p + 1] - old_ptr[p] + (add_idx[p] >= 0) : 2;
+}
+__global__ void k_mark_tracks(int n, const int* __restrict__ track_point, int* __restrict__ add_idx) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) add_idx[track_point[t]] = t;
+}
+// one thread per point moves its observations to their new place and appends the new keyframe's (its id is the
+// largest, so it is the last of the point's ascending list); a new point is seen by its anchor frame and the keyframe
+__global__ void k_grow_move(MapDev m, int Np_new, int newkey, const int* __restrict__ add_idx, const int* __restrict__ new_ptr,
+                            const double* __restrict__ track_center, const int* __restrict__ track_level,
+                            const int* __restrict__ new_anchor, const double* __restrict__ new_anchor_center,
+                            const int* __restrict__ new_anchor_level, const double* __restrict__ new_center,
+                            const int* __restrict__ new_level, int* __restrict__ vis_pose, double* __restrict__ center,
+                            int* __restrict__ level) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Np_new) return;
+  int at = new_ptr[p];
+  auto put = [&](int v, const double* c, int l) {
+    vis_pose[at] = v; level[at] = l;
+    center[3 * (size_t)at] = c[0]; center[3 * (size_t)at + 1] = c[1]; center[3 * (size_t)at + 2] = c[2];
+    ++at;
+  };
+  if (p < m.Np) {
+    for (int i = m.vis_ptr[p]; i < m.vis_ptr[p + 1]; ++i) put(m.vis_pose[i], m.center + 3 * (size_t)i, m.level[i]);
+    const int t = add_idx[p];
+    if (t >= 0) put(newkey, track_center + 3 * (size_t)t, track_level[t]);
+  } else {
+    const int q = p - m.Np;
+    put(new_anchor[q], new_anchor_center + 3 * (size_t)q, new_anchor_level[q]);
+    put(newkey, new_center + 3 * (size_t)q, new_level[q]);
+  }
+}
+
 }  // namespace
 
 struct svs_map {
@@ -144,6 +290,8 @@ struct svs_map {
   int last_E = 0;
   const int* d_win_last = nullptr; const int* d_act_last = nullptr; int last_P = 0, last_L = 0;   // the last assembled window
   char* d_upd = nullptr; size_t upd_cap = 0;   // staging of svs_map_update_*
+  char* d_graph = nullptr; size_t graph_cap = 0; GraphDev g{}; int nnzN = 0;   // svs_map_set_graph
+  char* d_sel = nullptr; size_t sel_cap = 0;   // work buffers of svs_map_select_window
 };
 
 #define GCK(call)                                                       \
@@ -156,6 +304,29 @@ struct svs_map {
   } while (0)
 
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct MapLayout { size_t o_pose, o_anch, o_xyz, o_vptr, o_vpose, o_cen, o_lvl, total; };
+static MapLayout map_layout(int V, int Np, int nnz) {
+  MapLayout lo{};
+  size_t off = 0;
+  lo.o_pose = off; off += al256(sizeof(double) * 7 * (size_t)V);
+  lo.o_anch = off; off += al256(sizeof(int) * (size_t)std::max(Np, 1));
+  lo.o_xyz = off; off += al256(sizeof(double) * 3 * (size_t)std::max(Np, 1));
+  lo.o_vptr = off; off += al256(sizeof(int) * ((size_t)Np + 1));
+  lo.o_vpose = off; off += al256(sizeof(int) * (size_t)std::max(nnz, 1));
+  lo.o_cen = off; off += al256(sizeof(double) * 3 * (size_t)std::max(nnz, 1));
+  lo.o_lvl = off; off += al256(sizeof(int) * (size_t)std::max(nnz, 1));
+  lo.total = off;
+  return lo;
+}
+static void map_bind(svs_map* h, char* B, const MapLayout& lo, int V, int Np, int nnz) {
+  h->V = V; h->Np = Np; h->nnz = nnz;
+  h->m.V = V; h->m.Np = Np;
+  h->m.pose = reinterpret_cast<const double*>(B + lo.o_pose); h->m.anchor = reinterpret_cast<const int*>(B + lo.o_anch);
+  h->m.xyz = reinterpret_cast<const double*>(B + lo.o_xyz); h->m.vis_ptr = reinterpret_cast<const int*>(B + lo.o_vptr);
+  h->m.vis_pose = reinterpret_cast<const int*>(B + lo.o_vpose); h->m.center = reinterpret_cast<const double*>(B + lo.o_cen);
+  h->m.level = reinterpret_cast<const int*>(B + lo.o_lvl);
+}
 
 extern "C" {
 
@@ -179,7 +350,7 @@ void svs_map_destroy(svs_map* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_map); cudaFree(h->d_work); cudaFree(h->d_upd);
+  cudaFree(h->d_map); cudaFree(h->d_work); cudaFree(h->d_upd); cudaFree(h->d_graph); cudaFree(h->d_sel);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -201,14 +372,10 @@ int svs_map_set(svs_map* h, int V, const double* T_me_from_world, int Np, const 
       return SVS_ERR_INVALID;
     }
   cudaSetDevice(h->device);
-  size_t off = 0;
-  const size_t o_pose = off; off += al256(sizeof(double) * 7 * (size_t)V);
-  const size_t o_anch = off; off += al256(sizeof(int) * (size_t)std::max(Np, 1));
-  const size_t o_xyz = off; off += al256(sizeof(double) * 3 * (size_t)std::max(Np, 1));
-  const size_t o_vptr = off; off += al256(sizeof(int) * ((size_t)Np + 1));
-  const size_t o_vpose = off; off += al256(sizeof(int) * (size_t)std::max(nnz, 1));
-  const size_t o_cen = off; off += al256(sizeof(double) * 3 * (size_t)std::max(nnz, 1));
-  const size_t o_lvl = off; off += al256(sizeof(int) * (size_t)std::max(nnz, 1));
+  const MapLayout lo = map_layout(V, Np, nnz);
+  const size_t off = lo.total;
+  const size_t o_pose = lo.o_pose, o_anch = lo.o_anch, o_xyz = lo.o_xyz, o_vptr = lo.o_vptr, o_vpose = lo.o_vpose, o_cen = lo.o_cen,
+               o_lvl = lo.o_lvl;
   GCK(cudaStreamSynchronize(h->stream));
   if (off > h->map_cap) {
     cudaFree(h->d_map); h->d_map = nullptr; h->map_cap = 0;
@@ -228,12 +395,8 @@ int svs_map_set(svs_map* h, int V, const double* T_me_from_world, int Np, const 
     GCK(cudaMemcpyAsync(B + o_lvl, feat_level, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
   }
   GCK(cudaStreamSynchronize(h->stream));
-  h->V = V; h->Np = Np; h->nnz = nnz;
-  h->m.V = V; h->m.Np = Np;
-  h->m.pose = reinterpret_cast<const double*>(B + o_pose); h->m.anchor = reinterpret_cast<const int*>(B + o_anch);
-  h->m.xyz = reinterpret_cast<const double*>(B + o_xyz); h->m.vis_ptr = reinterpret_cast<const int*>(B + o_vptr);
-  h->m.vis_pose = reinterpret_cast<const int*>(B + o_vpose); h->m.center = reinterpret_cast<const double*>(B + o_cen);
-  h->m.level = reinterpret_cast<const int*>(B + o_lvl);
+  map_bind(h, B, lo, V, Np, nnz);
+  h->g = GraphDev{}; h->nnzN = 0;   // a new map: its pose graph comes with svs_map_set_graph
   return SVS_OK;
 }
 
@@ -377,6 +540,199 @@ int svs_ba_set_problem_from_map(svs_ba* ba, svs_map* h, int P, const int* window
                                                 h->h_ea.data(), d_oi, C, c_i, c_j, c_T, c_Lambda, cam);
   if (rc != SVS_OK) h->err = std::string("svs_ba_set_problem: ") + svs_last_error(ba);
   return rc;
+}
+
+
+// ------------------------------------------------------------------ pose graph, window selection, growth
+
+int svs_map_set_graph(svs_map* h, const int* nbr_ptr, const int* nbr_id, const double* nbr_T, const double* nbr_Lambda) {
+  if (!h || !h->d_map || !nbr_ptr) return SVS_ERR_INVALID;
+  const int V = h->V, nn = nbr_ptr[V];
+  if (nbr_ptr[0] != 0 || nn < 0 || (nn && !nbr_id) || ((nbr_T == nullptr) != (nbr_Lambda == nullptr))) return SVS_ERR_INVALID;
+  for (int v = 0; v < V; ++v)
+    if (nbr_ptr[v + 1] < nbr_ptr[v]) { h->err = "nbr_ptr not ascending"; return SVS_ERR_INVALID; }
+  for (int i = 0; i < nn; ++i)
+    if (nbr_id[i] < 0 || nbr_id[i] >= V) { h->err = "neighbour outside [0, V)"; return SVS_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  size_t off = 0;
+  const size_t o_ptr = off; off += al256(sizeof(int) * ((size_t)V + 1));
+  const size_t o_id = off; off += al256(sizeof(int) * (size_t)std::max(nn, 1));
+  const size_t o_T = off; off += al256(sizeof(double) * 7 * (size_t)std::max(nn, 1));
+  const size_t o_L = off; off += al256(sizeof(double) * 36 * (size_t)std::max(nn, 1));
+  GCK(cudaStreamSynchronize(h->stream));
+  if (off > h->graph_cap) {
+    cudaFree(h->d_graph); h->d_graph = nullptr; h->graph_cap = 0;
+    GCK(cudaMalloc(&h->d_graph, off + off / 4));
+    h->graph_cap = off + off / 4;
+  }
+  char* B = h->d_graph;
+  GCK(cudaMemcpyAsync(B + o_ptr, nbr_ptr, sizeof(int) * ((size_t)V + 1), cudaMemcpyHostToDevice, h->stream));
+  if (nn) {
+    GCK(cudaMemcpyAsync(B + o_id, nbr_id, sizeof(int) * (size_t)nn, cudaMemcpyHostToDevice, h->stream));
+    if (nbr_T) {
+      GCK(cudaMemcpyAsync(B + o_T, nbr_T, sizeof(double) * 7 * (size_t)nn, cudaMemcpyHostToDevice, h->stream));
+      GCK(cudaMemcpyAsync(B + o_L, nbr_Lambda, sizeof(double) * 36 * (size_t)nn, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  GCK(cudaStreamSynchronize(h->stream));
+  h->g.nbr_ptr = reinterpret_cast<const int*>(B + o_ptr); h->g.nbr_id = reinterpret_cast<const int*>(B + o_id);
+  h->g.nbr_T = nbr_T ? reinterpret_cast<const double*>(B + o_T) : nullptr;
+  h->g.nbr_Lam = nbr_T ? reinterpret_cast<const double*>(B + o_L) : nullptr;
+  h->nnzN = nn;
+  return SVS_OK;
+}
+
+int svs_map_select_window(svs_map* h, int root, int inner_window_size, int double_window_size, int cap_P, int* P_out,
+                          int* window_vertex, unsigned char* inner, int cap_L, int* L_out, int* active_point, int cap_C,
+                          int* C_out, int* c_i, int* c_j, double* c_T, double* c_Lambda) {
+  if (!h || !h->d_map || !P_out || !window_vertex || !L_out || (cap_L && !active_point) || cap_P <= 0 || cap_L < 0 || cap_C < 0)
+    return SVS_ERR_INVALID;
+  if (!h->g.nbr_ptr) { h->err = "svs_map_set_graph has not been called for this map"; return SVS_ERR_STATE; }
+  const int V = h->V, Np = h->Np, nn = h->nnzN;
+  if (root < 0 || root >= V || inner_window_size < 0 || inner_window_size >= double_window_size) {   // assert at slam_graph.cpp:563
+    h->err = "root outside [0, V) or inner_window_size >= double_window_size";
+    return SVS_ERR_INVALID;
+  }
+  cudaSetDevice(h->device);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += al256(bytes); return o; };
+  const size_t o_type = take(sizeof(int) * V), o_ext = take(sizeof(int) * V), o_wtype = take(sizeof(int) * V);
+  const size_t o_flag = take(sizeof(int) * V), o_ptrV = take(sizeof(int) * ((size_t)V + 1)), o_win = take(sizeof(int) * V);
+  const size_t o_pos = take(sizeof(int) * V), o_act = take(sizeof(int) * (size_t)std::max(Np, 1));
+  const size_t o_ptrP = take(sizeof(int) * ((size_t)Np + 1)), o_actl = take(sizeof(int) * (size_t)std::max(Np, 1));
+  const size_t o_q = take(sizeof(int) * ((size_t)nn + 1)), o_cc = take(sizeof(int) * V), o_cp = take(sizeof(int) * ((size_t)V + 1));
+  const size_t o_ci = take(sizeof(int) * (size_t)std::max(nn, 1)), o_cj = take(sizeof(int) * (size_t)std::max(nn, 1));
+  const size_t o_cT = take(sizeof(double) * 7 * (size_t)std::max(nn, 1)), o_cL = take(sizeof(double) * 36 * (size_t)std::max(nn, 1));
+  GCK(cudaStreamSynchronize(h->stream));
+  if (off > h->sel_cap) {
+    cudaFree(h->d_sel); h->d_sel = nullptr; h->sel_cap = 0;
+    GCK(cudaMalloc(&h->d_sel, off + off / 4));
+    h->sel_cap = off + off / 4;
+  }
+  char* W = h->d_sel;
+  auto I = [&](size_t o) { return reinterpret_cast<int*>(W + o); };
+  GCK(cudaMemsetAsync(I(o_type), 0, sizeof(int) * V, h->stream));
+  GCK(cudaMemsetAsync(I(o_ext), 0, sizeof(int) * V, h->stream));
+  const int bV = (V + 255) / 256, bP = (std::max(Np, 1) + 255) / 256;
+  k_bfs<<<1, 32, 0, h->stream>>>(V, h->g, root, inner_window_size, double_window_size, I(o_type), I(o_q), nn + 1);
+  if (Np) k_active<<<bP, 256, 0, h->stream>>>(h->m, h->g, I(o_type), I(o_ext), I(o_act));
+  k_window_flags<<<bV, 256, 0, h->stream>>>(V, I(o_type), I(o_ext), I(o_wtype), I(o_flag));
+  k_scan<<<1, 1024, 0, h->stream>>>(I(o_flag), V, I(o_ptrV));
+  k_compact<<<bV, 256, 0, h->stream>>>(V, I(o_flag), I(o_ptrV), I(o_win), I(o_pos));
+  if (Np) {
+    k_scan<<<1, 1024, 0, h->stream>>>(I(o_act), Np, I(o_ptrP));
+    k_compact<<<bP, 256, 0, h->stream>>>(Np, I(o_act), I(o_ptrP), I(o_actl), nullptr);
+  }
+  k_pair_count<<<bV, 256, 0, h->stream>>>(V, h->g, I(o_wtype), I(o_cc));
+  k_scan<<<1, 1024, 0, h->stream>>>(I(o_cc), V, I(o_cp));
+  k_pair_emit<<<bV, 256, 0, h->stream>>>(V, h->g, I(o_wtype), I(o_pos), I(o_cp), I(o_ci), I(o_cj),
+                                        reinterpret_cast<double*>(W + o_cT), reinterpret_cast<double*>(W + o_cL));
+  GCK(cudaGetLastError());
+  int P = 0, L = 0, C = 0;
+  GCK(cudaMemcpyAsync(&P, I(o_ptrV) + V, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (Np) GCK(cudaMemcpyAsync(&L, I(o_ptrP) + Np, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  GCK(cudaMemcpyAsync(&C, I(o_cp) + V, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  GCK(cudaStreamSynchronize(h->stream));
+  *P_out = P; *L_out = L;
+  if (C_out) *C_out = C;
+  if (P > cap_P || L > cap_L || (c_i && C > cap_C)) { h->err = "window, active points or constraints exceed the caller's capacity"; return SVS_ERR_INVALID; }
+  GCK(cudaMemcpyAsync(window_vertex, I(o_win), sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost, h->stream));
+  if (L) GCK(cudaMemcpyAsync(active_point, I(o_actl), sizeof(int) * (size_t)L, cudaMemcpyDeviceToHost, h->stream));
+  h->h_winpos.resize(V);
+  GCK(cudaMemcpyAsync(h->h_winpos.data(), I(o_wtype), sizeof(int) * (size_t)V, cudaMemcpyDeviceToHost, h->stream));
+  if (c_i && C) {
+    if (!c_j || !c_T || !c_Lambda) return SVS_ERR_INVALID;
+    GCK(cudaMemcpyAsync(c_i, I(o_ci), sizeof(int) * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
+    GCK(cudaMemcpyAsync(c_j, I(o_cj), sizeof(int) * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
+    GCK(cudaMemcpyAsync(c_T, W + o_cT, sizeof(double) * 7 * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
+    GCK(cudaMemcpyAsync(c_Lambda, W + o_cL, sizeof(double) * 36 * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
+  }
+  GCK(cudaStreamSynchronize(h->stream));
+  if (inner)
+    for (int i = 0; i < P; ++i) inner[i] = h->h_winpos[window_vertex[i]] == 1;
+  return SVS_OK;
+}
+
+int svs_map_add_keyframe(svs_map* h, int oldkey, const double* T_newkey_from_oldkey, int n_new, const int* new_anchor,
+                         const double* new_xyz_anchor, const double* new_anchor_center, const int* new_anchor_level,
+                         const double* new_center, const int* new_level, int n_track, const int* track_point,
+                         const double* track_center, const int* track_level, int* vertex_index, int* first_new_point) {
+  if (!h || !h->d_map || !T_newkey_from_oldkey || n_new < 0 || n_track < 0 ||
+      (n_new && (!new_anchor || !new_xyz_anchor || !new_anchor_center || !new_anchor_level || !new_center || !new_level)) ||
+      (n_track && (!track_point || !track_center || !track_level)))
+    return SVS_ERR_INVALID;
+  const int V = h->V, Np = h->Np, nnz = h->nnz;
+  if (oldkey < 0 || oldkey >= V) { h->err = "oldkey outside [0, V)"; return SVS_ERR_INVALID; }
+  for (int q = 0; q < n_new; ++q)
+    if (new_anchor[q] < 0 || new_anchor[q] >= V || new_anchor_level[q] < 0 || new_anchor_level[q] > 30 || new_level[q] < 0 || new_level[q] > 30) {
+      h->err = "new point anchored outside [0, V) or bad pyramid level";
+      return SVS_ERR_INVALID;
+    }
+  {
+    std::vector<int> tp(track_point, track_point + n_track);
+    std::sort(tp.begin(), tp.end());
+    for (int t = 0; t < n_track; ++t)
+      if (tp[t] < 0 || tp[t] >= Np || (t && tp[t] == tp[t - 1]) || track_level[t] < 0 || track_level[t] > 30) {
+        h->err = "tracked point outside [0, Np), listed twice, or bad pyramid level";
+        return SVS_ERR_INVALID;
+      }
+  }
+  cudaSetDevice(h->device);
+  GCK(cudaStreamSynchronize(h->stream));
+  const int V2 = V + 1, Np2 = Np + n_new, nnz2 = nnz + n_track + 2 * n_new;
+  const MapLayout lo = map_layout(V2, Np2, nnz2);
+  char* B2 = nullptr;
+  GCK(cudaMalloc(&B2, lo.total + lo.total / 4));
+  // staging: everything the kernels read from the caller, in one pinned-less copy (keyframe rate, a few 10 KB)
+  std::vector<char> st;
+  auto push = [&](const void* src, size_t bytes) { const size_t o = st.size(); st.resize(o + al256(bytes)); if (bytes) memcpy(st.data() + o, src, bytes); return o; };
+  const size_t s_T = push(T_newkey_from_oldkey, sizeof(double) * 7);
+  const size_t s_na = push(new_anchor, sizeof(int) * (size_t)n_new), s_nx = push(new_xyz_anchor, sizeof(double) * 3 * (size_t)n_new);
+  const size_t s_nac = push(new_anchor_center, sizeof(double) * 3 * (size_t)n_new), s_nal = push(new_anchor_level, sizeof(int) * (size_t)n_new);
+  const size_t s_nc = push(new_center, sizeof(double) * 3 * (size_t)n_new), s_nl = push(new_level, sizeof(int) * (size_t)n_new);
+  const size_t s_tp = push(track_point, sizeof(int) * (size_t)n_track), s_tc = push(track_center, sizeof(double) * 3 * (size_t)n_track);
+  const size_t s_tl = push(track_level, sizeof(int) * (size_t)n_track);
+  const size_t s_add = st.size(); st.resize(s_add + al256(sizeof(int) * (size_t)Np2));
+  const size_t s_cnt = st.size(); st.resize(s_cnt + al256(sizeof(int) * (size_t)Np2));
+  if (st.size() > h->upd_cap) {
+    cudaFree(h->d_upd); h->d_upd = nullptr; h->upd_cap = 0;
+    if (cudaMalloc(&h->d_upd, 2 * st.size()) != cudaSuccess) { cudaFree(B2); h->err = "cudaMalloc"; return SVS_ERR_CUDA; }
+    h->upd_cap = 2 * st.size();
+  }
+  char* U = h->d_upd;
+  cudaError_t e = cudaMemcpyAsync(U, st.data(), s_add, cudaMemcpyHostToDevice, h->stream);
+  auto D = [&](size_t o) { return reinterpret_cast<double*>(U + o); };
+  auto Ii = [&](size_t o) { return reinterpret_cast<int*>(U + o); };
+  if (e == cudaSuccess) e = cudaMemsetAsync(U + s_add, 0xff, sizeof(int) * (size_t)Np2, h->stream);
+  // vertices
+  if (e == cudaSuccess) e = cudaMemcpyAsync(B2 + lo.o_pose, h->m.pose, sizeof(double) * 7 * (size_t)V, cudaMemcpyDeviceToDevice, h->stream);
+  k_new_pose<<<1, 32, 0, h->stream>>>(h->m.pose, oldkey, D(s_T), reinterpret_cast<double*>(B2 + lo.o_pose) + 7 * (size_t)V);
+  // points
+  if (Np && e == cudaSuccess) e = cudaMemcpyAsync(B2 + lo.o_anch, h->m.anchor, sizeof(int) * (size_t)Np, cudaMemcpyDeviceToDevice, h->stream);
+  if (Np && e == cudaSuccess) e = cudaMemcpyAsync(B2 + lo.o_xyz, h->m.xyz, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToDevice, h->stream);
+  if (n_new && e == cudaSuccess) e = cudaMemcpyAsync(B2 + lo.o_anch + sizeof(int) * (size_t)Np, U + s_na, sizeof(int) * (size_t)n_new, cudaMemcpyDeviceToDevice, h->stream);
+  if (n_new && e == cudaSuccess) e = cudaMemcpyAsync(B2 + lo.o_xyz + sizeof(double) * 3 * (size_t)Np, U + s_nx, sizeof(double) * 3 * (size_t)n_new, cudaMemcpyDeviceToDevice, h->stream);
+  // observations
+  if (Np2) {
+    if (n_track) k_mark_tracks<<<(n_track + 255) / 256, 256, 0, h->stream>>>(n_track, Ii(s_tp), Ii(s_add));
+    k_grow_count<<<(Np2 + 255) / 256, 256, 0, h->stream>>>(Np, Np2, h->m.vis_ptr, Ii(s_add), Ii(s_cnt));
+    k_scan<<<1, 1024, 0, h->stream>>>(Ii(s_cnt), Np2, reinterpret_cast<int*>(B2 + lo.o_vptr));
+    k_grow_move<<<(Np2 + 255) / 256, 256, 0, h->stream>>>(h->m, Np2, V, Ii(s_add), reinterpret_cast<const int*>(B2 + lo.o_vptr), D(s_tc),
+                                                        Ii(s_tl), Ii(s_na), D(s_nac), Ii(s_nal), D(s_nc), Ii(s_nl),
+                                                        reinterpret_cast<int*>(B2 + lo.o_vpose), reinterpret_cast<double*>(B2 + lo.o_cen),
+                                                        reinterpret_cast<int*>(B2 + lo.o_lvl));
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { cudaFree(B2); h->err = std::string("svs_map_add_keyframe: ") + cudaGetErrorString(e); return SVS_ERR_CUDA; }
+  cudaFree(h->d_map);
+  h->d_map = B2; h->map_cap = lo.total + lo.total / 4;
+  map_bind(h, B2, lo, V2, Np2, nnz2);
+  h->g = GraphDev{}; h->nnzN = 0;          // the pose graph changed with the new vertex: svs_map_set_graph again
+  h->d_win_last = nullptr;                 // (a window assembled before the growth can no longer be absorbed)
+  if (vertex_index) *vertex_index = V;
+  if (first_new_point) *first_new_point = Np;
+  return SVS_OK;
 }
 
 // the assembled edge list of the last svs_ba_set_problem_from_map, for inspection

@@ -56,3 +56,47 @@ def make_map(pb, extra_vertices=4, extra_points=10, seed=0):
              vis_pose=np.array([r[1] for r in rows], np.int32), feat_center=np.array([r[2] for r in rows], np.float64),
              feat_level=np.array([r[3] for r in rows], np.int32))
     return m, window_vertex, active_point
+
+
+def make_pose_graph(m, max_neighbours=6, seed=0, with_constraints=True):
+    """A pose graph over the vertices of `m` in the form SlamGraph keeps it: two frames are neighbours when they share
+    points; Vertex::neighbor_ids_ordered_by_strength holds ONE neighbour per strength value (it is a std::map keyed by
+    the strength), visited from the strongest (reference slam_graph.hpp:88-99, slam_graph.cpp:584-590).  Returns
+    (nbr_ptr, nbr_id, nbr_T, nbr_Lambda): symmetric lists, per directed entry a relative pose and an information matrix."""
+    rng = np.random.default_rng(seed)
+    V, Np = len(m["poses"]), len(m["point_anchor"])
+    strength = {}
+    for p in range(Np):
+        obs = m["vis_pose"][m["vis_ptr"][p]:m["vis_ptr"][p + 1]]
+        for i in range(len(obs)):
+            for j in range(i + 1, len(obs)):
+                a, b = int(obs[i]), int(obs[j])
+                if a != b:
+                    strength[(min(a, b), max(a, b))] = strength.get((min(a, b), max(a, b)), 0) + 1
+    cand = [dict() for _ in range(V)]
+    for (a, b), s in strength.items():
+        cand[a][b] = s; cand[b][a] = s
+    keep = set()
+    for v in range(V):
+        by_strength = {}
+        for b in sorted(cand[v]):                                  # one neighbour per strength value (std::map<int,int>)
+            by_strength[cand[v][b]] = b
+        for s in sorted(by_strength, reverse=True)[:max_neighbours]:
+            keep.add((min(v, by_strength[s]), max(v, by_strength[s])))
+    nbrs = [[] for _ in range(V)]
+    for a, b in keep:
+        nbrs[a].append((strength[(a, b)], b)); nbrs[b].append((strength[(a, b)], a))
+    nbr_ptr, nbr_id = [0], []
+    for v in range(V):
+        for s, b in sorted(nbrs[v], key=lambda t: (-t[0], t[1])):  # strongest first
+            nbr_id.append(b)
+        nbr_ptr.append(len(nbr_id))
+    nbr_ptr, nbr_id = np.array(nbr_ptr, np.int32), np.array(nbr_id, np.int32)
+    if not with_constraints:
+        return nbr_ptr, nbr_id, None, None
+    n = len(nbr_id)
+    q = rng.normal(0, 1, (n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    nbr_T = np.concatenate([q, rng.normal(0, 1, (n, 3))], 1)
+    A = rng.normal(0, 1, (n, 6, 6))
+    nbr_L = (A @ A.transpose(0, 2, 1) + 6 * np.eye(6)).reshape(n, 36)
+    return nbr_ptr, nbr_id, nbr_T, nbr_L

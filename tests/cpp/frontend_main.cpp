@@ -112,12 +112,35 @@ int main(int argc, char** argv) {
   std::vector<double> o_pose, o_xyz;
   if (!dm.get(&o_pose, &o_xyz)) return 8;
 
+  // window selection from the pose graph (a ring over the vertices) and growth by one keyframe, on the device tables
+  const int Vm = (int)(m_pose.size() / 7);
+  std::vector<int> nbr_ptr(Vm + 1), nbr_id;
+  for (int v = 0; v < Vm; ++v) {
+    nbr_ptr[v] = (int)nbr_id.size();
+    nbr_id.push_back((v + 1) % Vm); nbr_id.push_back((v + Vm - 1) % Vm);
+  }
+  nbr_ptr[Vm] = (int)nbr_id.size();
+  if (!dm.setGraph(nbr_ptr, nbr_id)) return 9;
+  svs::DeviceMap::DoubleWindow dw;
+  if (!dm.computeDoubleWindow(win[0], 3, 6, &dw)) { fprintf(stderr, "%s\n", dm.last_error()); return 9; }
+  const double T_rel[7] = {0, 0, 0, 1, 0.25, -0.5, 0.125};
+  std::vector<int> tracked = {0, 1, 2, 3, 4}, tlevel = {0, 1, 0, 1, 0};
+  std::vector<double> tcenter(15, 100.);
+  const int newv = dm.addKeyframe(win[1], T_rel, {}, {}, {}, {}, {}, {}, tracked, tcenter, tlevel);
+  if (newv != Vm) { fprintf(stderr, "%s\n", dm.last_error()); return 9; }
+  std::vector<double> g_pose, g_xyz;
+  if (!dm.get(&g_pose, &g_xyz)) return 9;
+  std::vector<double> new_pose(g_pose.end() - 7, g_pose.end());
+
   FILE* o = fopen(argv[2], "wb");
   std::vector<int> counts = {(int)(xy[0].size() / 2), (int)(xy[1].size() / 2), (int)ap.size(), nm, E, ost.num_obs};
   wr(o, counts); wr(o, xy[0]); wr(o, xy[1]);
   std::vector<int> midx(track.size());
   for (size_t i = 0; i < track.size(); ++i) midx[i] = track[i].matched ? track[i].index : -1;
   wr(o, midx); wr(o, T_track); wr(o, T_pose); wr(o, o_pose); wr(o, o_xyz);
+  std::vector<int> counts2 = {(int)dw.window_vertex.size(), (int)dw.active_point.size(), (int)dw.c_i.size(), newv};
+  std::vector<int> inner_i(dw.inner.begin(), dw.inner.end());
+  wr(o, counts2); wr(o, dw.window_vertex); wr(o, inner_i); wr(o, dw.active_point); wr(o, dw.c_i); wr(o, dw.c_j); wr(o, new_pose);
   fclose(o);
   printf("OK corners=%d/%d candidates=%d matched=%d edges=%d\n", counts[0], counts[1], counts[2], nm, E);
   return 0;

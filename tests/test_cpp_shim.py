@@ -158,6 +158,13 @@ def test_cpp_frontend_and_map_wrappers_equal_the_c_abi(svs, tmp_path):
     assert ba.optimize(2)[0] == 2
     dm.absorb(ba)
     mp, mx = dm.get()
+    Vm = len(m["poses"])
+    ring = np.stack([(np.arange(Vm) + 1) % Vm, (np.arange(Vm) + Vm - 1) % Vm], 1).astype(np.int32)
+    dm.set_graph(np.arange(0, 2 * Vm + 1, 2, dtype=np.int32), ring.reshape(-1))
+    sel = dm.select_window(int(win[0]), 3, 6)
+    newv, _ = dm.add_keyframe(int(win[1]), [0, 0, 0, 1, 0.25, -0.5, 0.125], track_point=[0, 1, 2, 3, 4],
+                              track_center=np.full((5, 3), 100.0), track_level=[0, 1, 0, 1, 0])
+    new_pose = dm.get()[0][-1]
 
     with open(tmp_path / "out.bin", "rb") as f:
         cnt = np.fromfile(f, np.int32, 6)
@@ -167,6 +174,10 @@ def test_cpp_frontend_and_map_wrappers_equal_the_c_abi(svs, tmp_path):
         c_track, c_pose = np.fromfile(f, np.float64, 7), np.fromfile(f, np.float64, 7)
         c_mp = np.fromfile(f, np.float64, mp.size).reshape(mp.shape)
         c_mx = np.fromfile(f, np.float64, mx.size).reshape(mx.shape)
+        cnt2 = np.fromfile(f, np.int32, 4)
+        c_win, c_inner, c_act = np.fromfile(f, np.int32, cnt2[0]), np.fromfile(f, np.int32, cnt2[0]), np.fromfile(f, np.int32, cnt2[1])
+        c_ci, c_cj = np.fromfile(f, np.int32, cnt2[2]), np.fromfile(f, np.int32, cnt2[2])
+        c_new_pose = np.fromfile(f, np.float64, 7)
     np.testing.assert_array_equal(c_xy0, xy0); np.testing.assert_array_equal(c_xy1, xy1)
     assert cnt[2] == len(pts) and cnt[3] == int(res["matched"].sum()) and cnt[4] == E and cnt[3] > 50
     np.testing.assert_array_equal(c_midx, np.where(res["matched"] == 1, res["index"], -1))
@@ -174,3 +185,8 @@ def test_cpp_frontend_and_map_wrappers_equal_the_c_abi(svs, tmp_path):
     np.testing.assert_array_equal(c_pose, T_pose)
     np.testing.assert_allclose(c_mp, mp, rtol=1e-9, atol=1e-12)     # FP64 atomics in the Schur scatter
     np.testing.assert_allclose(c_mx, mx, rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(c_win, sel["window_vertex"]); np.testing.assert_array_equal(c_inner, sel["inner"])
+    np.testing.assert_array_equal(c_act, sel["active_point"])
+    np.testing.assert_array_equal(c_ci, sel["c_i"]); np.testing.assert_array_equal(c_cj, sel["c_j"])
+    assert cnt2[3] == newv == Vm and len(c_win) >= 6 and len(c_ci) > 0
+    np.testing.assert_allclose(c_new_pose, new_pose, rtol=1e-9, atol=1e-12)   # composed from the absorbed pose of win[1]
