@@ -1,7 +1,7 @@
 """Developer probe (GPU box): host-side phases of end-to-end calls on C2 (SVS_HOST_TIMING=1), alternating between
 two windows with different edge lists (full structure analysis every call), then the same window again."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from scavislam_b200 import synth, capi
 

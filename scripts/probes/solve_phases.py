@@ -1,6 +1,6 @@
 """Developer probe (GPU box): C2/C5 timing breakdown of the BA kernels + k_solve phase cycles."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from scavislam_b200 import synth, capi
 from oracle import pyoracle as po

@@ -1,6 +1,6 @@
 """Developer probe (GPU box): solve_reduced vs numpy on a mid-size banded window, several repetitions (race hunting)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from scavislam_b200 import synth, capi
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 200
