@@ -268,6 +268,10 @@ int svs_dt_chi2(svs_dt *h, int level, const double T_cur_from_prev[7], double *c
  * (21 values: for r: for c <= r), jacobian_times_res (6) */
 int svs_dt_jacobian_reduction(svs_dt *h, int level, const double T_cur_from_prev[7], double H21[21],
                               double b6[6], double *chi2);
+/* GpuTracker::residualImage (gpu/dense_tracking.cu:494-567; called once per level at the end of
+ * denseTrackingGpu, dense_tracking.cpp:180-188): res_rgba = w*h packed float4 -- grey max(0, 1 - 50 r^2) where the
+ * pixel contributes, (1,0,0,1) where it projects outside the frame, (0,1,0,1) where it has no depth */
+int svs_dt_residual_image(svs_dt *h, int level, const double T_cur_from_prev[7], float *res_rgba);
 /* DenseTracker::denseTrackingGpu (dense_tracking.cpp:62-193): coarse-to-fine LM, T updated in place */
 int svs_dt_track(svs_dt *h, double T_cur_from_actkey[7], svs_dt_stats *stats);
 

@@ -215,6 +215,14 @@ class DenseTracker {
     memcpy(T, T_cur_from_actkey.q, 32); memcpy(T + 4, T_cur_from_actkey.t, 24);
     return ok_ && svs_dt_compute_point_cloud(h_, T, level_cams) == SVS_OK;
   }
+  // GpuTracker::residualImage of one level at T_cur_from_prev (dev_residual_img[l], dense_tracking.cpp:180-188):
+  // res_rgba receives w_l * h_l float4
+  bool residualImage(int level, const SE3d& T_cur_from_prev, std::vector<float>* res_rgba, int w_l, int h_l) {
+    double T[7];
+    memcpy(T, T_cur_from_prev.q, 32); memcpy(T + 4, T_cur_from_prev.t, 24);
+    res_rgba->resize((size_t)4 * w_l * h_l);
+    return ok_ && svs_dt_residual_image(h_, level, T, res_rgba->data()) == SVS_OK;
+  }
 
  private:
   svs_dt* h_ = nullptr;

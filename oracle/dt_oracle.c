@@ -106,6 +106,30 @@ void odt_pass(const odt_level *L, const double T[7], int exact, double *chi2, do
   if (n_valid) *n_valid = n;
 }
 
+/* residualImage_kernel (gpu/dense_tracking.cu:494-541): out = w*h packed float4 */
+void odt_residual_image(const odt_level *L, const double T[7], int exact, float *out) {
+  float m[12];
+  odt_pose_to_m34(T, m);
+  for (int v = 0; v < L->h; ++v)
+    for (int u = 0; u < L->w; ++u) {
+      float *o = out + 4 * ((size_t)v * L->w + u);
+      const float *p = L->cloud + 4 * ((size_t)v * L->cloud_stride + u);
+      o[3] = 1.f;
+      if (p[3] > 0) {
+        float res, jac[6];
+        if (pixel_terms(L, m, u, v, exact, 0, &res, jac)) {
+          const float r2 = 1 - 50.f * res * res;
+          const float g = r2 > 0.f ? r2 : 0.f;
+          o[0] = o[1] = o[2] = g;
+        } else {
+          o[0] = 1.f; o[1] = 0.f; o[2] = 0.f;
+        }
+      } else {
+        o[0] = 0.f; o[1] = 1.f; o[2] = 0.f;
+      }
+    }
+}
+
 /* solve (H + mu diag(H)) x = -b, H packed as above; plain Gaussian elimination with pivoting */
 static void solve6(const double H21[21], const double b6[6], double mu, double x[6]) {
   double A[6][7];

@@ -111,6 +111,8 @@ def lib():
         c_fp = C.POINTER(C.c_float)
         L.odt_pass.argtypes = [C.POINTER(ODtLevel), c_dp, C.c_int, c_dp, c_dp, c_dp, c_ip]
         L.odt_pass.restype = None
+        L.odt_residual_image.argtypes = [C.POINTER(ODtLevel), c_dp, C.c_int, c_fp]
+        L.odt_residual_image.restype = None
         L.odt_track.argtypes = [C.POINTER(ODtLevel), C.c_int, c_dp, C.c_int, C.POINTER(ODtStats)]
         L.odt_track.restype = None
         L.odt_point_cloud.argtypes = [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]
@@ -343,6 +345,15 @@ def dt_pass(level, T, exact=False, want_jac=True):
     lib().odt_pass(arr, _dp(T), int(exact), C.byref(chi), _dp(H) if want_jac else None, _dp(b) if want_jac else None,
                    C.byref(n))
     return chi.value, H, b, n.value
+
+
+def dt_residual_image(level, T, exact=False):
+    arr, keep = dt_levels([level])
+    T = np.ascontiguousarray(T, np.float64)
+    h, w = keep[0]["prev"].shape
+    out = np.zeros((h, w, 4), np.float32)
+    lib().odt_residual_image(arr, _dp(T), int(exact), out.ctypes.data_as(c_fp))
+    return out
 
 
 def dt_track(levels, T, exact=False):

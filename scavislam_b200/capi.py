@@ -114,7 +114,7 @@ EXPORTS = [
     "svs_fast_set_image_device", "svs_fast_detect", "svs_fast_detect_adaptively",
     "svs_dt_create", "svs_dt_destroy", "svs_dt_last_error", "svs_dt_set_intrinsics", "svs_dt_set_images",
     "svs_dt_set_disparity", "svs_dt_compute_point_cloud", "svs_dt_set_point_cloud", "svs_dt_get_point_cloud",
-    "svs_dt_chi2", "svs_dt_jacobian_reduction", "svs_dt_track",
+    "svs_dt_chi2", "svs_dt_jacobian_reduction", "svs_dt_track", "svs_dt_residual_image",
     "svs_matcher_create", "svs_matcher_destroy", "svs_matcher_last_error", "svs_matcher_set_keyframe",
     "svs_matcher_set_current", "svs_matcher_set_features", "svs_matcher_set_features_from_fast", "svs_match",
     "svs_prep_create", "svs_prep_destroy", "svs_prep_last_error", "svs_prep_process", "svs_prep_level",
@@ -207,6 +207,7 @@ def lib():
     L.svs_dt_chi2.argtypes = [vp, C.c_int, c_dp, c_dp]
     L.svs_dt_jacobian_reduction.argtypes = [vp, C.c_int, c_dp, c_dp, c_dp, c_dp]
     L.svs_dt_track.argtypes = [vp, c_dp, C.POINTER(SvsDtStats)]
+    L.svs_dt_residual_image.argtypes = [vp, C.c_int, c_dp, c_fp]
     L.svs_prep_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.svs_prep_destroy.argtypes = [vp]
     L.svs_prep_destroy.restype = None
@@ -608,6 +609,13 @@ class DenseTracker:
         H, b, v = np.zeros(21), np.zeros(6), C.c_double()
         self._ck(lib().svs_dt_jacobian_reduction(self._h, level, _dp(T), _dp(H), _dp(b), C.byref(v)))
         return H, b, v.value
+
+    def residual_image(self, level, T):
+        """GpuTracker::residualImage: (h, w, 4) float32."""
+        T = np.ascontiguousarray(T, np.float64)
+        out = np.zeros((self.h0 >> level, self.w0 >> level, 4), np.float32)
+        self._ck(lib().svs_dt_residual_image(self._h, level, _dp(T), self._fp(out)))
+        return out
 
     def track(self, T):
         T = np.ascontiguousarray(T, np.float64).copy()

@@ -25,6 +25,7 @@
 #include "ba_kernels.cuh"
 #include "nccl_dyn.cuh"
 #include "host_pool.hpp"
+#include "svs_nvtx.hpp"
 
 using namespace svs;
 
@@ -894,6 +895,7 @@ int svs_ba_set_problem(svs_ba* h, int P, const double* T_qt, const unsigned char
                        int E, const int* e_point, const int* e_pose, const int* e_anchor, const double* e_obs,
                        const double* e_info, int C, const int* c_i, const int* c_j, const double* c_T,
                        const double* c_Lambda, const svs_cam* cam) {
+  svs::NvtxRange nvtx_("copyDataToG2o");
   if (h) h->L_full = 0;
   return set_problem_impl(h, P, T_qt, fixed, L, psi, E, e_point, e_pose, e_anchor, e_obs, e_info, C, c_i, c_j, c_T, c_Lambda,
                           cam, nullptr);
@@ -924,6 +926,7 @@ static int clear_system(svs_ba* h) {
 
 int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, double lambda_init, int max_trials,
                     svs_ba_stats* st) {
+  svs::NvtxRange nvtx_("optimize");
   if (!h) return -100 + SVS_ERR_INVALID;
   if (!h->has_problem) { h->err = "no problem set"; return -100 + SVS_ERR_STATE; }
   if (st) memset(st, 0, sizeof *st);
@@ -1273,6 +1276,7 @@ int svs_ba_set_problem_sharded(svs_ba* h, int P, const double* T_qt, const unsig
                                int E, const int* e_point, const int* e_pose, const int* e_anchor, const double* e_obs,
                                const double* e_info, int C, const int* c_i, const int* c_j, const double* c_T,
                                const double* c_Lambda, const svs_cam* cam) {
+  svs::NvtxRange nvtx_("copyDataToG2o");
   if (!h) return SVS_ERR_INVALID;
   if (P < 0 || L < 0 || E < 0 || C < 0) return fail(h, SVS_ERR_INVALID, "negative size");
   if (E && (!e_point || !e_pose || !e_anchor || !e_obs || !e_info)) return fail(h, SVS_ERR_INVALID, "null array");

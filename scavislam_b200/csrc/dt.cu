@@ -25,6 +25,7 @@
 
 #include "../../include/svs_b200.h"
 #include "se3_dev.cuh"
+#include "svs_nvtx.hpp"
 
 namespace cg = cooperative_groups;
 
@@ -300,6 +301,34 @@ k_dt_pass(DtLevel L, const double* T, double* partial, int exact, int want_jac) 
   accumulate_pass(L, Te, exact, want_jac != 0, partial, sred);
 }
 
+// residualImage_kernel (dense_tracking.cu:494-541): the per-pixel visualisation of the photometric residual at the
+// final pose of a level -- grey max(0, 1 - 50 r^2) where the pixel contributes, red where it projects outside the
+// frame, green where it has no depth; packed float4 rows (w * h)
+__global__ void k_dt_residual_image(DtLevel L, const double* __restrict__ T, int exact, float4* __restrict__ out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y * blockDim.y + threadIdx.y;
+  if (u >= L.w || v >= L.h) return;
+  double Te[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) Te[k] = T[k];
+  float m[12];
+  pose_to_m34(Te, m);
+  float4 o;
+  const float4 p = __ldg(L.cloud + (size_t)v * L.cloud_stride + u);
+  if (p.w > 0) {
+    float res, jac[6];
+    if (pixel_terms(L, m, u, v, exact, false, res, jac)) {
+      const float g = fmaxf(0.f, 1 - 50.f * res * res);
+      o = make_float4(g, g, g, 1.f);
+    } else {
+      o = make_float4(1.f, 0.f, 0.f, 1.f);
+    }
+  } else {
+    o = make_float4(0.f, 1.f, 0.f, 1.f);
+  }
+  out[(size_t)v * L.w + u] = o;
+}
+
 // pointcloud_kernel (dense_tracking.cu:82-122)
 struct M4 { float m[16]; };
 __global__ void k_dt_pointcloud(M4 TQ, const float* __restrict__ disp, int width, int height, int stride_in, int stride_out,
@@ -340,6 +369,7 @@ struct svs_dt {
   double* d_partial = nullptr;
   double* d_T = nullptr;
   unsigned* d_sync = nullptr;   // ticket, generation of k_dt_track_level
+  float4* d_res = nullptr;      // residual image of the largest level (made on the first svs_dt_residual_image)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int max_blocks = 0, track_blocks = 0;
   float* stage = nullptr;   // pinned staging for image uploads
@@ -415,7 +445,7 @@ void svs_dt_destroy(svs_dt* h) {
     for (int k = 0; k < 4; ++k) cudaFree(h->img[l][k]);
     cudaFree(h->cloud[l]);
   }
-  cudaFree(h->disp); cudaFree(h->d_ctl); cudaFree(h->d_partial); cudaFree(h->d_T); cudaFree(h->d_sync);
+  cudaFree(h->disp); cudaFree(h->d_ctl); cudaFree(h->d_partial); cudaFree(h->d_T); cudaFree(h->d_sync); cudaFree(h->d_res);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -504,6 +534,7 @@ int svs_dt_get_point_cloud(svs_dt* h, int level, float* cloud_xyzw) {
 
 // DenseTracker::computeDensePointCloudGpu (dense_tracking.cpp:195-216): per level TQ = T^-1 Q(level camera)
 int svs_dt_compute_point_cloud(svs_dt* h, const double T_cur_from_actkey[7], const svs_cam* cams) {
+  svs::NvtxRange nvtx_("dense point cloud");
   if (!h || !T_cur_from_actkey || !cams) return SVS_ERR_INVALID;
   cudaSetDevice(h->device);
   // T^-1 in double
@@ -574,7 +605,22 @@ int svs_dt_jacobian_reduction(svs_dt* h, int level, const double T[7], double H2
   return SVS_OK;
 }
 
+int svs_dt_residual_image(svs_dt* h, int level, const double T[7], float* res_rgba) {
+  if (!h || level < 0 || level >= h->nlevels || !T || !res_rgba) return SVS_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const DtLevel& L = h->lv[level];
+  if (!h->d_res) DCK(cudaMalloc(&h->d_res, sizeof(float4) * (size_t)h->w0 * h->h0));
+  DCK(cudaMemcpyAsync(h->d_T, T, sizeof(double) * 7, cudaMemcpyHostToDevice, h->stream));
+  const dim3 block(32, 8), grid((L.w + 31) / 32, (L.h + 7) / 8);
+  k_dt_residual_image<<<grid, block, 0, h->stream>>>(L, h->d_T, (h->flags & SVS_DT_EXACT_BILINEAR) ? 1 : 0, h->d_res);
+  DCK(cudaMemcpyAsync(res_rgba, h->d_res, sizeof(float4) * (size_t)L.w * L.h, cudaMemcpyDeviceToHost, h->stream));
+  DCK(cudaStreamSynchronize(h->stream));
+  DCK(cudaGetLastError());
+  return SVS_OK;
+}
+
 int svs_dt_track(svs_dt* h, double T[7], svs_dt_stats* st) {
+  svs::NvtxRange nvtx_("dense tracking");
   if (!h || !T) return SVS_ERR_INVALID;
   cudaSetDevice(h->device);
   DCK(cudaMemcpyAsync(h->d_ctl, T, sizeof(double) * 7, cudaMemcpyHostToDevice, h->stream));   // DtCtl::T is first

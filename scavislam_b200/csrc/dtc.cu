@@ -19,6 +19,7 @@
 
 #include "../../include/svs_b200.h"
 #include "se3_dev.cuh"
+#include "svs_nvtx.hpp"
 
 namespace {
 
@@ -351,6 +352,7 @@ int svs_dtc_set_disparity(svs_dtc* h, const float* disp, int stride_floats) {
 }
 
 int svs_computeDensePointCloudCpu(svs_dtc* h, const double T[7], const svs_cam* cams) {
+  svs::NvtxRange nvtx_("dense point cloud");
   if (!h || !T || !cams) return SVS_ERR_INVALID;
   cudaSetDevice(h->device);
   // T^-1 (Sophus inverse: conjugate quaternion, -R^T t)
@@ -398,6 +400,7 @@ int svs_dtc_set_point_cloud(svs_dtc* h, int level, const float* cloud_xyzw) {
 }
 
 int svs_denseTrackingCpu(svs_dtc* h, const svs_cam* cams, double T[7], svs_dt_stats* st) {
+  svs::NvtxRange nvtx_("dense tracking");
   if (!h || !cams || !T) return SVS_ERR_INVALID;
   cudaSetDevice(h->device);
   memcpy(h->h_ctl->T, T, sizeof(double) * 7);

@@ -19,6 +19,7 @@
 
 #include "../../include/svs_b200.h"
 #include "internal.cuh"
+#include "svs_nvtx.hpp"
 
 namespace {
 
@@ -425,6 +426,7 @@ static int run_detect(svs_fast* h, svs_fast_cell* cells, int ncells, const svs_f
 }
 
 int svs_fast_detect(svs_fast* h, const svs_fast_cell* cells, int ncells, int* out_xy, int max_out, int* cell_off) {
+  svs::NvtxRange nvtx_("fast");
   if (!cells || ncells <= 0 || ncells > kMaxCells) return SVS_ERR_INVALID;
   std::vector<svs_fast_cell> tmp(cells, cells + ncells);
   return run_detect(h, tmp.data(), ncells, nullptr, 0, out_xy, max_out, cell_off, 0);
@@ -432,6 +434,7 @@ int svs_fast_detect(svs_fast* h, const svs_fast_cell* cells, int ncells, int* ou
 
 int svs_fast_detect_adaptively(svs_fast* h, const svs_fast_grid_params* grid, svs_fast_cell* cells, int trials,
                                int* out_xy, int max_out, int* cell_off) {
+  svs::NvtxRange nvtx_("fast");
   if (!grid) return SVS_ERR_INVALID;
   return run_detect(h, cells, grid->grid_w * grid->grid_h, grid, trials, out_xy, max_out, cell_off, 1);
 }

@@ -22,6 +22,7 @@
 #include "../../include/svs_b200.h"
 #include "internal.cuh"
 #include "se3_dev.cuh"
+#include "svs_nvtx.hpp"
 
 namespace {
 
@@ -445,6 +446,7 @@ int svs_map_get(svs_map* h, double* T_me_from_world, double* xyz_anchor) {
 // SlamGraph::restoreDataFromG2o (slam_graph.cpp:1037-1058): the optimised window of `ba` (loaded with
 // svs_ba_set_problem_from_map from THIS map) goes back into the map, device to device
 int svs_map_absorb(svs_map* h, svs_ba* ba) {
+  svs::NvtxRange nvtx_("restoreDataFromG2o");
   if (!h || !ba || !h->d_map || !h->d_win_last) return SVS_ERR_INVALID;
   if (svs::ba_device(ba) != h->device) { h->err = "map and bundle adjuster live on different devices"; return SVS_ERR_INVALID; }
   const double* const* pose; const double* const* psi; const int* lm_user; const int* cur; cudaStream_t st; int P, L;
@@ -465,6 +467,7 @@ int svs_map_absorb(svs_map* h, svs_ba* ba) {
 int svs_ba_set_problem_from_map(svs_ba* ba, svs_map* h, int P, const int* window_vertex, const unsigned char* fixed, int L,
                                 const int* active_point, int C, const int* c_i, const int* c_j, const double* c_T,
                                 const double* c_Lambda, const svs_cam* cam, int* num_edges) {
+  svs::NvtxRange nvtx_("copyDataToG2o");
   if (!ba || !h || P <= 0 || L < 0 || C < 0 || !window_vertex || (L && !active_point) || !cam || !h->d_map) return SVS_ERR_INVALID;
   if (svs::ba_device(ba) != h->device) { h->err = "map and bundle adjuster live on different devices"; return SVS_ERR_INVALID; }
   // window position of every vertex (-1 = outside the double window)

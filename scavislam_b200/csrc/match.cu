@@ -21,6 +21,7 @@
 #include "../../include/svs_b200.h"
 #include "internal.cuh"
 #include "se3_dev.cuh"
+#include "svs_nvtx.hpp"
 
 namespace {
 
@@ -460,6 +461,7 @@ int svs_matcher_set_features_from_fast(svs_matcher * h, int level, svs_fast* fas
 
 int svs_match(svs_matcher * h, const double T_cur_from_actkey[7], const double T_actkey_from_w[7],
               const svs_match_point* pts, int n, int search_radius, int thr_mean, int thr_std, svs_match_result* out) {
+  svs::NvtxRange nvtx_("match");
   if (!h || !T_cur_from_actkey || !T_actkey_from_w || n < 0 || n > h->max_pts || (n && (!pts || !out)) || search_radius < 0)
     return SVS_ERR_INVALID;
   h->last_n = 0;

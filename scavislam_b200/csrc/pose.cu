@@ -19,6 +19,7 @@
 #include "../../include/svs_b200.h"
 #include "internal.cuh"
 #include "se3_dev.cuh"
+#include "svs_nvtx.hpp"
 
 namespace {
 
@@ -352,6 +353,7 @@ const char* svs_pose_last_error(const svs_pose* h) { return h ? h->err.c_str() :
 int svs_calcFastMotionOnly(svs_pose* h, int n, const int* obs_point_id, const double* obs_uvu, int npoints,
                            const double* point_xyz, const svs_cam* cam, const svs_pose_params* params, double T_frame[7],
                            svs_pose_stats* stats) {
+  svs::NvtxRange nvtx_("match");
   if (!h || n <= 0 || !obs_point_id || !obs_uvu || npoints <= 0 || !point_xyz || !cam || !params || !T_frame)
     return SVS_ERR_INVALID;                       // the reference asserts obs_list.size() > 0
   if (n > h->max_obs || npoints > h->max_obs) { h->err = "more observations/points than the handle's capacity"; return SVS_ERR_INVALID; }
@@ -370,6 +372,7 @@ int svs_calcFastMotionOnly(svs_pose* h, int n, const int* obs_point_id, const do
 
 int svs_calcFastMotionOnly_matched(svs_pose* h, svs_matcher* m, const svs_cam* cam, const svs_pose_params* params,
                                    double T_frame[7], svs_pose_stats* stats) {
+  svs::NvtxRange nvtx_("match");
   if (!h || !m || !cam || !params || !T_frame) return SVS_ERR_INVALID;
   const svs_match_result* d_res = nullptr;
   int n = 0, dev = -1;

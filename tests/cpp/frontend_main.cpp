@@ -64,6 +64,11 @@ int main(int argc, char** argv) {
   svs::SE3d T;   // identity
   if (!dt.computeDensePointCloudGpu(T, cams) || !dt.denseTrackingGpu(&T)) return 6;
   std::vector<double> T_track = {T.q[0], T.q[1], T.q[2], T.q[3], T.t[0], T.t[1], T.t[2]};
+  // residual image of the coarsest level at the tracked pose: every pixel is one of the three classes
+  std::vector<float> res_img;
+  if (!dt.residualImage(2, T, &res_img, W / 4, H / 4)) return 6;
+  for (size_t i = 0; i < res_img.size(); i += 4)
+    if (res_img[i + 3] != 1.f || res_img[i] < 0.f || res_img[i] > 1.f) return 6;
 
   // guided matching of the keyframe's corners (level 0) into frame 1
   std::vector<svs_match_level> lv = {{W, H, cams[0].f, cams[0].px, cams[0].py}, {W / 2, H / 2, cams[1].f, cams[1].px, cams[1].py}};

@@ -71,6 +71,25 @@ def test_chi2_and_jacobian_reduction(svs, oracle, seq, flags):
 
 
 @pytest.mark.parametrize("flags", [0, 1])
+def test_residual_image_bit_exact(svs, oracle, seq, flags):
+    """GpuTracker::residualImage (gpu/dense_tracking.cu:494-567): per-pixel FP32, no sums -> bit-exact."""
+    dt, levels, cams = _setup(svs, oracle, seq, flags)
+    T = oracle.se3_exp(np.array([0.03, 0.01, -0.05, 0.002, -0.02, 0.004]))   # some pixels leave the frame
+    disp = seq[0]["disp"].copy()
+    disp[60:90, 100:400] = 0                                                 # and some have no depth
+    dt.set_disparity(disp)
+    dt.compute_point_cloud(I7, cams)
+    for l in range(3):
+        levels[l]["cloud"] = oracle.dt_point_cloud(I7, cams[l], disp, l, 640 >> l, 480 >> l)
+        for pose in (I7, T):
+            ref = oracle.dt_residual_image(levels[l], pose, exact=bool(flags))
+            out = dt.residual_image(l, pose)
+            np.testing.assert_array_equal(out, ref)
+            assert (ref[..., 1] > ref[..., 0]).any() and (ref[..., 0] == ref[..., 1]).any()   # green and grey both occur
+    dt.close()
+
+
+@pytest.mark.parametrize("flags", [0, 1])
 def test_track_matches_oracle(svs, oracle, seq, flags):
     """DenseTracker::denseTrackingGpu: 3 levels, identity start (C3 shape: 640x480)."""
     dt, levels, cams = _setup(svs, oracle, seq, flags)

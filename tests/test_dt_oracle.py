@@ -106,3 +106,23 @@ def test_sweep_matches_an_independent_numpy_restatement(oracle):
         np.testing.assert_allclose(chi, chi_n, rtol=2e-4)
         np.testing.assert_allclose(H, H_n, rtol=2e-4, atol=2e-4 * np.abs(H_n).max())
         np.testing.assert_allclose(b, b_n, rtol=2e-3, atol=2e-4 * np.abs(b_n).max())
+
+
+def test_residual_image_is_consistent_with_the_chi2_sweep(oracle):
+    """residualImage_kernel classifies exactly the pixels chi2_kernel sums: grey pixels = contributing pixels, and the
+    grey value inverts to the squared residual wherever it is not clamped."""
+    lv, _ = _levels(oracle, 2)
+    T = oracle.se3_exp(np.array([0.03, 0.01, -0.05, 0.002, -0.02, 0.004]))
+    for l in (0, 1):
+        chi, _, _, n = oracle.dt_pass(lv[l], T, exact=False, want_jac=False)
+        img = oracle.dt_residual_image(lv[l], T, exact=False)
+        assert img.shape == lv[l]["prev"].shape + (4,) and (img[..., 3] == 1).all()
+        grey = (img[..., 0] == img[..., 1]) & (img[..., 1] == img[..., 2])
+        red = (img[..., 0] == 1) & (img[..., 1] == 0) & (img[..., 2] == 0)
+        green = (img[..., 0] == 0) & (img[..., 1] == 1) & (img[..., 2] == 0)
+        assert int(grey.sum()) == n and int((grey | red | green).sum()) == grey.size
+        assert int(green.sum()) == int((np.asarray(lv[l]["cloud"])[..., 3] <= 0).sum())
+        g = img[..., 0][grey].astype(np.float64)
+        unclamped = g > 0
+        r2 = (1 - g[unclamped]) / 50
+        assert r2.sum() <= chi * (1 + 1e-3) and (g >= 0).all() and (g <= 1).all()
