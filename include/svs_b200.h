@@ -422,7 +422,10 @@ int svs_calcFastMotionOnly_matched(svs_pose *h, svs_matcher *m, const svs_cam *c
  * Inputs: T_me_from_world[P][7]; the feature_table keys of every pose as CSR (feat_ptr[P+1], feat_point,
  * strictly ascending per pose); for every point the index of its anchor pose and xyz_anchor.  Anchor frames
  * outside the double window (computeAbsolutePose in the reference) are passed like any other pose.
- * A pair without shared points gets Lambda = 0 and visibility_strength = 0. */
+ * A pair without shared points gets Lambda = 0 and visibility_strength = 0 (the reference calls median() of an empty
+ * multiset there: undefined).  median(): VisionTools is not vendored with the reference, so its rule for an EVEN
+ * number of shared points is an assumption written down here -- the mean of the two middle depths (odd n: the middle
+ * one); constraint_oracle.c and csrc/constraint.cu both implement exactly this. */
 typedef struct svs_constraints svs_constraints;
 int svs_constraints_create(int device, svs_constraints **out);
 void svs_constraints_destroy(svs_constraints *h);

@@ -32,22 +32,35 @@ constexpr int kWvInts = 8 + 40;   // slot poses, pair table (36) padded
 size_t build_wave_smem_bytes() { return (size_t)kWvWarps * (kWvDoubles * 8 + kWvInts * 4); }
 
 __global__ void __launch_bounds__(kWvWarps * 32)
-k_build_wave(BaDev d, int robust, double delta, int n_task_blocks, int prof) {
+k_build_wave(BaDev d, int robust, double delta, int n_task_blocks, int prof, int persist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LmCtl* __restrict__ ctl = d.ctl;
   if (ctl->max_iters > 0 && (ctl->stop || ctl->iter >= ctl->max_iters)) return;   // speculatively enqueued trial: nothing left to do
   const int cur = ctl->cur;
-  if ((int)blockIdx.x >= n_task_blocks) {
-    // pose-pose constraints (G2oEdgeSE3), one thread each, riding on trailing CTAs of this launch so
-    // that their long serial 6x6 arithmetic overlaps the landmark work instead of following it
-    const int c = ((int)blockIdx.x - n_task_blocks) * (kWvWarps * 32) + (int)threadIdx.x;
-    if (c < d.C) constraint_build(d, d.pose[cur], c);
-    return;
+  // pose-pose constraints (G2oEdgeSE3), one thread each, riding on CTAs of this launch so that their long
+  // serial 6x6 arithmetic overlaps the landmark work instead of following it: the trailing CTAs of a
+  // one-task-per-warp grid, the LEADING ones of a persistent grid (its task CTAs stay until the list is empty)
+  {
+    const int c_blocks = (int)gridDim.x - n_task_blocks;
+    const int cb = persist ? (int)blockIdx.x : (int)blockIdx.x - n_task_blocks;
+    if (cb >= 0 && cb < c_blocks) {
+      const int c = cb * (kWvWarps * 32) + (int)threadIdx.x;
+      if (c < d.C) constraint_build(d, d.pose[cur], c);
+      return;
+    }
   }
-  const int task = (int)blockIdx.x * kWvWarps + warp;
-  if (task >= d.ntasks) return;
+  // persistent grid: the warps draw tasks from one counter (longest tasks first, set_problem sorts them), so a
+  // warp slot is never idle while tasks remain; the last warp to leave resets the counter pair for the next launch
+  unsigned* const tctr = d.ticket + 1;
+  auto next_task = [&]() {
+    int t = 0;
+    if (lane == 0) t = (int)atomicAdd(tctr, 1u);
+    return __shfl_sync(0xffffffffu, t, 0);
+  };
   const double lambda = ctl->lambda;
+  for (int task = persist ? next_task() : (int)blockIdx.x * kWvWarps + warp; task < d.ntasks;
+       task = persist ? next_task() : d.ntasks) {
   double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kWvDoubles;
   double* sJp = sm;
   double* sJa = sJp + 32 * kWvJ;
@@ -322,6 +335,12 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks, int prof) {
   if (prof && lane == 0)
     for (int i = 0; i < 7; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(d.dbg) + 48 + i, (unsigned long long)pacc[i]);
 #undef PBW
+    __syncwarp();   // the next task reuses this warp's shared-memory tables
+  }
+  if (persist && lane == 0) {
+    const unsigned nwarps_total = (unsigned)n_task_blocks * kWvWarps;
+    if (atomicAdd(tctr + 1, 1u) == nwarps_total - 1) { tctr[0] = 0u; tctr[1] = 0u; }   // every other warp has drawn its last ticket
+  }
 }
 
 // The same kernel with a TEAM of two warps per task: the 32 edge lanes of a wave are warp 0's, every later phase is
@@ -625,6 +644,21 @@ k_build_wave2(BaDev d, int robust, double delta, int n_task_blocks, int prof) {
 }
 
 
+// resident CTAs of k_build_wave on the current device (occupancy x SM count), cached per device
+static int build_wave_resident_ctas() {
+  static int cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 1 << 30;
+  if (cache[dev] == 0) {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_build_wave, kWvWarps * 32, build_wave_smem_bytes());
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = per_sm > 0 && sms > 0 ? per_sm * sms : 1 << 30;
+  }
+  return cache[dev];
+}
+
 void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st) {
   if (d.ntasks == 0 && d.C == 0) return;
   static const int prof = getenv("SVS_BUILD_TIMING") ? 1 : 0;
@@ -637,9 +671,15 @@ void launch_build_wave(const BaDev& d, int robust, double delta, cudaStream_t st
   if (one_warp) {
     if (device_needs_smem_optin(0, build_wave_smem_bytes()))
       cudaFuncSetAttribute(k_build_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_wave_smem_bytes());
-    const int task_blocks = (d.ntasks + kWvWarps - 1) / kWvWarps;
+    int task_blocks = (d.ntasks + kWvWarps - 1) / kWvWarps;
     const int c_blocks = (d.C + kWvWarps * 32 - 1) / (kWvWarps * 32);
-    k_build_wave<<<task_blocks + c_blocks, kWvWarps * 32, build_wave_smem_bytes(), st>>>(d, robust, delta, task_blocks, prof);
+    // persistent grid (default): as many task CTAs as are resident at once (255 registers and 111 KB of shared memory
+    // per CTA: two per SM), tasks drawn from a counter; SVS_BUILD_STATIC=1 keeps one task per warp for the A/B
+    static const int persist_on = getenv("SVS_BUILD_STATIC") ? 0 : 1;
+    const int resident = build_wave_resident_ctas();
+    const int persist = (persist_on && task_blocks > resident) ? 1 : 0;
+    if (persist) task_blocks = resident;
+    k_build_wave<<<task_blocks + c_blocks, kWvWarps * 32, build_wave_smem_bytes(), st>>>(d, robust, delta, task_blocks, prof, persist);
     return;
   }
   if (device_needs_smem_optin(2, build_wave_smem_bytes()))

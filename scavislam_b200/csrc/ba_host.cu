@@ -503,7 +503,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       CK(cudaMemcpyAsync(h->arena + h->off_num, h->stage + h->off_num, h->upload_bytes - h->off_num, cudaMemcpyHostToDevice,
                          h->stream));
       launch_regroup(d, d_obs_info ? d_obs_info : h->d_raw, h->stream);
-      CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
+      CK(cudaMemsetAsync(d.ticket, 0, 4 * sizeof(unsigned), h->stream));   // k_update's ticket, k_build_wave's task counter pair
       CK(cudaMemsetAsync(d.chi_c, 0, std::max(C, 1) * sizeof(double), h->stream));
       CK(cudaMemsetAsync(d.chi_c_new, 0, std::max(C, 1) * sizeof(double), h->stream));
       ++h->reuse_hits;
@@ -737,6 +737,28 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       long_lm.insert(long_lm.end(), t_long[t].begin(), t_long[t].end());
       Kmax_gen = std::max(Kmax_gen, t_kmax[t]);
     }
+    // longest tasks first: the warps of the persistent k_build_wave draw tasks from one counter, so the short
+    // tasks fill the end of the launch.  Cost = waves (<= 32 edges, 40 slots, 8 landmarks each); a stable counting
+    // sort by waves, descending (landmark order inside a class is kept for the locality of the scatter)
+    if (!getenv("SVS_BUILD_NO_LPT") && task_lm.size() > 1) {
+      const size_t nt_all = task_lm.size();
+      constexpr int kMaxWaves = 64;
+      std::vector<unsigned char> wv(nt_all);
+      int hist[kMaxWaves + 1] = {};
+      for (size_t t = 0; t < nt_all; ++t) {
+        const int li = task_lm[t], cnt = task_cnt[t];
+        const int kk = lm_eptr[li + 1] - lm_eptr[li], KK = lm_sptr[li + 1] - lm_sptr[li];
+        const int nw_max = std::max(1, std::min(std::min(32 / std::max(kk, 1), 40 / std::max(KK, 1)), 8));
+        const int waves = std::min((cnt + nw_max - 1) / nw_max, kMaxWaves);
+        wv[t] = (unsigned char)waves;
+        hist[waves]++;
+      }
+      int start[kMaxWaves + 1];
+      for (int w = kMaxWaves, at = 0; w >= 0; --w) { start[w] = at; at += hist[w]; }
+      std::vector<int> lm2(nt_all), cnt2(nt_all);
+      for (size_t t = 0; t < nt_all; ++t) { const int at = start[wv[t]]++; lm2[at] = task_lm[t]; cnt2[at] = task_cnt[t]; }
+      task_lm.swap(lm2); task_cnt.swap(cnt2);
+    }
   }
 
   lap("tasks");
@@ -857,7 +879,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     AL(x, 6 * (size_t)P); AL(Nrow, 36 * (size_t)std::max(sy.nblk - P, 1));
     AL(chi_c, C); AL(chi_c_new, C); AL(Linv, 36 * (size_t)P); AL(ywork, 6 * (size_t)P);
     AL(ctl, 1);
-    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 1); AL(dbg, 160);
+    AL(part, 3 * (size_t)update_grid_blocks(L, C)); AL(ticket, 4); AL(dbg, 160);
 #undef AL
   };
   h->measuring = true;
@@ -874,7 +896,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   CK(cudaMemcpyAsync(h->arena, h->stage, upload_bytes, cudaMemcpyHostToDevice, h->stream));
   d.e_obs = d.e_obs_w; d.e_w = d.e_w_w;
   launch_regroup(d, d_obs_info ? d_obs_info : h->d_raw, h->stream);   // [3][E] internal order <- [E][3] user order
-  CK(cudaMemsetAsync(d.ticket, 0, sizeof(unsigned), h->stream));
+  CK(cudaMemsetAsync(d.ticket, 0, 4 * sizeof(unsigned), h->stream));   // k_update's ticket, k_build_wave's task counter pair
   CK(cudaMemsetAsync(d.dbg, 0, 160 * sizeof(long long), h->stream));
   h->max_col_blocks = sy.max_col_sep; h->max_col_branch = sy.max_col_branch; h->max_row_blocks = sy.max_row;
   d.nbranch = h->nbranch;

@@ -89,7 +89,7 @@ struct BaDev {
   const int* branch_ptr;    // [nbranch + 1] column ranges of the branches; [nbranch] = first separator column
   double* ywork;       // [6P]
   double* part;        // [update grid][3] per-CTA partial sums (chi2 accepted, chi2 trial, scale)
-  unsigned* ticket;    // last-CTA-done counter of k_update
+  unsigned* ticket;    // [4] last-CTA-done counter of k_update; [1], [2]: task counter / warps-done counter of a persistent k_build_wave
   double* totals;      // [3] chi2 accepted / chi2 trial / scale of this rank's landmarks (sharded window)
   long long* dbg;      // [24] per-phase cycle counters of k_solve (thread 0, thread 64)
   LmCtl* ctl;
