@@ -58,6 +58,7 @@ __device__ __forceinline__ void stereo_residual(const BaDev& d, const double y[3
 __device__ __forceinline__ double edge_cost(const BaDev& d, const double* __restrict__ Rt, int ip, const double Ra[9],
                                             const double ta[3], const double xa[3], const double obs[3],
                                             const double om[3], int robust, double delta) {
+  if (om[0] == 0. && om[1] == 0. && om[2] == 0.) return 0.;   // zero information (padding edges): no cost, whatever the projection
   double Rc[9], tc[3], R[9], t[3], y[3], e[3];
   load12(Rt, ip, Rc, tc);
   rel_pose(Rc, tc, Ra, ta, R, t);
@@ -212,6 +213,16 @@ __device__ __forceinline__ double linearize_edge(const BaDev& d, const double* _
                                                double* __restrict__ Ja, double* __restrict__ Js, double* __restrict__ Ee) {
   const double obs[3] = {__ldg(d.e_obs + e), __ldg(d.e_obs + (size_t)d.E + e), __ldg(d.e_obs + 2 * (size_t)d.E + e)};
   const double om[3] = {__ldg(d.e_w + e), __ldg(d.e_w + (size_t)d.E + e), __ldg(d.e_w + 2 * (size_t)d.E + e)};
+  if (om[0] == 0. && om[1] == 0. && om[2] == 0.) {
+    // zero information: the edge contributes nothing, and its projection (a padding edge names a frame that never
+    // saw the point) must not be evaluated -- 0 x inf would poison the sums
+#pragma unroll
+    for (int i = 0; i < 18; ++i) { Jp[i] = 0.; Ja[i] = 0.; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Js[i] = 0.;
+    Ee[0] = Ee[1] = Ee[2] = 0.;
+    return 0.;
+  }
   double Rc[9], tc[3], R[9], t[3], y[3], er[3];
   load12(Rt, ip, Rc, tc);
   rel_pose(Rc, tc, Ra, ta, R, t);

@@ -118,7 +118,7 @@ struct svs_ba {
   // host scratch of set_problem, kept across calls (fresh multi-MB vectors page-fault every time)
   std::vector<std::pair<unsigned long long, int>> w_ko;
   std::vector<int> w_cnt, w_eptr, w_eord, w_fill, w_anchor, w_K, w_order, w_lm_eptr, w_lm_sptr, w_lm_anchor, w_ie_pose, w_bucket;
-  std::vector<unsigned char> w_self, w_lm_self, w_adj;
+  std::vector<unsigned char> w_self, w_lm_self, w_adj, w_npad;
   std::vector<unsigned long long> w_key;
   std::vector<double> w_psi;
   std::vector<int> w_edge_src;
@@ -599,6 +599,16 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   // per landmark: anchor, self-observation flag, observer edges sorted by pose index (in place in eord)
   auto& l_anchor = h->w_anchor; auto& l_K = h->w_K; auto& l_self = h->w_self; auto& key = h->w_key;
   l_anchor.assign(L, -1); l_K.assign(L, 0); l_self.assign(L, 0); key.resize(L);
+  // Track padding (SVS_BUILD_NO_PAD=1 switches it off): a track with a few visibility drop-outs -- observers
+  // lo..hi with gaps -- is completed with ZERO-WEIGHT edges to the frames it skips, when the completed track still
+  // fits the fused kernel (<= 8 slots) and at most half as many edges are added as there are.  A zero-weight edge
+  // adds exactly 0 to every sum (linearize_edge / edge_cost return zeros for it without touching the projection),
+  // so the reduced system, the update and chi2 are unchanged; what changes is that the landmark now has the slot
+  // list of its undamaged neighbours and joins their run, instead of being a task of its own (20 % drop-outs on
+  // the 200-keyframe window: 9 700 runs of 2 landmarks -> 3 600 runs of 6).
+  auto& l_npad = h->w_npad;
+  l_npad.assign(L, 0);
+  const bool pad_tracks = getenv("SVS_BUILD_NO_PAD") == nullptr;
   int Kmax = 1;
   int bad = 0;
   const int nchunk = L > 4096 ? 4 * nthr : 1;   // contiguous landmark ranges, handed out dynamically
@@ -632,7 +642,13 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       }
       for (int k = b + 1; k < en; ++k)
         if (e_pose[eord[k]] == e_pose[eord[k - 1]]) bad = std::max(bad, 2);
-      const int K = 1 + (en - b) - nself;
+      int K = 1 + (en - b) - nself;
+      if (pad_tracks && bad == 0 && nself <= 1 && en - b - nself >= 2) {
+        const int m = en - b - nself, lo = e_pose[eord[b + nself]], hi = e_pose[eord[en - 1]];
+        const int span = hi - lo + 1 - ((anchor > lo && anchor < hi) ? 1 : 0);   // frames lo..hi without the anchor
+        const int np = span - m;
+        if (np > 0 && 1 + span <= 8 && np <= std::max(1, m / 2)) { l_npad[l] = (unsigned char)np; K += np; }
+      }
       l_anchor[l] = anchor; l_self[l] = (unsigned char)nself; l_K[l] = K;
       Kmax = std::max(Kmax, K);
       // locality key: track shape (self flag, length, first and last observer) inside an anchor, so that
@@ -671,15 +687,15 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   lap("order");
   auto& lm_eptr = h->w_lm_eptr; auto& lm_sptr = h->w_lm_sptr; auto& lm_anchor = h->w_lm_anchor; auto& ie_pose = h->w_ie_pose;
   auto& lm_self = h->w_lm_self; auto& edge_src = h->w_edge_src; auto& ipsi = h->w_psi;
-  lm_eptr.assign(L + 1, 0); lm_sptr.assign(L + 1, 0); lm_anchor.assign(L, 0); ie_pose.resize(E);
-  lm_self.assign(L, 0); edge_src.resize(E); ipsi.resize(3 * (size_t)L);
+  lm_eptr.assign(L + 1, 0); lm_sptr.assign(L + 1, 0); lm_anchor.assign(L, 0);
+  lm_self.assign(L, 0); ipsi.resize(3 * (size_t)L);
   for (int li = 0; li < L; ++li) {
     const int l = order[li];
-    lm_eptr[li + 1] = lm_eptr[li] + (eptr[l + 1] - eptr[l]);
+    lm_eptr[li + 1] = lm_eptr[li] + (eptr[l + 1] - eptr[l]) + l_npad[l];
     lm_sptr[li + 1] = lm_sptr[li] + l_K[l];
   }
-  const int ne = lm_eptr[L], ns = lm_sptr[L];
-  (void)ne;
+  const int ne = lm_eptr[L], ns = lm_sptr[L];   // ne = E + padding edges: the internal edge count
+  ie_pose.resize(ne); edge_src.resize(ne);
   h->pool.parallel_for(nchunk, [&](int ck) {
     for (int li = (int)((long long)L * ck / nchunk), li_end = (int)((long long)L * (ck + 1) / nchunk); li < li_end; ++li) {
       const int l = order[li];
@@ -687,10 +703,23 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       if (l_anchor[l] < 0) continue;
       lm_anchor[li] = l_anchor[l]; lm_self[li] = l_self[l];
       int at = lm_eptr[li];
-      for (int k = eptr[l]; k < eptr[l + 1]; ++k, ++at) {
-        const int e = eord[k];
-        ie_pose[at] = e_pose[e];
-        edge_src[at] = e;   // the doubles follow on the device (k_regroup)
+      if (l_npad[l] == 0) {
+        for (int k = eptr[l]; k < eptr[l + 1]; ++k, ++at) {
+          const int e = eord[k];
+          ie_pose[at] = e_pose[e];
+          edge_src[at] = e;   // the doubles follow on the device (k_regroup)
+        }
+      } else {   // completed track: the self edge, then every frame lo..hi but the anchor; -1 = zero-weight padding edge
+        int k = eptr[l];
+        const int en = eptr[l + 1], anchor = l_anchor[l];
+        if (l_self[l]) { ie_pose[at] = anchor; edge_src[at++] = eord[k++]; }
+        const int lo = e_pose[eord[k]], hi = e_pose[eord[en - 1]];
+        for (int p = lo; p <= hi; ++p) {
+          if (p == anchor) continue;
+          ie_pose[at] = p;
+          if (k < en && e_pose[eord[k]] == p) edge_src[at++] = eord[k++];
+          else edge_src[at++] = -1;
+        }
       }
     }
   });
@@ -699,7 +728,11 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   std::vector<int> task_lm, task_cnt, gen_lm, long_lm;   // long_lm: more than kMaxTrack slots (streaming kernel, any length)
   int Kmax_gen = 1;
   {
-    int chunk = L / (148 * 16);
+    // landmarks per task.  Measured on B200 with the persistent grid (1 184 resident warps), build kernel per trial on
+    // the 200-keyframe window / with 20 % drop-outs: chunk 8: 0.100 / 0.116 ms, 12: 0.095 / 0.113, 16: 0.097 / 0.110,
+    // 20: 0.108 / 0.113, 24: 0.125 / 0.127, 32: 0.156 / 0.159 (fewer flushes against a coarser tail); the
+    // 1 000-keyframe window is flat from 32 up
+    int chunk = L / (148 * 11);
     chunk = chunk < 4 ? 4 : (chunk > 32 ? 32 : chunk);
     if (const char* cs = getenv("SVS_BUILD_CHUNK")) chunk = atoi(cs);   // tuning knob
     if (getenv("SVS_BUILD_V1")) chunk = 0;   // A/B switch: everything through the one-warp-per-landmark kernel
@@ -838,7 +871,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   lap("analyse");
   // ---- device image: constant arrays (uploaded in one copy) followed by work buffers
   BaDev& d = h->d;
-  d.P = P; d.L = L; d.E = E; d.C = C; d.nslots = ns; d.nblk = sy.nblk; d.flags = h->flags;
+  d.P = P; d.L = L; d.E = ne; d.E_user = E; d.C = C; d.nslots = ns; d.nblk = sy.nblk; d.flags = h->flags;
   d.f = cam->f; d.px = cam->px; d.py = cam->py; d.b = cam->b;
   std::vector<unsigned char> fx(P, 0);
   if (fixed) fx.assign(fixed, fixed + P);
@@ -868,7 +901,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     h->upload_bytes = upload_bytes;
 #define AL(field, n) dev_alloc(h, &d.field, (size_t)(n))
     for (int b = 0; b < 2; ++b) { AL(pose[b], 7 * (size_t)P); AL(Rt[b], 12 * (size_t)P); AL(psi[b], 3 * (size_t)L); }
-    AL(e_obs_w, 3 * (size_t)E); AL(e_w_w, 3 * (size_t)E);
+    AL(e_obs_w, 3 * (size_t)ne); AL(e_w_w, 3 * (size_t)ne);
     AL(W, 18 * (size_t)ns); AL(Dbl, 12 * (size_t)L); AL(chi_l, L); AL(chi_new_l, L); AL(scale_l, L);
     {   // reduced system S | bp | bc | totals in ONE buffer: a sharded window sums it with a single all-reduce
       double* sys = nullptr;
@@ -1058,7 +1091,7 @@ int svs_ba_optimize(svs_ba* h, int num_iters, int robust, double huber_delta, do
       st->lambda_iter[i] = c.lambda_iter[i];
       st->trials_iter[i] = c.trials_iter[i];
     }
-    st->num_frames = d.P; st->num_points = d.L; st->num_point_edges = d.E; st->num_frame_edges = d.C;
+    st->num_frames = d.P; st->num_points = d.L; st->num_point_edges = d.E_user; st->num_frame_edges = d.C;
     st->nnzb_S = h->nnzb_S; st->nnzb_L = d.nblk; st->max_track = h->Kmax;
     cudaEventElapsedTime(&st->ms_total, h->ev[0], h->ev[6]);
     st->ms_build = ms[0]; st->ms_solve = ms[1]; st->ms_update = ms[2]; st->ms_control = ms[3];
@@ -1459,7 +1492,7 @@ int svs_ba_lm_stats(svs_ba* h, svs_ba_stats* st) {
   for (int i = 0; i < c.iter && i < SVS_BA_MAX_ITERS; ++i) {
     st->chi2_iter[i] = c.chi_iter[i]; st->lambda_iter[i] = c.lambda_iter[i]; st->trials_iter[i] = c.trials_iter[i];
   }
-  st->num_frames = h->d.P; st->num_points = h->d.L; st->num_point_edges = h->d.E; st->num_frame_edges = h->d.C;
+  st->num_frames = h->d.P; st->num_points = h->d.L; st->num_point_edges = h->d.E_user; st->num_frame_edges = h->d.C;
   st->nnzb_S = h->nnzb_S; st->nnzb_L = h->d.nblk; st->max_track = h->Kmax;
   return SVS_OK;
 }

@@ -31,7 +31,8 @@ struct LmCtl {
 };
 
 struct BaDev {
-  int P, L, E, C, nslots, nblk;
+  int P, L, E, C, nslots, nblk;   // E = internal edges = the caller's (E_user) + zero-weight padding edges (set_problem)
+  int E_user;
   int flags;
   double f, px, py, b;
   // state, double buffered (index ctl->cur = accepted, the other = trial)

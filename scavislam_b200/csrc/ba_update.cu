@@ -295,9 +295,18 @@ __global__ void k_prep(BaDev d, int buf) {
 __global__ void k_regroup(BaDev d, const double* __restrict__ raw) {
   const int at = blockIdx.x * blockDim.x + threadIdx.x;
   if (at >= d.E) return;
-  const size_t e = (size_t)d.edge_src[at];
+  const int src = d.edge_src[at];
+  if (src < 0) {   // padding edge of a completed track (set_problem): weight zero, observation irrelevant
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      d.e_obs_w[(size_t)q * d.E + at] = 0.;
+      d.e_w_w[(size_t)q * d.E + at] = 0.;
+    }
+    return;
+  }
+  const size_t e = (size_t)src;
   const double* o = raw + 3 * e;
-  const double* w = raw + 3 * (size_t)d.E + 3 * e;
+  const double* w = raw + 3 * (size_t)d.E_user + 3 * e;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     d.e_obs_w[(size_t)q * d.E + at] = o[q];

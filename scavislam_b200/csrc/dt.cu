@@ -34,6 +34,7 @@ namespace {
 constexpr int kMaxLevels = 8;
 constexpr int kThreads = 256;
 constexpr int kAcc = 28;   // 21 Hessian + 6 gradient + chi2
+constexpr int kPxBatch = 4;   // pixels a thread has in flight in the fused pass (accumulate_pass)
 
 struct DtLevel {
   int w, h, stride, cloud_stride;
@@ -117,20 +118,75 @@ __device__ void accumulate_pass(const DtLevel& L, const double T[7], int exact, 
   double acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; ++i) acc[i] = 0.;
+  // kPxBatch pixels of the grid-stride sequence at a time, every load of the batch unconditional (a pixel that does
+  // not contribute reads the taps of (1, 1) instead): the loads of the whole batch are in flight together, where the
+  // one-pixel loop paid cloud -> taps -> next pixel's cloud -> ... in sequence.  Per-pixel arithmetic and the order
+  // of the additions are those of pixel_terms / the one-pixel loop.
   const int npx = L.w * L.h;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npx; idx += gridDim.x * blockDim.x) {
-    const int v = idx / L.w, u = idx - v * L.w;
-    float res, jac[6];
-    if (!pixel_terms(L, m, u, v, exact, want_jac, res, jac)) continue;
-    acc[27] += (double)(res * res);
-    if (want_jac) {
-      int i = 0;
+  const int stride_px = gridDim.x * blockDim.x;
+  for (int idx0 = blockIdx.x * blockDim.x + threadIdx.x; idx0 < npx; idx0 += kPxBatch * stride_px) {
+    int pu[kPxBatch], pv[kPxBatch];
+    float4 pc[kPxBatch];
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+    for (int q = 0; q < kPxBatch; ++q) {
+      const int idx = idx0 + q * stride_px;
+      const bool in = idx < npx;
+      const int ii = in ? idx : 0;
+      pv[q] = ii / L.w; pu[q] = ii - pv[q] * L.w;
+      pc[q] = __ldg(L.cloud + (size_t)pv[q] * L.cloud_stride + pu[q]);
+      if (!in) pc[q].w = -1.f;
+    }
+    bool ok[kPxBatch];
+    float cxq[kPxBatch], cyq[kPxBatch], czq[kPxBatch], ucq[kPxBatch], vcq[kPxBatch];
 #pragma unroll
-        for (int c = 0; c <= r; ++c) acc[i++] += (double)(jac[r] * jac[c]);
+    for (int q = 0; q < kPxBatch; ++q) {
+      const float4 p = pc[q];
+      const float cx = p.x * m[0] + p.y * m[3] + p.z * m[6] + p.w * m[9];
+      const float cy = p.x * m[1] + p.y * m[4] + p.z * m[7] + p.w * m[10];
+      const float cz = p.x * m[2] + p.y * m[5] + p.z * m[8] + p.w * m[11];
+      const float uc = L.f * cx / cz + L.px;
+      const float vc = L.f * cy / cz + L.py;
+      ok[q] = (p.w > 0) && (uc >= 1.f && vc >= 1.f && uc <= (float)(L.w - 2) && vc <= (float)(L.h - 2));
+      cxq[q] = cx; cyq[q] = cy; czq[q] = cz;
+      ucq[q] = ok[q] ? uc : 1.f; vcq[q] = ok[q] ? vc : 1.f;
+    }
+    float ipq[kPxBatch], icq[kPxBatch], dxq[kPxBatch], dyq[kPxBatch];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) acc[21 + r] += (double)(jac[r] * res);
+    for (int q = 0; q < kPxBatch; ++q) {
+      ipq[q] = __ldg(L.prev + (size_t)pv[q] * L.stride + pu[q]);
+      icq[q] = bilinear(L.cur, L.stride, ucq[q], vcq[q], exact);
+      if (want_jac) {
+        dxq[q] = bilinear(L.dx, L.stride, ucq[q], vcq[q], exact);
+        dyq[q] = bilinear(L.dy, L.stride, ucq[q], vcq[q], exact);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kPxBatch; ++q) {
+      if (!ok[q]) continue;
+      const float res = ipq[q] - icq[q];
+      acc[27] += (double)(res * res);
+      if (want_jac) {
+        const float cx = cxq[q], cy = cyq[q], cz = czq[q];
+        float jac[6];
+        float dx = 0.5f * dxq[q];
+        float dy = 0.5f * dyq[q];
+        const float z_sq = cz * cz;   // frameJacobian (dense_tracking.cu:65-80), literally (as in pixel_terms)
+        dx *= L.f;
+        dy *= L.f;
+        jac[0] = (float)(-dx * (1. / cz));
+        jac[1] = (float)(-dy * 1. / cz);
+        jac[2] = (dx * cx / z_sq + dy * cy / z_sq);
+        jac[3] = (dx * (cx * cy) / z_sq + dy * (1.f + cy * cy / z_sq));
+        jac[4] = (-dx * (1.f + (cx * cx / z_sq)) - dy * (cx * cy) / z_sq);
+        jac[5] = (dx * cy / cz - dy * cx / cz);
+        int i = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) acc[i++] += (double)(jac[r] * jac[c]);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[21 + r] += (double)(jac[r] * res);
+      }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -146,9 +202,9 @@ __device__ void accumulate_pass(const DtLevel& L, const double T[7], int exact, 
     double s = 0;
     for (int w = 0; w < kThreads / 32; ++w) s += sred[w][threadIdx.x];
     partial[(size_t)blockIdx.x * kAcc + threadIdx.x] = s;
-    __threadfence();   // visible to the CTA that sums the partials (k_dt_track_level's ticket)
   }
-  __syncthreads();
+  __syncthreads();   // (k_dt_track_level: thread 0 fences behind this barrier before it takes the ticket, which
+                     //  publishes these stores to the CTA that sums the partials -- fences are cumulative)
 }
 
 // (H + mu diag(H)) x = -b by LDL^T (H.ldlt().solve(-b), dense_tracking.cpp:127-135)
@@ -195,7 +251,7 @@ __device__ void propose_step(DtCtl* c) {
 // which CTA happens to be last), takes the Levenberg decision, writes the next pose and bumps a generation
 // counter the other CTAs spin on (all CTAs are co-resident: cooperative launch).
 constexpr int kSeg = 8;
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exact, int level) {
   __shared__ double sred[kThreads / 32][kAcc];
   __shared__ double sseg[kSeg][kAcc];
@@ -204,7 +260,7 @@ k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exa
   __shared__ int sLast;
   if (threadIdx.x == 0) sGen = *(volatile unsigned*)&sync[1];   // no CTA can bump it before every CTA has arrived once
   __syncthreads();
-  unsigned gen = sGen;
+  unsigned gen = sGen & 0x7fffffffu;   // bit 31 = "level finished" of the previous launch
   for (int pass = 0;; ++pass) {
     double Te[7];
     const double* Tsrc = pass == 0 ? ctl->T : ctl->Teval;   // the first pass evaluates the incoming pose
@@ -221,8 +277,19 @@ k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exa
       {
         const int i = threadIdx.x & 31, seg = threadIdx.x >> 5;   // kThreads / 32 == kSeg
         if (i < kAcc) {
+          // fixed order (b = seg, seg + 8, ...), eight independent loads in flight per round: the loop used to
+          // wait for one L2 round trip per partial (37 in a row for 296 CTAs)
           double s = 0;
-          for (unsigned b = seg; b < gridDim.x; b += kSeg) s += __ldcg(&partial[(size_t)b * kAcc + i]);
+          for (unsigned b0 = seg; b0 < gridDim.x; b0 += 8 * kSeg) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const unsigned b = b0 + q * kSeg;
+              v[q] = b < gridDim.x ? __ldcg(&partial[(size_t)b * kAcc + i]) : 0.;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += v[q];
+          }
           sseg[seg][i] = s;
         }
       }
@@ -278,16 +345,20 @@ k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exa
         }
         sync[0] = 0;
         __threadfence();
-        atomicAdd(&sync[1], 1u);   // releases the other CTAs
+        // releases the other CTAs; bit 31 of the word they spin on says "level finished", so nobody needs another
+        // L2 round trip for ctl->done (the next launch masks the bit off when it reads its starting generation)
+        *(volatile unsigned*)&sync[1] = ((gen + 1u) & 0x7fffffffu) | (c->done ? 0x80000000u : 0u);
       }
     }
     if (threadIdx.x == 0) {
-      while (*(volatile unsigned*)&sync[1] == gen) {}
+      unsigned g;
+      while (((g = *(volatile unsigned*)&sync[1]) & 0x7fffffffu) == gen) {}
       __threadfence();
+      sGen = g;
     }
     __syncthreads();
-    ++gen;
-    if (__ldcg(&ctl->done)) break;
+    gen = (gen + 1u) & 0x7fffffffu;
+    if (sGen & 0x80000000u) break;   // (sGen is next written behind the barriers of the next pass)
   }
 }
 

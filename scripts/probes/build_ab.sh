@@ -3,10 +3,10 @@
 cd /root/repo
 mkdir -p gpurun_out
 {
+timeout 900 python -m pytest tests/test_ba_gpu.py tests/test_map_gpu.py tests/test_cpp_shim.py tests/test_dist_gpu.py -m gpu -x -q 2>&1 | tail -5
 python scripts/probes/build_ab.py
-SVS_BUILD_STATIC=1 python scripts/probes/build_ab.py
-SVS_BUILD_STATIC=1 SVS_BUILD_NO_LPT=1 python scripts/probes/build_ab.py
-SVS_BUILD_NO_LPT=1 python scripts/probes/build_ab.py C2 C5
-for c in 4 6 12; do SVS_BUILD_CHUNK=$c python scripts/probes/build_ab.py C2 C2d C5; done
-} 2>&1 | grep -v "^$" | tee gpurun_out/build_ab.txt
-timeout 600 python -m pytest tests/test_ba_gpu.py tests/test_dt_gpu.py tests/test_cpp_shim.py -m gpu -x -q 2>&1 | tail -3 | tee -a gpurun_out/build_ab.txt
+SVS_BUILD_NO_PAD=1 python scripts/probes/build_ab.py C2d
+for c in 12 16 20 24 32; do SVS_BUILD_CHUNK=$c python scripts/probes/build_ab.py C2 C2d C2l; done
+SVS_BUILD_CHUNK=48 python scripts/probes/build_ab.py C5
+SVS_HOST_TIMING=1 python scripts/probes/e2e_host_phases.py 2 2>&1 | tail -60
+} 2>&1 | grep -v "^$" | tee gpurun_out/build_ab2.txt

@@ -251,6 +251,68 @@ def test_two_ended_split_is_used_and_equals_the_chain(ba, oracle, svs):
         del os.environ["SVS_SOLVE_CHAIN"]
 
 
+# ---------------------------------------------------------------- tracks with holes: zero-weight padding (set_problem)
+
+def test_tracks_with_holes_are_completed_without_changing_any_sum(ba, oracle, svs):
+    """set_problem completes a track with a few drop-outs with zero-weight edges so that it shares the slot list of its
+    neighbours (ba_host.cu, 'Track padding').  The reduced system, chi2 and the LM trajectory must not move: against
+    the oracle (which knows nothing of the padding) and against the same library with SVS_BUILD_NO_PAD=1."""
+    import os
+    pb = synth.with_dropouts(synth.make_window(40, 3000, seed=41), 0.2, seed=3)
+    ba.set_problem(pb)
+    S, bs, chi = ba.reduced_system(True, 1.0, 50.0)
+    So, bso, chio = oracle.reduced_system(pb, True, 1.0, 50.0)
+    assert abs(chi - chio) <= 1e-11 * abs(chio)
+    assert _rel(S, So) < 1e-11 and _rel(bs, bso) < 1e-10
+    st = _check_against_oracle(ba, oracle, pb, iters=5)
+    assert st["num_point_edges"] == pb.E          # the caller's count, not the padded one
+    poses = ba.poses()
+    os.environ["SVS_BUILD_NO_PAD"] = "1"
+    try:
+        b2 = svs.BundleAdjuster()
+        b2.set_problem(pb)
+        S2, bs2, chi2 = b2.reduced_system(True, 1.0, 50.0)
+        it2, st2 = b2.optimize(5)
+        assert _rel(S, S2) < 1e-12 and _rel(bs, bs2) < 1e-11 and abs(chi - chi2) <= 1e-12 * abs(chi2)
+        assert _rel(b2.poses(), poses) < 1e-9
+        b2.close()
+    finally:
+        del os.environ["SVS_BUILD_NO_PAD"]
+
+
+def test_padding_edges_never_evaluate_their_projection(ba, oracle):
+    """A padding edge names a frame that never saw the point.  Here that frame looks the other way (every point is
+    BEHIND it, depth <= 0 in its coordinates): evaluating the projection would put inf/NaN into the sums."""
+    pb = synth.make_window(12, 600, seed=43)
+    hole = 5
+    keep = (pb.e_pose != hole) & (pb.e_anchor != hole)     # frame 5 observes nothing and anchors nothing that is observed
+    out = pb.copy()
+    for k in ("e_point", "e_pose", "e_anchor", "e_obs", "e_info"):
+        setattr(out, k, np.ascontiguousarray(getattr(pb, k)[keep]))
+    out.E = int(keep.sum())
+    # turn frame 5 by 180 degrees about its y axis: T' = Ry(pi) T  (q' = (0,1,0,0) * q, t' = Ry t), and fix it
+    q, t = out.pose_qt[hole, :4].copy(), out.pose_qt[hole, 4:].copy()
+    x, y, z, w = q
+    out.pose_qt[hole, :4] = np.array([z, w, -x, -y])        # (0,1,0,0) * (x,y,z,w)
+    out.pose_qt[hole, 4:] = np.array([-t[0], t[1], -t[2]])
+    out.fixed = out.fixed.copy()
+    out.fixed[hole] = 1
+    ck = (out.c_i != hole) & (out.c_j != hole)               # its pose-pose constraints go too
+    out.c_i, out.c_j, out.c_T, out.c_Lambda = out.c_i[ck].copy(), out.c_j[ck].copy(), out.c_T[ck].copy(), out.c_Lambda[ck].copy()
+    out.C = int(ck.sum())
+    spans = 0
+    for l in range(out.L):
+        fr = np.sort(out.e_pose[(out.e_point == l) & (out.e_pose != out.e_anchor)])
+        spans += int(fr.size >= 2 and fr[0] < hole < fr[-1])
+    assert spans > 20                                        # tracks that do span the hole exist
+    ba.set_problem(out)
+    S, bs, chi = ba.reduced_system(True, 1.0, 50.0)
+    So, bso, chio = oracle.reduced_system(out, True, 1.0, 50.0)
+    assert np.isfinite(S).all() and np.isfinite(bs).all() and np.isfinite(chi)
+    assert abs(chi - chio) <= 1e-11 * abs(chio) and _rel(S, So) < 1e-11 and _rel(bs, bso) < 1e-10
+    _check_against_oracle(ba, oracle, out, iters=3)
+
+
 # ---------------------------------------------------------------- C2-sized structure variants (bench extras)
 
 def test_c2_with_visibility_dropouts_full_size(ba, oracle):
