@@ -124,6 +124,24 @@ __device__ void accumulate_pass(const DtLevel& L, const double T[7], int exact, 
   // of the additions are those of pixel_terms / the one-pixel loop.
   const int npx = L.w * L.h;
   const int stride_px = gridDim.x * blockDim.x;
+  if (npx <= 2 * stride_px) {   // coarse levels: one or two pixels per thread, nothing to batch
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npx; idx += stride_px) {
+      const int v = idx / L.w, u = idx - v * L.w;
+      float res, jac[6];
+      if (pixel_terms(L, m, u, v, exact, want_jac, res, jac)) {
+        acc[27] += (double)(res * res);
+        if (want_jac) {
+          int i = 0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) acc[i++] += (double)(jac[r] * jac[c]);
+#pragma unroll
+          for (int r = 0; r < 6; ++r) acc[21 + r] += (double)(jac[r] * res);
+        }
+      }
+    }
+  } else
   for (int idx0 = blockIdx.x * blockDim.x + threadIdx.x; idx0 < npx; idx0 += kPxBatch * stride_px) {
     int pu[kPxBatch], pv[kPxBatch];
     float4 pc[kPxBatch];
@@ -207,34 +225,58 @@ __device__ void accumulate_pass(const DtLevel& L, const double T[7], int exact, 
                      //  publishes these stores to the CTA that sums the partials -- fences are cumulative)
 }
 
-// (H + mu diag(H)) x = -b by LDL^T (H.ldlt().solve(-b), dense_tracking.cpp:127-135)
+// 1/a for the pivots of solve6: hardware approximation + two Newton steps (full double precision up to rounding).
+// An IEEE double division is a ~25-instruction dependent sequence; the solve sits on the one-thread critical path of
+// every LM pass (all other CTAs spin meanwhile), and the 21 divisions of the textbook LDL^T were most of it.
+__device__ __forceinline__ double dt_inv(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+
+// (H + mu diag(H)) x = -b by LDL^T (H.ldlt().solve(-b), dense_tracking.cpp:127-135): six reciprocals, no division
 __device__ void solve6(const double H21[21], const double b6[6], double mu, double x[6]) {
   double A[6][6];
   int i = 0;
+#pragma unroll
   for (int r = 0; r < 6; ++r)
-    for (int c = 0; c <= r; ++c) { A[r][c] = H21[i]; A[c][r] = H21[i]; ++i; }
+#pragma unroll
+    for (int c = 0; c <= r; ++c) { A[r][c] = H21[i]; ++i; }
+#pragma unroll
   for (int r = 0; r < 6; ++r) A[r][r] += mu * A[r][r];
-  double Lm[6][6], D[6];
+  double Lm[6][6], LD[6][6], Di[6];   // LD = L D (row scaled), Di = 1 / D
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     double d = A[j][j];
-    for (int k = 0; k < j; ++k) d -= Lm[j][k] * Lm[j][k] * D[k];
-    D[j] = d;
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= Lm[j][k] * LD[j][k];
+    Di[j] = d != 0. ? dt_inv(d) : 0.;
+#pragma unroll
     for (int r = j + 1; r < 6; ++r) {
-      double s = A[r][j];
-      for (int k = 0; k < j; ++k) s -= Lm[r][k] * Lm[j][k] * D[k];
-      Lm[r][j] = d != 0. ? s / d : 0.;
+      double sv = A[r][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) sv -= Lm[r][k] * LD[j][k];
+      LD[r][j] = sv;              // = L[r][j] * D[j]
+      Lm[r][j] = sv * Di[j];
     }
   }
   double y[6];
+#pragma unroll
   for (int r = 0; r < 6; ++r) {
-    double s = -b6[r];
-    for (int k = 0; k < r; ++k) s -= Lm[r][k] * y[k];
-    y[r] = s;
+    double sv = -b6[r];
+#pragma unroll
+    for (int k = 0; k < r; ++k) sv -= Lm[r][k] * y[k];
+    y[r] = sv;
   }
+#pragma unroll
   for (int r = 5; r >= 0; --r) {
-    double s = D[r] != 0. ? y[r] / D[r] : 0.;
-    for (int k = r + 1; k < 6; ++k) s -= Lm[k][r] * x[k];
-    x[r] = s;
+    double sv = y[r] * Di[r];
+#pragma unroll
+    for (int k = r + 1; k < 6; ++k) sv -= Lm[k][r] * x[k];
+    x[r] = sv;
   }
 }
 
