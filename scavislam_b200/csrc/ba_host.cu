@@ -736,7 +736,6 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     chunk = chunk < 4 ? 4 : (chunk > 32 ? 32 : chunk);
     if (const char* cs = getenv("SVS_BUILD_CHUNK")) chunk = atoi(cs);   // tuning knob
     if (getenv("SVS_BUILD_V1")) chunk = 0;   // A/B switch: everything through the one-warp-per-landmark kernel
-    const bool whole_waves = getenv("SVS_BUILD_ANY_CHUNK") == nullptr;
     auto same_slots = [&](int la, int lb) {   // internal indices
       const int ka = lm_eptr[la + 1] - lm_eptr[la], kb = lm_eptr[lb + 1] - lm_eptr[lb];
       if (ka != kb || lm_anchor[la] != lm_anchor[lb] || lm_self[la] != lm_self[lb]) return false;
@@ -750,7 +749,6 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     std::vector<int> t_kmax(nt, 1);
     h->pool.parallel_for(nt, [&](int t) {
       auto& tl = t_lm[t]; auto& tc = t_cnt[t];
-      int lim = chunk;   // landmarks the task being filled may hold
       const int l0 = (int)((long long)L * t / nt), l1 = (int)((long long)L * (t + 1) / nt);
       for (int li = l0; li < l1; ++li) {
         const int kk = lm_eptr[li + 1] - lm_eptr[li], KK = lm_sptr[li + 1] - lm_sptr[li];
@@ -760,16 +758,10 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
           t_kmax[t] = std::max(t_kmax[t], KK);
           continue;
         }
-        // a task holds whole waves: the limit is `chunk` rounded down to a multiple of the landmarks one wave of the
-        // kernel takes for this track shape (<= 32 edges, 40 slots, 8 landmarks), so the last wave of a full task is
-        // not a mostly empty one
-        if (!tl.empty() && tl.back() + tc.back() == li && tc.back() < lim && same_slots(tl.back(), li))
+        // (rounding the limit to whole 32-edge waves of the track shape was measured: no difference)
+        if (!tl.empty() && tl.back() + tc.back() == li && tc.back() < chunk && same_slots(tl.back(), li))
           tc.back()++;
-        else {
-          tl.push_back(li); tc.push_back(1);
-          const int nw = std::max(1, std::min(std::min(32 / kk, 40 / KK), 8));
-          lim = whole_waves ? std::max(nw, chunk / nw * nw) : chunk;
-        }
+        else { tl.push_back(li); tc.push_back(1); }
       }
     });
     for (int t = 0; t < nt; ++t) {

@@ -16,6 +16,8 @@
 // translation unit is compiled with -fmad=false so that it matches the CPU oracle bit for bit);
 // sums over pixels are accumulated in double (deviation D-DT1).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -54,6 +56,9 @@ struct DtCtl {
   int trial, stop, iter, phase, done, passes;
   double chi2_level[kMaxLevels];
   int passes_level[kMaxLevels];
+  // SVS_DT_TIMING: cycles per stage summed over the passes of a frame, per level [level][stage]: CTA 0's pose load,
+  // pixel loop + CTA reduction, ticket, wait for the release; the last CTA's partial sums, decision + solve, release
+  unsigned long long prof[kMaxLevels][8];
 };
 
 __device__ __forceinline__ float bilinear(const float* __restrict__ img, int stride, float u, float v, int exact) {
@@ -237,64 +242,143 @@ __device__ __forceinline__ double dt_inv(double a) {
   return fma(y, e, y);
 }
 
-// (H + mu diag(H)) x = -b by LDL^T (H.ldlt().solve(-b), dense_tracking.cpp:127-135): six reciprocals, no division
-__device__ void solve6(const double H21[21], const double b6[6], double mu, double x[6]) {
-  double A[6][6];
-  int i = 0;
+// (H + mu diag(H)) x = -b by LDL^T (H.ldlt().solve(-b), dense_tracking.cpp:127-135): in place on the packed lower
+// triangle (H21[r (r + 1) / 2 + c]), six reciprocals and no division.  H21 / b6 may point to shared or global memory.
+// kGlobal: the system lies in the control block in global memory, written by whichever CTA was last in an earlier pass:
+// read it past L1 (ld.global.cg), which is not coherent between SMs.
+template <bool kGlobal>
+__device__ __forceinline__ void solve6(const double* __restrict__ H21, const double* __restrict__ b6, double mu, double x[6]) {
+  double a[21], D[6], Di[6], bb[6];
 #pragma unroll
-  for (int r = 0; r < 6; ++r)
+  for (int i = 0; i < 21; ++i) a[i] = kGlobal ? __ldcg(H21 + i) : H21[i];
 #pragma unroll
-    for (int c = 0; c <= r; ++c) { A[r][c] = H21[i]; ++i; }
+  for (int i = 0; i < 6; ++i) bb[i] = kGlobal ? __ldcg(b6 + i) : b6[i];
 #pragma unroll
-  for (int r = 0; r < 6; ++r) A[r][r] += mu * A[r][r];
-  double Lm[6][6], LD[6][6], Di[6];   // LD = L D (row scaled), Di = 1 / D
+  for (int r = 0; r < 6; ++r) a[r * (r + 1) / 2 + r] += mu * a[r * (r + 1) / 2 + r];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = A[j][j];
+    double d = a[j * (j + 1) / 2 + j];
 #pragma unroll
-    for (int k = 0; k < j; ++k) d -= Lm[j][k] * LD[j][k];
+    for (int q = 0; q < j; ++q) d -= a[j * (j + 1) / 2 + q] * a[j * (j + 1) / 2 + q] * D[q];
+    D[j] = d;
     Di[j] = d != 0. ? dt_inv(d) : 0.;
 #pragma unroll
     for (int r = j + 1; r < 6; ++r) {
-      double sv = A[r][j];
+      double sv = a[r * (r + 1) / 2 + j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) sv -= Lm[r][k] * LD[j][k];
-      LD[r][j] = sv;              // = L[r][j] * D[j]
-      Lm[r][j] = sv * Di[j];
+      for (int q = 0; q < j; ++q) sv -= a[r * (r + 1) / 2 + q] * a[j * (j + 1) / 2 + q] * D[q];
+      a[r * (r + 1) / 2 + j] = sv * Di[j];   // L[r][j]
     }
   }
   double y[6];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
-    double sv = -b6[r];
+    double sv = -bb[r];
 #pragma unroll
-    for (int k = 0; k < r; ++k) sv -= Lm[r][k] * y[k];
+    for (int q = 0; q < r; ++q) sv -= a[r * (r + 1) / 2 + q] * y[q];
     y[r] = sv;
   }
 #pragma unroll
   for (int r = 5; r >= 0; --r) {
     double sv = y[r] * Di[r];
 #pragma unroll
-    for (int k = r + 1; k < 6; ++k) sv -= Lm[k][r] * x[k];
+    for (int q = r + 1; q < 6; ++q) sv -= a[q * (q + 1) / 2 + r] * x[q];
     x[r] = sv;
   }
 }
 
-__device__ void propose_step(DtCtl* c) {
-  double x[6], dT[7];
-  solve6(c->H, c->b, c->mu, x);
-  svs::se3_exp(x, dT);
-  svs::se3_mul(dT, c->T, c->Teval);
+// The Levenberg decision of one pass and the next trial pose (dense_tracking.cpp:105-178), run by thread 0 of the
+// last CTA to arrive.  A function of its own (not inlined): its 27 + 14 doubles of state and the unrolled 6x6 solve
+// would otherwise share the register allocation of the pixel loop.  Returns true when the level is finished.
+__device__ __noinline__ bool decide_and_propose(DtCtl* c, const double* ssum, const double* Te, int pass, int level) {
+  // The control block lives in global memory (the last CTA is a different one every pass).  What this decision needs
+  // is fetched in ONE batch of independent loads; the block used to be read and written field by field, four or five
+  // dependent L2 round trips per pass.
+  double chi2 = 0, mu = 0, nu = 2, Tacc[7], b_old[6];
+  int trial = 0, iter = 0, passes = 0;
+  if (pass != 0) {
+    chi2 = __ldcg(&c->chi2); mu = __ldcg(&c->mu); nu = __ldcg(&c->nu);
+    trial = __ldcg(&c->trial); iter = __ldcg(&c->iter); passes = __ldcg(&c->passes);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Tacc[k] = __ldcg(&c->T[k]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) b_old[i] = __ldcg(&c->b[i]);
+  }
+  bool finished = false, new_system = false, new_pose = false;
+  int stop = 0;
+  if (pass == 0) {   // chi2 and (H, b) at the incoming pose (Te = ctl->T)
+    passes = 1;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Tacc[k] = Te[k];
+    chi2 = ssum[27];
+    mu = (double)0.01f; nu = 2.; trial = 0; iter = 0;
+    new_system = true;
+    c->phase = 1;
+  } else {
+    passes += 1;
+    const double chin = ssum[27];
+    const double rho = chi2 - chin;
+    if (rho > 0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) Tacc[k] = Te[k];   // the evaluated pose is accepted
+      new_pose = true;
+      chi2 = chin;
+      double nm = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) nm = fmax(nm, fabs(b_old[k]));   // b of the step just taken
+      stop = nm <= 1e-10;   // norm_max(b) <= EPS
+      const double u = 2 * rho - 1;
+      mu *= fmax(1. / 3., 1 - u * u * u);
+      nu = 2.;
+      trial = 0;
+      new_system = true;
+      if (stop) finished = true;
+      else { iter += 1; if (iter >= 15) finished = true; }
+    } else {
+      mu *= nu;
+      nu *= 2.;
+      trial += 1;
+      if (trial == 2) { stop = 1; finished = true; }
+    }
+  }
+  int done = 0;
+  if (finished) {
+    done = 1;
+    c->chi2_level[level] = chi2;
+    c->passes_level[level] = passes;
+  } else {   // (H + mu diag H) x = -b, Teval = exp(x) T; the system of an accepted pass is still in shared memory
+    double x[6], dT[7], Tev[7];
+    if (new_system) solve6<false>(ssum, ssum + 21, mu, x);
+    else solve6<true>(c->H, c->b, mu, x);
+    svs::se3_exp(x, dT);
+    svs::se3_mul(dT, Tacc, Tev);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c->Teval[k] = Tev[k];
+  }
+  // write back what changed (plain stores: nobody reads them before the next rendezvous)
+  c->chi2 = chi2; c->mu = mu; c->nu = nu; c->trial = trial; c->iter = iter; c->passes = passes; c->stop = stop;
+  c->done = done;
+  if (new_pose) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c->T[k] = Tacc[k];
+  }
+  if (new_system) {
+#pragma unroll
+    for (int i = 0; i < 21; ++i) c->H[i] = ssum[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) c->b[i] = ssum[21 + i];
+  }
+  return done != 0;
 }
 
 // The LM loop of DenseTracker::denseTrackingGpu for one level (dense_tracking.cpp:90-178).
 // One grid-wide rendezvous per pass: every CTA publishes its partial sums and takes a ticket; the LAST CTA to
-// arrive sums the partials with all its threads in a fixed order (8 segments x 28 components, independent of
+// arrive sums the partials with all its threads in a fixed order (18 segments x 28 components, independent of
 // which CTA happens to be last), takes the Levenberg decision, writes the next pose and bumps a generation
 // counter the other CTAs spin on (all CTAs are co-resident: cooperative launch).
-constexpr int kSeg = 8;
+constexpr int kSeg = 18;
 __global__ void __launch_bounds__(kThreads, 2)
-k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exact, int level) {
+k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exact, int level, int prof) {
   __shared__ double sred[kThreads / 32][kAcc];
   __shared__ double sseg[kSeg][kAcc];
   __shared__ double ssum[kAcc];
@@ -306,34 +390,45 @@ k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exa
   for (int pass = 0;; ++pass) {
     double Te[7];
     const double* Tsrc = pass == 0 ? ctl->T : ctl->Teval;   // the first pass evaluates the incoming pose
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const bool stamp = prof && threadIdx.x == 0;
+    if (stamp) c0 = clock64();
 #pragma unroll
     for (int k = 0; k < 7; ++k) Te[k] = __ldcg(&Tsrc[k]);
+    if (stamp) { c1 = clock64() + (long long)(Te[0] == 123.456); }   // (behind the loads)
     accumulate_pass(L, Te, exact, true, partial, sred);
+    if (stamp) c2 = clock64();
     if (threadIdx.x == 0) {
       __threadfence();
       sLast = atomicAdd(&sync[0], 1u) == gridDim.x - 1;
     }
     __syncthreads();
+    if (stamp) c3 = clock64();
+    if (stamp && blockIdx.x == 0) {
+      atomicAdd(&ctl->prof[level][0], (unsigned long long)(c1 - c0));
+      atomicAdd(&ctl->prof[level][1], (unsigned long long)(c2 - c1));
+      atomicAdd(&ctl->prof[level][2], (unsigned long long)(c3 - c2));
+    }
     if (sLast) {
       __threadfence();
-      {
-        const int i = threadIdx.x & 31, seg = threadIdx.x >> 5;   // kThreads / 32 == kSeg
-        if (i < kAcc) {
-          // fixed order (b = seg, seg + 8, ...), eight independent loads in flight per round: the loop used to
-          // wait for one L2 round trip per partial (37 in a row for 296 CTAs)
-          double s = 0;
-          for (unsigned b0 = seg; b0 < gridDim.x; b0 += 8 * kSeg) {
-            double v[8];
+      if (threadIdx.x < 14 * kSeg) {
+        // 18 segments x 14 lanes, each lane two components (one 16-byte load per partial), nine loads in flight:
+        // 296 partials are two L2 round trips per lane.  Fixed order (b = seg, seg + 18, ...), independent of which
+        // CTA happens to be the last.
+        const int i2 = threadIdx.x % 14, seg = threadIdx.x / 14;
+        double sx = 0, sy = 0;
+        for (unsigned b0 = seg; b0 < gridDim.x; b0 += 9 * kSeg) {
+          double2 v[9];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const unsigned b = b0 + q * kSeg;
-              v[q] = b < gridDim.x ? __ldcg(&partial[(size_t)b * kAcc + i]) : 0.;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) s += v[q];
+          for (int q = 0; q < 9; ++q) {
+            const unsigned b = b0 + q * kSeg;
+            v[q] = b < gridDim.x ? __ldcg(reinterpret_cast<const double2*>(partial + (size_t)b * kAcc) + i2) : make_double2(0., 0.);
           }
-          sseg[seg][i] = s;
+#pragma unroll
+          for (int q = 0; q < 9; ++q) { sx += v[q].x; sy += v[q].y; }
         }
+        sseg[seg][2 * i2] = sx;
+        sseg[seg][2 * i2 + 1] = sy;
       }
       __syncthreads();
       if (threadIdx.x < kAcc) {
@@ -343,53 +438,24 @@ k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exa
         ssum[threadIdx.x] = s;
       }
       __syncthreads();
+      long long c4 = 0;
+      if (stamp) c4 = clock64();
       if (threadIdx.x == 0) {
         DtCtl* c = ctl;
-        if (pass == 0) {   // chi2 and (H, b) at the incoming pose
-          c->passes = 1;
-          for (int i = 0; i < 21; ++i) c->H[i] = ssum[i];
-          for (int i = 0; i < 6; ++i) c->b[i] = ssum[21 + i];
-          c->chi2 = ssum[27];
-          c->mu = (double)0.01f; c->nu = 2.; c->trial = 0; c->stop = 0; c->iter = 0; c->phase = 1; c->done = 0;
-          propose_step(c);
-        } else {
-          c->passes += 1;
-          const double chin = ssum[27];
-          const double rho = c->chi2 - chin;
-          bool finished = false;
-          if (rho > 0) {
-            for (int k = 0; k < 7; ++k) c->T[k] = c->Teval[k];
-            c->chi2 = chin;
-            double nm = 0;
-            for (int k = 0; k < 6; ++k) nm = fmax(nm, fabs(c->b[k]));
-            c->stop = nm <= 1e-10;   // norm_max(b) <= EPS
-            const double u = 2 * rho - 1;
-            c->mu *= fmax(1. / 3., 1 - u * u * u);
-            c->nu = 2.;
-            c->trial = 0;
-            for (int i = 0; i < 21; ++i) c->H[i] = ssum[i];
-            for (int i = 0; i < 6; ++i) c->b[i] = ssum[21 + i];
-            if (c->stop) finished = true;
-            else { c->iter += 1; if (c->iter >= 15) finished = true; }
-          } else {
-            c->mu *= c->nu;
-            c->nu *= 2.;
-            c->trial += 1;
-            if (c->trial == 2) { c->stop = 1; finished = true; }
-          }
-          if (finished) {
-            c->done = 1;
-            c->chi2_level[level] = c->chi2;
-            c->passes_level[level] = c->passes;
-          } else {
-            propose_step(c);
-          }
-        }
+        const bool level_done = decide_and_propose(c, ssum, Te, pass, level);
+        long long c5 = 0;
+        if (stamp) c5 = clock64();
         sync[0] = 0;
         __threadfence();
         // releases the other CTAs; bit 31 of the word they spin on says "level finished", so nobody needs another
         // L2 round trip for ctl->done (the next launch masks the bit off when it reads its starting generation)
-        *(volatile unsigned*)&sync[1] = ((gen + 1u) & 0x7fffffffu) | (c->done ? 0x80000000u : 0u);
+        *(volatile unsigned*)&sync[1] = ((gen + 1u) & 0x7fffffffu) | (level_done ? 0x80000000u : 0u);
+        if (stamp) {
+          const long long c6 = clock64();
+          atomicAdd(&c->prof[level][4], (unsigned long long)(c4 - c3));
+          atomicAdd(&c->prof[level][5], (unsigned long long)(c5 - c4));
+          atomicAdd(&c->prof[level][6], (unsigned long long)(c6 - c5));
+        }
       }
     }
     if (threadIdx.x == 0) {
@@ -397,6 +463,7 @@ k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exa
       while (((g = *(volatile unsigned*)&sync[1]) & 0x7fffffffu) == gen) {}
       __threadfence();
       sGen = g;
+      if (stamp && blockIdx.x == 0) atomicAdd(&ctl->prof[level][3], (unsigned long long)(clock64() - c3));
     }
     __syncthreads();
     gen = (gen + 1u) & 0x7fffffffu;
@@ -747,7 +814,9 @@ int svs_dt_track(svs_dt* h, double T[7], svs_dt_stats* st) {
     double* part = h->d_partial;
     unsigned* sync = h->d_sync;
     int level = l;
-    void* args[] = {&L, &ctl, &part, &sync, &exact, &level};
+    static const int prof_on = getenv("SVS_DT_TIMING") ? 1 : 0;
+    int prof = prof_on;
+    void* args[] = {&L, &ctl, &part, &sync, &exact, &level, &prof};
     DCK(cudaLaunchCooperativeKernel((void*)k_dt_track_level, dim3(blocks), dim3(kThreads), args, 0, h->stream));
   }
   cudaEventRecord(e1, h->stream);
@@ -755,6 +824,14 @@ int svs_dt_track(svs_dt* h, double T[7], svs_dt_stats* st) {
   DCK(cudaStreamSynchronize(h->stream));
   DCK(cudaGetLastError());
   memcpy(T, h->h_ctl->T, sizeof(double) * 7);
+  if (getenv("SVS_DT_TIMING")) {   // cumulative over the handle's frames (the control block is only zeroed at creation)
+    static const char* names[7] = {"pose load", "pixels+reduce", "ticket", "wait(release)", "last: partial sums", "last: decide+solve", "last: release"};
+    for (int l = h->nlevels - 1; l >= 0; --l) {
+      fprintf(stderr, "svs_dt level %d passes(last frame) %d cycles:", l, h->h_ctl->passes_level[l]);
+      for (int q = 0; q < 7; ++q) fprintf(stderr, " %s=%llu", names[q], h->h_ctl->prof[l][q]);
+      fprintf(stderr, "\n");
+    }
+  }
   if (st) {
     memset(st, 0, sizeof *st);
     cudaEventElapsedTime(&st->ms_total, e0, e1);

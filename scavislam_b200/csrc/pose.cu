@@ -72,7 +72,10 @@ __device__ void pass(const PoseArgs& a, const double R[9], const double t[3], bo
     const double x = R[0] * X0 + R[1] * X1 + R[2] * X2 + t[0];
     const double y = R[3] * X0 + R[4] * X1 + R[5] * X2 + t[1];
     const double z = R[6] * X0 + R[7] * X1 + R[8] * X2 + t[2];
-    // StereoCamera::map_uvu (stereo_camera.cpp:36-44)
+    // StereoCamera::map_uvu (stereo_camera.cpp:36-44).  The divisions and square roots stay IEEE operations in the
+    // reference's order: with reciprocal-multiply arithmetic (measured: the sweep is FP64-issue-bound on its one SM and
+    // these are most of it) the accept/reject sequence of a nearly converged problem no longer matches the oracle's
+    // (tests/test_pose_gpu.py, n = 20) -- parity first.
     double f0 = ob[0] - (a.f * (x / z) + a.px);
     double f1 = ob[1] - (a.f * (y / z) + a.py);
     double f2 = ob[2] - ((x - a.b) / z * a.f + a.px);
@@ -122,6 +125,8 @@ struct Shared {
   int count;
   double R[9], t[3];     // pose under evaluation
   int go;                // 1 = evaluate Teval, 0 = finished
+  // thread 0's state of the LM loop: in shared memory so that it does not occupy 82 registers of every thread of the sweep
+  double A[21], B[6], T[7], Tn[7];
 };
 
 // block-wide reduction of a PassOut into sh.sum / sh.count (fixed order)
@@ -180,7 +185,8 @@ __device__ void solve6(const double* U21, const double* B, double mu, double x[6
 __global__ void __launch_bounds__(kThreads) k_pose_lm(PoseArgs a, PoseCtl* ctl) {
   __shared__ Shared sh;
   // thread-0 state of the LM loop (pose_optimizer.h:142-152, 188-198)
-  double T[7], Tn[7], A[21], B[6], mu = 0, nu = 2, chi2 = 0, max_err = 0;
+  double mu = 0, nu = 2, chi2 = 0, max_err = 0;
+  double* const T = sh.T; double* const Tn = sh.Tn; double* const A = sh.A; double* const B = sh.B;
   int stop = 0, trial = 0, ig = 0, iterations = 0, trials = 0;
   if (threadIdx.x == 0) {
     for (int k = 0; k < 7; ++k) T[k] = ctl->T[k];
