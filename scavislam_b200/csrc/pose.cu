@@ -11,9 +11,11 @@
 // unchanged frame after a rejection, which gives the same numbers.  Sums are FP64, reduced in a fixed
 // tree order (deterministic).  There is no host round trip inside the loop.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "../../include/svs_b200.h"
@@ -59,11 +61,12 @@ struct PassOut {
 };
 
 // one sweep over the observations at pose (R, t)
-__device__ void pass(const PoseArgs& a, const double R[9], const double t[3], bool want_system, PassOut& o) {
+__device__ void pass(const PoseArgs& a, const double R[9], const double t[3], bool want_system, PassOut& o,
+                     int first = threadIdx.x, int stride = kThreads) {
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) o.acc[k] = 0;
   o.max_err = 0; o.norm_max_A = 0; o.count = 0;
-  for (int i = threadIdx.x; i < a.n; i += kThreads) {
+  for (int i = first; i < a.n; i += stride) {
     if (a.valid && *reinterpret_cast<const int*>(a.valid + (size_t)i * a.valid_stride) == 0) continue;
     const int p = a.pid ? a.pid[i] : i;
     const double* X = reinterpret_cast<const double*>(a.xyz + (size_t)p * a.xyz_stride);
@@ -271,6 +274,158 @@ __global__ void __launch_bounds__(kThreads) k_pose_lm(PoseArgs a, PoseCtl* ctl) 
   }
 }
 
+
+// ---------------------------------------------------------------- the same LM loop on a thread-block cluster
+// The sweep is instruction-bound on one SM (ncu: 38 k warp-instructions per pass for 1 800 observations -- five IEEE
+// divisions, two square roots and a 27-term accumulation per observation, kept operation for operation for parity).
+// For more than kClusterMinObs observations the loop therefore runs on a cluster of kCl CTAs, each with its own SM:
+// every CTA sweeps its share and reduces it in shared memory; after a cluster barrier CTA 0 adds the kCl partial
+// results in rank order through distributed shared memory, its thread 0 takes the Levenberg decision (the code of
+// k_pose_lm) and the next pose is written into every CTA's shared memory before the second barrier of the pass.
+constexpr int kCl = 8;
+constexpr int kClThreads = 256;
+constexpr int kClWarps = kClThreads / 32;
+constexpr int kClusterMinObs = 512;
+
+struct ClShared {
+  double part[kClWarps][kAcc + 2];
+  int cnt[kClWarps];
+  double sum[kAcc + 2];   // this CTA's share (read by CTA 0 through DSMEM)
+  int count;
+  double R[9], t[3];      // pose under evaluation (written by CTA 0 into every CTA)
+  int go;
+  double tot[kAcc + 2];   // CTA 0: sums over the cluster
+  int tot_count;
+  double A[21], B[6], T[7], Tn[7];   // CTA 0, thread 0: state of the LM loop
+};
+
+__device__ void reduce_cl(ClShared& sh, PassOut& o) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) {
+    const double s = wsum(o.acc[k]);
+    if (lane == 0) sh.part[w][k] = s;
+  }
+  const double me = wmax(o.max_err), na = wmax(o.norm_max_A);
+  int c = o.count;
+#pragma unroll
+  for (int s = 16; s; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+  if (lane == 0) { sh.part[w][kAcc] = me; sh.part[w][kAcc + 1] = na; sh.cnt[w] = c; }
+  __syncthreads();
+  if (threadIdx.x < kAcc + 2) {
+    double s = 0;
+    if (threadIdx.x < kAcc) for (int q = 0; q < kClWarps; ++q) s += sh.part[q][threadIdx.x];
+    else for (int q = 0; q < kClWarps; ++q) s = fmax(s, sh.part[q][threadIdx.x]);
+    sh.sum[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 64) { int s = 0; for (int q = 0; q < kClWarps; ++q) s += sh.cnt[q]; sh.count = s; }
+}
+
+__global__ void __launch_bounds__(kClThreads) k_pose_lm_cluster(PoseArgs a, PoseCtl* ctl) {
+  namespace cg = cooperative_groups;
+  __shared__ ClShared sh;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), nr = (int)cluster.num_blocks();
+  double mu = 0, nu = 2, chi2 = 0, max_err = 0;
+  int stop = 0, trial = 0, ig = 0, iterations = 0, trials = 0;
+  double* const T = sh.T; double* const Tn = sh.Tn; double* const A = sh.A; double* const B = sh.B;
+  // the pose the first sweep evaluates: every CTA reads it itself
+  if (threadIdx.x == 0) {
+    double T0[7];
+    for (int k = 0; k < 7; ++k) T0[k] = ctl->T[k];
+    svs::quat_to_R(T0, sh.R);
+    sh.t[0] = T0[4]; sh.t[1] = T0[5]; sh.t[2] = T0[6];
+    sh.go = 1;
+    if (rank == 0) for (int k = 0; k < 7; ++k) T[k] = T0[k];
+  }
+  __syncthreads();
+  PassOut o;
+  for (int sweep = 0; sh.go; ++sweep) {
+    double R[9], t[3];
+    for (int k = 0; k < 9; ++k) R[k] = sh.R[k];
+    for (int k = 0; k < 3; ++k) t[k] = sh.t[k];
+    pass(a, R, t, true, o, rank * kClThreads + (int)threadIdx.x, nr * kClThreads);
+    reduce_cl(sh, o);
+    cluster.sync();   // every CTA's share is in its sh.sum / sh.count
+    if (rank == 0) {
+      if (threadIdx.x < kAcc + 2) {   // fixed order: rank 0, 1, ..., nr - 1
+        double s = 0;
+        for (int r = 0; r < nr; ++r) {
+          const double v = cluster.map_shared_rank(sh.sum, r)[threadIdx.x];
+          s = threadIdx.x < kAcc ? s + v : fmax(s, v);
+        }
+        sh.tot[threadIdx.x] = s;
+      }
+      if (threadIdx.x == 64) {
+        int c = 0;
+        for (int r = 0; r < nr; ++r) c += *cluster.map_shared_rank(&sh.count, r);
+        sh.tot_count = c;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int go = 0;
+        if (sweep == 0) {   // pose_optimizer.h:142-152, 188-198
+          for (int k = 0; k < 21; ++k) A[k] = sh.tot[k];
+          for (int k = 0; k < 6; ++k) B[k] = sh.tot[21 + k];
+          chi2 = sh.tot[27]; max_err = sh.tot[kAcc];
+          ctl->initial_chi2 = chi2; ctl->num_obs = sh.tot_count; ctl->nan_error = 0;
+          mu = a.initial_mu == -1 ? a.tau * sh.tot[kAcc + 1] : a.initial_mu;
+          go = (a.num_iter > 0 && sh.tot_count > 0) ? 1 : 0;
+        } else {
+          const double new_chi2 = sh.tot[27];
+          ++trials;
+          bool next_iter = false;
+          if (isnan(new_chi2)) {            // the reference throws (pose_optimizer.h:265-268)
+            ctl->nan_error = 1; stop = 1;
+          } else {
+            const double rho = chi2 - new_chi2;
+            if (rho > 0) {                  // :270-278
+              for (int k = 0; k < 7; ++k) T[k] = Tn[k];
+              chi2 = new_chi2; max_err = sh.tot[kAcc];
+              double nb = 0;
+              for (int k = 0; k < 6; ++k) nb = fmax(nb, fabs(B[k]));
+              stop = nb <= kEps;
+              const double c = 2 * rho - 1;
+              mu *= fmax(1. / 3., 1 - c * c * c);
+              nu = 2.; trial = 0; ++iterations;
+              for (int k = 0; k < 21; ++k) A[k] = sh.tot[k];
+              for (int k = 0; k < 6; ++k) B[k] = sh.tot[21 + k];
+              next_iter = true;
+            } else {                        // :280-293
+              mu *= nu; nu *= 2.; ++trial;
+              if (trial == 5) stop = 1;
+            }
+          }
+          if (next_iter) ++ig;
+          go = (stop || (next_iter && ig >= a.num_iter)) ? 0 : 1;
+        }
+        if (go) {
+          double x[6], dT[7];
+          solve6(A, B, mu, x);
+          svs::se3_exp(x, dT);              // SE3_AbstractPoint::add (transformations.h:408-411)
+          svs::se3_mul(dT, T, Tn);
+          svs::quat_to_R(Tn, sh.R);
+          sh.t[0] = Tn[4]; sh.t[1] = Tn[5]; sh.t[2] = Tn[6];
+        }
+        sh.go = go;
+      }
+      __syncthreads();
+      // the next pose (or the end) goes into every other CTA's shared memory
+      for (int i = threadIdx.x; i < (nr - 1) * 13; i += kClThreads) {
+        const int r = 1 + i / 13, q = i - (r - 1) * 13;
+        if (q < 9) cluster.map_shared_rank(sh.R, r)[q] = sh.R[q];
+        else if (q < 12) cluster.map_shared_rank(sh.t, r)[q - 9] = sh.t[q - 9];
+        else *cluster.map_shared_rank(&sh.go, r) = sh.go;
+      }
+    }
+    cluster.sync();   // the pose of the next sweep is in place; nobody reads a remote sh.sum any more
+  }
+  if (rank == 0 && threadIdx.x == 0) {
+    for (int k = 0; k < 7; ++k) ctl->T[k] = T[k];
+    ctl->chi2 = chi2; ctl->max_err = max_err; ctl->iterations = iterations; ctl->trials = trials;
+  }
+}
+
 }  // namespace
 
 struct svs_pose {
@@ -303,7 +458,22 @@ static int run(svs_pose* h, PoseArgs& a, cudaStream_t producer, const svs_cam* c
   QCK(cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(double) * 7, cudaMemcpyHostToDevice, h->stream));
   (void)producer;
   QCK(cudaEventRecord(h->ev0, h->stream));
-  k_pose_lm<<<1, kThreads, 0, h->stream>>>(a, h->d_ctl);
+  static const bool single_cta = getenv("SVS_POSE_SINGLE_CTA") != nullptr;   // A/B switch
+  if (a.n > kClusterMinObs && !single_cta) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kCl, 1, 1);
+    cfg.blockDim = dim3(kClThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QCK(cudaLaunchKernelEx(&cfg, k_pose_lm_cluster, a, h->d_ctl));
+  } else {
+    k_pose_lm<<<1, kThreads, 0, h->stream>>>(a, h->d_ctl);
+  }
   QCK(cudaGetLastError());
   QCK(cudaEventRecord(h->ev1, h->stream));
   QCK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(PoseCtl), cudaMemcpyDeviceToHost, h->stream));
