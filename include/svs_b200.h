@@ -136,7 +136,10 @@ int svs_optimiseInnerAndOuterWindow(svs_ba *h, int P, double *T_qt, const unsign
  * solve is replicated, back-substitution stays local.  Call order per trial:
  *   svs_ba_trial_build -> all-reduce(S, bp, bc) -> svs_ba_trial_solve -> all-reduce(totals) -> svs_ba_trial_decide */
 /* Pose pairs that must be present in the block pattern of the reduced system although this rank
- * may hold no landmark coupling them (the whole window's pattern); call before svs_ba_set_problem. */
+ * may hold no landmark coupling them (the whole window's pattern); call before svs_ba_set_problem.
+ * A handle with a prescribed pattern adds no pose pairs of its own (its tracks with visibility drop-outs are
+ * not completed with zero-weight edges), so that all handles of the window lay the system out identically;
+ * npairs = 0 takes the prescription back. */
 int svs_ba_set_structure(svs_ba *h, int npairs, const int *pose_i, const int *pose_j);
 /* lm->setUserLambdaInit(lambda); ni = 2 (slam_graph.cpp:338-342) */
 int svs_ba_lm_begin(svs_ba *h, double lambda_init, int max_trials);

@@ -108,6 +108,7 @@ struct svs_ba {
   int C_edges = 0;
   int max_col_blocks = 0, max_col_branch = 0, nbranch = 1, nsep_blk = 0, max_row_blocks = 0;
   std::vector<int> extra_pairs;   // svs_ba_set_structure: pose pairs added to the block pattern
+  bool extra_pairs_from_caller = false;   // set by svs_ba_set_structure (not by the in-library sharded window)
   // one window sharded by landmarks across ranks: NCCL communicator of this handle
   NcclComm comm = nullptr; int comm_rank = 0, comm_size = 1;
   size_t sys_count = 0;            // doubles of the packed S | bp | bc buffer (one all-reduce per trial)
@@ -375,6 +376,17 @@ int choose_branches(int P, const std::vector<std::vector<int>>& adj, std::vector
   return 2;
 }
 
+// Track padding rule (set_problem_impl, 'Track padding'): a track of m >= 2 non-anchor observers lo..hi is completed
+// with zero-weight edges to the np frames of lo..hi it skips (the anchor frame is never one of them) when the completed
+// track has at most 8 slots and np <= max(1, m / 2).  Returns np (0: leave the track as it is).  The sharded window
+// uses the same rule for the block pattern every rank must agree on.
+inline int track_padding(int m, int lo, int hi, int anchor) {
+  if (m < 2) return 0;
+  const int span = hi - lo + 1 - ((anchor > lo && anchor < hi) ? 1 : 0);   // frames lo..hi without the anchor
+  const int np = span - m;
+  return (np > 0 && 1 + span <= 8 && np <= std::max(1, m / 2)) ? np : 0;
+}
+
 int fail(svs_ba* h, int code, const std::string& msg) {
   h->err = msg;
   return code;
@@ -572,10 +584,11 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
     // prefix over (landmark, thread), per-thread scatter.  The index ranges are checked in the counting pass.
     const int nt = (E > 32768 && L > 0) ? nthr : 1;
     auto& cnt = h->w_cnt;
-    cnt.assign((size_t)nt * (L + 1), 0);
+    cnt.resize((size_t)nt * (L + 1));
     std::atomic<int> out_of_range{0};
     h->pool.parallel_for(nt, [&](int t) {
       int* c = cnt.data() + (size_t)t * (L + 1);
+      memset(c, 0, sizeof(int) * (size_t)(L + 1));   // every thread clears its own histogram
       const int e0 = (int)((long long)E * t / nt), e1 = (int)((long long)E * (t + 1) / nt);
       for (int e = e0; e < e1; ++e) {
         const int l = e_point[e];
@@ -584,12 +597,32 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
       }
     });
     if (out_of_range.load()) return fail(h, SVS_ERR_INVALID, "observation edge index out of range");
-    int run = 0;
-    for (int l = 0; l < L; ++l) {
-      eptr[l] = run;
-      for (int t = 0; t < nt; ++t) { int& c = cnt[(size_t)t * (L + 1) + l]; const int n = c; c = run; run += n; }
+    // prefix over (landmark, thread).  Only the prefix over the L landmark totals is serial; the totals and the
+    // per-thread start offsets are computed on the pool over landmark ranges (the flat double loop was nt x L serial
+    // steps and grew with the thread count: measured 0.26 ms of the grouping phase at 8 threads, 0.50 at 24)
+    if (nt == 1) {
+      int run = 0;
+      for (int l = 0; l < L; ++l) { int& c = cnt[l]; const int n = c; eptr[l] = run; c = run; run += n; }
+      eptr[L] = run;
+    } else {
+      h->pool.parallel_for(nt, [&](int r) {
+        const int l0 = (int)((long long)L * r / nt), l1 = (int)((long long)L * (r + 1) / nt);
+        for (int l = l0; l < l1; ++l) {
+          int tot = 0;
+          for (int t = 0; t < nt; ++t) tot += cnt[(size_t)t * (L + 1) + l];
+          eptr[l + 1] = tot;   // totals first, turned into the prefix below
+        }
+      });
+      eptr[0] = 0;
+      for (int l = 0; l < L; ++l) eptr[l + 1] += eptr[l];
+      h->pool.parallel_for(nt, [&](int r) {
+        const int l0 = (int)((long long)L * r / nt), l1 = (int)((long long)L * (r + 1) / nt);
+        for (int l = l0; l < l1; ++l) {
+          int run = eptr[l];
+          for (int t = 0; t < nt; ++t) { int& c = cnt[(size_t)t * (L + 1) + l]; const int n = c; c = run; run += n; }
+        }
+      });
     }
-    eptr[L] = run;
     h->pool.parallel_for(nt, [&](int t) {
       int* c = cnt.data() + (size_t)t * (L + 1);
       const int e0 = (int)((long long)E * t / nt), e1 = (int)((long long)E * (t + 1) / nt);
@@ -608,7 +641,7 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
   // the 200-keyframe window: 9 700 runs of 2 landmarks -> 3 600 runs of 6).
   auto& l_npad = h->w_npad;
   l_npad.assign(L, 0);
-  const bool pad_tracks = getenv("SVS_BUILD_NO_PAD") == nullptr;
+  const bool pad_tracks = getenv("SVS_BUILD_NO_PAD") == nullptr && !h->extra_pairs_from_caller;
   int Kmax = 1;
   int bad = 0;
   const int nchunk = L > 4096 ? 4 * nthr : 1;   // contiguous landmark ranges, handed out dynamically
@@ -644,10 +677,8 @@ static int set_problem_impl(svs_ba* h, int P, const double* T_qt, const unsigned
         if (e_pose[eord[k]] == e_pose[eord[k - 1]]) bad = std::max(bad, 2);
       int K = 1 + (en - b) - nself;
       if (pad_tracks && bad == 0 && nself <= 1 && en - b - nself >= 2) {
-        const int m = en - b - nself, lo = e_pose[eord[b + nself]], hi = e_pose[eord[en - 1]];
-        const int span = hi - lo + 1 - ((anchor > lo && anchor < hi) ? 1 : 0);   // frames lo..hi without the anchor
-        const int np = span - m;
-        if (np > 0 && 1 + span <= 8 && np <= std::max(1, m / 2)) { l_npad[l] = (unsigned char)np; K += np; }
+        const int np = track_padding(en - b - nself, e_pose[eord[b + nself]], e_pose[eord[en - 1]], anchor);
+        if (np > 0) { l_npad[l] = (unsigned char)np; K += np; }
       }
       l_anchor[l] = anchor; l_self[l] = (unsigned char)nself; l_K[l] = K;
       Kmax = std::max(Kmax, K);
@@ -1353,8 +1384,19 @@ int svs_ba_set_problem_sharded(svs_ba* h, int P, const double* T_qt, const unsig
     for (int l = 0; l < L; ++l) {
       if (ptr[l] == ptr[l + 1]) continue;
       ps.clear();
-      ps.push_back(e_anchor[ord[ptr[l]]]);
-      for (int k = ptr[l]; k < ptr[l + 1]; ++k) ps.push_back(e_pose[ord[k]]);
+      const int anchor = e_anchor[ord[ptr[l]]];
+      ps.push_back(anchor);
+      int nself = 0, lo = P, hi = -1;
+      for (int k = ptr[l]; k < ptr[l + 1]; ++k) {
+        const int f = e_pose[ord[k]];
+        ps.push_back(f);
+        if (f == anchor) ++nself;
+        else { lo = std::min(lo, f); hi = std::max(hi, f); }
+      }
+      // the frames the owning rank's set_problem pads this track with (zero-weight edges) are part of the pattern too
+      if (!getenv("SVS_BUILD_NO_PAD") && nself <= 1 && track_padding(ptr[l + 1] - ptr[l] - nself, lo, hi, anchor) > 0)
+        for (int f = lo; f <= hi; ++f)
+          if (f != anchor) ps.push_back(f);
       for (size_t x = 0; x < ps.size(); ++x)
         for (size_t y = x + 1; y < ps.size(); ++y) {
           const int a = std::min(ps[x], ps[y]), b = std::max(ps[x], ps[y]);
@@ -1423,6 +1465,9 @@ int svs_ba_set_structure(svs_ba* h, int npairs, const int* pose_i, const int* po
   if (!h || npairs < 0 || (npairs && (!pose_i || !pose_j))) return SVS_ERR_INVALID;
   h->extra_pairs.clear();
   for (int q = 0; q < npairs; ++q) { h->extra_pairs.push_back(pose_i[q]); h->extra_pairs.push_back(pose_j[q]); }
+  // A caller that prescribes the block pattern (several handles summing their reduced systems element by element)
+  // has derived it from its own edge lists: this handle must not add pose pairs of its own, so its tracks are not padded
+  h->extra_pairs_from_caller = npairs > 0;
   return SVS_OK;
 }
 

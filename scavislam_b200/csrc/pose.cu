@@ -470,7 +470,10 @@ static int run(svs_pose* h, PoseArgs& a, cudaStream_t producer, const svs_cam* c
     attr[0].val.clusterDim.x = kCl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    QCK(cudaLaunchKernelEx(&cfg, k_pose_lm_cluster, a, h->d_ctl));
+    if (cudaLaunchKernelEx(&cfg, k_pose_lm_cluster, a, h->d_ctl) != cudaSuccess) {
+      (void)cudaGetLastError();   // a partition that cannot co-schedule eight CTAs: the one-CTA kernel computes the same
+      k_pose_lm<<<1, kThreads, 0, h->stream>>>(a, h->d_ctl);
+    }
   } else {
     k_pose_lm<<<1, kThreads, 0, h->stream>>>(a, h->d_ctl);
   }

@@ -39,6 +39,16 @@ def main():
     ba.set_problem_sharded(pb)
     it2, st2 = ba.optimize(2)
     assert it2 == 2 and st2["trials_iter"] == st_o["trials_iter"][:2]
+    # tracks with visibility drop-outs: every rank completes ITS tracks with zero-weight edges, so the block pattern all
+    # ranks agree on must contain the pose pairs of every rank's padding (svs_ba_set_problem_sharded derives it from the
+    # whole window with the same rule) -- a mismatch would sum different blocks in the all-reduce
+    pbd = synth.with_dropouts(pb, 0.2, seed=5)
+    ba.set_problem_sharded(pbd)
+    itd, std = ba.optimize(4)
+    p_d, s_d, st_d = po.optimize(pbd, 4)
+    assert itd == st_d["iterations"] and std["trials_iter"] == st_d["trials_iter"]
+    np.testing.assert_allclose(std["chi2_iter"], st_d["chi2_iter"], rtol=1e-7)
+    assert rel(ba.poses(), p_d) < 1e-6 and rel(ba.points_all(), s_d) < 1e-6
     ba.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -40,6 +40,25 @@ def test_sharded_window_equals_whole_window(svs, oracle, nshards):
         h.close()
 
 
+def test_sharded_window_with_track_dropouts(svs, oracle):
+    """Shards with a prescribed block pattern (svs_ba_set_structure) must not pad their tracks (a shard's padding would
+    add pose pairs the other shards' layouts lack); the whole-window handle does pad -- both give the oracle's result."""
+    pb = synth.with_dropouts(synth.make_window(40, 3000, seed=78), 0.2, seed=2)
+    whole = svs.BundleAdjuster()
+    whole.set_problem(pb)
+    it_w, st_w = whole.optimize(4)
+    handles = [svs.BundleAdjuster() for _ in range(3)]
+    sw = sdist.ShardedWindow(handles, pb)
+    it_s, st_s = sw.optimize(4)
+    assert it_s == it_w == 4 and st_s["trials_iter"] == st_w["trials_iter"]
+    np.testing.assert_allclose(st_s["chi2_iter"], st_w["chi2_iter"], rtol=1e-9)
+    assert _rel(sw.poses(), whole.poses()) < 1e-9
+    p_o, s_o, _ = oracle.optimize(pb, 4)
+    assert _rel(sw.poses(), p_o) < 1e-6 and _rel(whole.poses(), p_o) < 1e-6
+    for h in handles + [whole]:
+        h.close()
+
+
 def _nccl_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
