@@ -60,7 +60,10 @@ def shard_landmarks(pb, rank: int, world: int):
 
 def global_pose_pairs(pb):
     """Unordered pose pairs coupled by a landmark track or a constraint: the block pattern of the
-    reduced camera system of the WHOLE window (every rank needs the same one)."""
+    reduced camera system of the WHOLE window (every rank needs the same one).  A handle that is given
+    this pattern (svs_ba_set_structure) does not complete its tracks with zero-weight edges -- a shard's
+    padding would add pairs the other shards' layouts lack; the in-library sharded window
+    (svs_ba_set_problem_sharded) derives the padded pattern itself and keeps the padding."""
     order = np.argsort(pb.e_point, kind="stable")
     ep, ef = pb.e_point[order], pb.e_pose[order]
     anchors = pb.e_anchor[order]

@@ -282,3 +282,43 @@ def test_se3_exp_log_match_the_matrix_exponential(oracle):
         if scale >= 1e-3:
             Lg = np.real(logm(M))
             np.testing.assert_allclose(oracle.se3_log(T)[:3], Lg[:3, 3], atol=1e-9)
+
+
+def test_zero_information_edges_change_nothing(oracle):
+    """The basis of the library's track padding (svs_ba_set_problem completes a track with visibility drop-outs
+    with ZERO-WEIGHT edges to the frames it skips): in the reference's arithmetic an edge with Omega = 0 contributes
+    exactly nothing -- J^T 0 J = 0, J^T 0 e = 0, chi2 += 0 -- so the reduced system, chi2 and the whole Levenberg
+    trajectory of the padded edge list are those of the caller's list."""
+    pb = synth.with_dropouts(synth.make_window(14, 500, seed=51), 0.25, seed=7)
+    ep, ef, ea, eo, ei = [list(getattr(pb, k)) for k in ("e_point", "e_pose", "e_anchor", "e_obs", "e_info")]
+    added = 0
+    for l in range(pb.L):
+        sel = pb.e_point == l
+        if not sel.any():
+            continue
+        a = int(pb.e_anchor[sel][0])
+        obs = sorted(int(f) for f in pb.e_pose[sel] if f != a)
+        if len(obs) < 2:
+            continue
+        for f in range(obs[0], obs[-1] + 1):
+            if f != a and f not in obs:       # a frame the track skips: observation arbitrary, information zero
+                ep.append(l); ef.append(f); ea.append(a)
+                eo.append(np.array([123.0, 45.0, 100.0])); ei.append(np.zeros(3))
+                added += 1
+    assert added > 50
+    pad = pb.copy()
+    pad.e_point = np.asarray(ep, np.int32); pad.e_pose = np.asarray(ef, np.int32); pad.e_anchor = np.asarray(ea, np.int32)
+    pad.e_obs = np.asarray(eo, np.float64).reshape(-1, 3); pad.e_info = np.asarray(ei, np.float64).reshape(-1, 3)
+    pad.E = len(ep)
+    for robust in (True, False):
+        S0, b0, c0 = oracle.reduced_system(pb, robust, 1.0, 50.0)
+        S1, b1, c1 = oracle.reduced_system(pad, robust, 1.0, 50.0)
+        assert c0 == c1 or abs(c0 - c1) <= 1e-14 * abs(c0)
+        np.testing.assert_allclose(S1, S0, rtol=0, atol=1e-12 * np.abs(S0).max())
+        np.testing.assert_allclose(b1, b0, rtol=0, atol=1e-12 * np.abs(b0).max())
+    p0, s0, st0 = oracle.optimize(pb, 5)
+    p1, s1, st1 = oracle.optimize(pad, 5)
+    assert st0["trials_iter"] == st1["trials_iter"]
+    np.testing.assert_allclose(st1["chi2_iter"], st0["chi2_iter"], rtol=1e-12)
+    np.testing.assert_allclose(p1, p0, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s1, s0, rtol=0, atol=1e-11)
