@@ -14,6 +14,7 @@
 //
 // Reference semantics: G2oEdgeProjectPSI2UVU::linearizeOplus (anchored_points.cpp:168-189), g2o
 // BaseMultiEdge::constructQuadraticForm, BlockSolver<6,3>::buildSystem / solve (Schur part).
+#include <algorithm>
 #include <cstdlib>
 
 #include "ba_dev.cuh"
@@ -59,6 +60,9 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks, int prof, int
     return __shfl_sync(0xffffffffu, t, 0);
   };
   const double lambda = ctl->lambda;
+  // (Drawing the next ticket early was measured, profiles/r02_build_spill_prefetch_ab.txt: when a task starts, the
+  //  atomic's round trip is hidden but a reserved task waits for its owner while other warps run dry at the end of
+  //  the list -- 0.105 instead of 0.082 ms on the 200-keyframe window; before the flush: no difference.)
   for (int task = persist ? next_task() : (int)blockIdx.x * kWvWarps + warp; task < d.ntasks;
        task = persist ? next_task() : d.ntasks) {
   double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kWvDoubles;
@@ -219,9 +223,31 @@ k_build_wave(BaDev d, int robust, double delta, int n_task_blocks, int prof, int
       for (int c = 0; c < 3; ++c) Y[c] = b0 * Di[c] + b1 * Di[3 + c] + b2 * Di[6 + c];
     }
     {
-      const size_t s0 = (size_t)s_base + (size_t)w0 * K;
-      for (int c = 0; c < 18; ++c)
-        for (int sg = lane; sg < nslots_w; sg += 32) d.W[(size_t)c * d.nslots + s0 + sg] = sB[18 * sg + c];
+      // (ncu source view, round 2: written as a double loop over (c, sg) with the address formed per element this
+      //  spill was the hottest line of the kernel -- 16 % of the stall samples, 9 % of the instructions.  A wave has at
+      //  most 40 slots: two per lane, one pointer bumped by nslots per component, the 18 values of a slot read with
+      //  16-byte shared-memory loads)
+      const bool v0 = lane < nslots_w, v1 = lane + 32 < nslots_w;
+      const double2* b0 = reinterpret_cast<const double2*>(sB + 18 * lane);
+      const double2* b1 = reinterpret_cast<const double2*>(sB + 18 * (lane + 32));
+      double* w = d.W + (size_t)s_base + (size_t)w0 * K + lane;
+      const size_t ns = (size_t)d.nslots;
+      if (v0) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          const double2 t2 = b0[c];
+          w[(size_t)(2 * c) * ns] = t2.x;
+          w[(size_t)(2 * c + 1) * ns] = t2.y;
+        }
+      }
+      if (v1) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          const double2 t2 = b1[c];
+          w[(size_t)(2 * c) * ns + 32] = t2.x;
+          w[(size_t)(2 * c + 1) * ns + 32] = t2.y;
+        }
+      }
     }
     __syncwarp();
     PBW(3);
