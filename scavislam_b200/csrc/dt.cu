@@ -395,7 +395,9 @@ k_dt_track_level(DtLevel L, DtCtl* ctl, double* partial, unsigned* sync, int exa
     if (stamp) c0 = clock64();
 #pragma unroll
     for (int k = 0; k < 7; ++k) Te[k] = __ldcg(&Tsrc[k]);
-    if (stamp) { c1 = clock64() + (long long)(Te[0] == 123.456); }   // (behind the loads)
+    // (the comparison makes the stamp depend on the first loaded value, i.e. it is taken BEHIND the loads; it adds 0
+    //  for any real pose, whose quaternion components lie in [-1, 1])
+    if (stamp) { c1 = clock64() + (long long)(Te[0] == 123.456); }
     accumulate_pass(L, Te, exact, true, partial, sred);
     if (stamp) c2 = clock64();
     if (threadIdx.x == 0) {
